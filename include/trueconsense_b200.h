@@ -1,0 +1,207 @@
+/*
+ * trueconsense_b200.h — C-ABI of the B200 pileup-and-call hot path.
+ *
+ * This is the drop-in boundary for the path TrueConsense implements in
+ *   TrueConsense/indexing.py:75-154   (BuildIndex: whole-BAM pileup -> count table)
+ *   TrueConsense/Events.py:5-82       (ListInserts / ExtractInserts)
+ *   TrueConsense/Coverage.py:1-34     (coverage column)
+ *   TrueConsense/Sequences.py:119-165 (GetNucleotide / GetDistribution ranking)
+ *   TrueConsense/Ambig.py:102-228     (IsAmbiguous and helpers)
+ *   TrueConsense/Events.py:85-106     (MinorityDel)
+ * The reference has no FFI of its own (it is pure Python on top of pysam/htslib); the
+ * entry points below are what a ctypes binding inside those modules would call
+ * (INTEGRATION.md shows the stubs).  Plain pointers and sizes only; every pointer
+ * argument may be a host pointer (pageable or pinned) or a device pointer — the
+ * library asks the CUDA runtime which (cudaPointerGetAttributes) and stages host
+ * buffers through context-owned device memory.  All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).  Calls that
+ * return results to HOST memory synchronise the stream before returning; calls whose
+ * outputs are device pointers return as soon as the work is enqueued.
+ *
+ * Thread-safety: a tc_ctx_t may be used by one thread at a time; different
+ * contexts are independent.  The reference calls BuildIndex from a pool thread
+ * (TrueConsense/TrueConsense.py:225-226), so every entry point sets the CUDA
+ * device of its context itself.
+ *
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device
+ * tc_ctx_create fails with TC_ERR_NO_DEVICE.
+ */
+#ifndef TRUECONSENSE_B200_H
+#define TRUECONSENSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_ABI_VERSION 1
+
+/* ---- error codes (0 = success, negative = failure) ---- */
+#define TC_OK              0
+#define TC_ERR_CUDA       -1  /* a CUDA runtime call failed; see tc_last_error() */
+#define TC_ERR_ARG        -2  /* bad argument (NULL pointer, negative size, ...) */
+#define TC_ERR_UNSORTED   -3  /* reads are not sorted by position (htslib: "Unsorted input. Pileup aborts") */
+#define TC_ERR_DEPTH_CAP  -4  /* the max_depth cap of the full-file pileup could bind; not emulated in bulk */
+#define TC_ERR_NOMEM      -5
+#define TC_ERR_NO_DEVICE  -6
+#define TC_ERR_RANGE      -7  /* an offset / CIGAR walks outside its buffer */
+#define TC_ERR_CAPACITY   -8  /* caller-provided output buffer too small */
+
+/* ---- count table: int32 counts[TC_NROWS][ref_len], row-major planes ----
+ * Rows 0..6 are the seven columns of the reference's index frame in its own order
+ * (indexing.py:134: coverage, A, T, C, G, X, I); row 7 is padding so one position's
+ * plane stride stays a multiple of 32 bytes. Column j is reference position j+1. */
+enum {
+    TC_ROW_COV = 0, TC_ROW_A = 1, TC_ROW_T = 2, TC_ROW_C = 3, TC_ROW_G = 4,
+    TC_ROW_X = 5, TC_ROW_I = 6, TC_ROW_PAD = 7, TC_NROWS = 8
+};
+
+/* ---- flat read arrays (what the BAM decoder produces; BAM field names) ----
+ * Reads are in file order and must be sorted by `pos` (coordinate-sorted BAM, one contig).
+ * seq4 uses BAM's own packing (high nibble first, codes "=ACMGRSVTWYHKDBN"), but every
+ * read starts on a 32-bit word boundary: read i occupies words seq_off[i] .. seq_off[i+1]-1,
+ * the byte stream inside those words is the BAM byte stream.  QUAL shares the same
+ * offsets: base q of read i is qual[8*seq_off[i] + q].  A read with l_seq == 0 (SEQ '*')
+ * has no words.  cigar uses BAM's encoding (len<<4 | op, ops MIDNSHP=X = 0..8); read i
+ * owns cigar[cigar_off[i] .. cigar_off[i+1]-1]. */
+typedef struct tc_reads {
+    int64_t n_reads;
+    int64_t n_seq_words;        /* total 32-bit words in seq4 (== seq_off[n_reads]) */
+    int64_t n_cigar_ops;        /* total CIGAR ops (== cigar_off[n_reads]) */
+    const int32_t*  pos;        /* [n]   0-based leftmost reference coordinate */
+    const uint16_t* flag;       /* [n]   BAM FLAG */
+    const uint8_t*  mapq;       /* [n]   MAPQ */
+    const int32_t*  l_seq;      /* [n]   query length (0 when SEQ is '*') */
+    const uint32_t* seq_off;    /* [n+1] word offsets into seq4 (and /8 byte offsets into qual) */
+    const uint32_t* cigar_off;  /* [n+1] op offsets into cigar */
+    const uint32_t* seq4;       /* [n_seq_words] */
+    const uint8_t*  qual;       /* [8*n_seq_words] phred bytes; may be NULL when no pass reads QUAL */
+    const uint32_t* cigar;      /* [n_cigar_ops] */
+    /* mate information, only read by the samtools-stepper emulation (tc_extract_inserts);
+     * may be NULL for unpaired data */
+    const uint64_t* qname_hash; /* [n] any hash of QNAME that is equal for both mates */
+    const int32_t*  mpos;       /* [n] PNEXT (0-based, -1 if unavailable) */
+    const int32_t*  isize;      /* [n] TLEN */
+} tc_reads_t;
+
+/* ---- pileup filters: the arguments of pysam's AlignmentFile.pileup() that the
+ * reference passes (indexing.py:100) or leaves at their defaults (Events.py:66) ---- */
+typedef struct tc_pileup_params {
+    uint32_t flag_filter;       /* reads with (flag & flag_filter) != 0 are skipped. BuildIndex: 0x4 (htslib
+                                   always drops UNMAP); ExtractInserts: 0x4|0x100|0x200|0x400 */
+    int32_t  min_mapq;          /* reads with mapq < min_mapq are skipped (both call sites: 0) */
+    int32_t  min_base_quality;  /* entries with qual < this are skipped. BuildIndex: 0; ExtractInserts: 13 */
+    int32_t  ignore_orphans;    /* skip PAIRED && !PROPER_PAIR reads. BuildIndex (nofilter): 0; ExtractInserts: 1 */
+    int64_t  max_depth;         /* BuildIndex: 10000000; ExtractInserts: 8000 */
+    int32_t  kernel;            /* 0 = library's choice; 1 = scatter (smem atomics); 2 = SWAR column kernel */
+    int32_t  reserved;
+} tc_pileup_params_t;
+
+/* ---- per-position call table (struct of arrays, each of length ref_len) ----
+ * Everything Sequences.BuildConsensus (Sequences.py:179-318) reads per position. */
+#define TC_CF_LOWCOV        0x01  /* cov <  mincov           (Sequences.py:191) */
+#define TC_CF_PRIMARY_X     0x02  /* rank-1 letter is 'X'    (Sequences.py:210,277) */
+#define TC_CF_MINORITY_DEL  0x04  /* (X/cov)*100 >= 15       (Events.py:100-106); 0 when cov == 0 */
+#define TC_CF_INS_CANDIDATE 0x08  /* ListInserts test        (Events.py:25-36) */
+#define TC_CF_COV_GT_MINCOV 0x10  /* cov >  mincov (strict)  (Sequences.py:311, ORFs.py:139) */
+#define TC_CF_XRUN_OFF_END  0x20  /* the X-run after this position reaches ref_len: WalkForward
+                                     (Sequences.py:44-52) would raise KeyError(ref_len+1) */
+#define TC_CF_ZERO_COV      0x40  /* cov == 0: MinorityDel here raises ZeroDivisionError (Events.py:102) */
+#define TC_CF_AMBIG         0x80  /* IsAmbiguous(...)[0]     (Ambig.py:179-228) */
+
+typedef struct tc_call_table {
+    uint8_t* call_char;     /* the character the walk appends when it takes the plain branch:
+                               rank-1 != 'X': ambiguity char if include_ambig && ambiguous, else rank-1 letter,
+                                              lower-case when its count < mincov (Sequences.py:269-275);
+                               rank-1 == 'X': rank-2 letter, lower-case when its count < mincov (Sequences.py:283-291) */
+    uint8_t* flags;         /* TC_CF_* */
+    int32_t* xrun;          /* len(WalkForward(index, p)): consecutive positions after p whose rank-1 is 'X' */
+    uint8_t* rank_letter;   /* [4][ref_len]  GetNucleotide(index,p,k) letters for k=1..4 ('A','T','C','G','X') */
+    int32_t* rank_count;    /* [4][ref_len]  ... and their counts */
+    uint8_t* ambig_char;    /* IsAmbiguous(...)[1] as ASCII, 0 when not ambiguous */
+} tc_call_table_t;
+
+typedef struct tc_call_params {
+    int32_t mincov;
+    int32_t include_ambig;      /* IncludeAmbig of BuildConsensus */
+    double  ambig_maxdist;      /* 10  (Ambig.py:156) */
+    double  minority_del_pct;   /* 15  (Events.py:104) */
+    double  insert_pct;         /* 55  (Events.py:36) */
+} tc_call_params_t;
+
+/* ---- result of the ExtractInserts emulation for one candidate position ---- */
+typedef struct tc_insert_call {
+    int32_t pos;            /* 1-based position, the reference's dict key */
+    int32_t n_entries;      /* strings in the column after all filters (0: pysam returns "" -> (None, None)) */
+    int32_t mode_count;     /* multiplicity of the modal upper-cased string */
+    int32_t first_read;     /* index of the read that contributed its first occurrence */
+    int32_t head;           /* ASCII of the modal string's first character (already upper-cased) */
+    int32_t indel;          /* >0 "+n<bases>", <0 "-n" followed by n 'N', 0 no suffix */
+    int64_t bases_off;      /* offset of the n inserted characters in the bases buffer (indel > 0) */
+} tc_insert_call_t;
+
+typedef struct tc_ctx tc_ctx_t;
+
+/* ---- lifecycle ---- */
+int  tc_abi_version(void);
+/* device < 0: current device.  Fails with TC_ERR_NO_DEVICE when no CUDA device is usable. */
+int  tc_ctx_create(int device, tc_ctx_t** out);
+int  tc_ctx_destroy(tc_ctx_t* ctx);
+/* text of the last failure on this context (or of the last failed tc_ctx_create when ctx == NULL) */
+const char* tc_last_error(const tc_ctx_t* ctx);
+/* number of kernel launches this context has issued so far (bench.py's gpu_launches) */
+int64_t tc_launch_count(const tc_ctx_t* ctx);
+
+/* Copy a host read batch into context-owned device memory and fill *dev with device
+ * pointers (valid until the next tc_reads_upload on this context or tc_ctx_destroy).
+ * Arrays that are NULL in *host stay NULL.  Already-device pointers are passed through. */
+int  tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* dev, void* stream);
+
+/* ---- (1) pileup: replaces pysam pileup + parse_query_sequences, indexing.py:100-143 ----
+ * counts: int32[TC_NROWS][ref_len] (host or device), fully overwritten, zero rows for uncovered
+ * positions (indexing.py:147-151).  Reads starting at or beyond ref_len are an error (TC_ERR_RANGE). */
+int  tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len,
+                      const tc_pileup_params_t* params, int32_t* counts, void* stream);
+
+/* ---- (3) depth: the `coverage` column alone (Coverage.py:1-34 reads it), as a difference
+ * array over read spans + inclusive scan.  depth: int32[ref_len].  Only valid for
+ * min_base_quality == 0 (every entry of a span counts); otherwise TC_ERR_ARG. */
+int  tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len,
+              const tc_pileup_params_t* params, int32_t* depth, void* stream);
+
+/* ---- (4) per-position call: Sequences.py:119-165 + Ambig.py + Events.py:25-36,85-106 ----
+ * counts as produced by tc_pileup_counts (or an overridden index).  Any member of *table may be NULL. */
+int  tc_call(tc_ctx_t* ctx, const int32_t* counts, int32_t ref_len,
+             const tc_call_params_t* params, const tc_call_table_t* table, void* stream);
+
+/* IsAmbiguous on n independent columns given already-ranked (letter,count) tuples
+ * (Ambig.py:179): letters uint8[4][n], cnts int32[4][n], cov int32[n] -> out_char uint8[n] (0 = not ambiguous). */
+int  tc_is_ambiguous(tc_ctx_t* ctx, const uint8_t* letters, const int32_t* cnts, const int32_t* cov,
+                     int64_t n, double maxdist, uint8_t* out_char, void* stream);
+
+/* ---- (2) insertions: ExtractInserts, Events.py:47-82, for n_cand 1-based positions ----
+ * For every candidate the column at pos-1 is piled up under `params` (the pysam defaults of
+ * Events.py:66: samtools stepper, min_base_quality 13, max_depth 8000), every entry becomes a
+ * fixed-width key (head char, indel, packed inserted bases), keys are radix-sorted and
+ * run-length encoded, and the most common upper-cased string (ties: first encountered,
+ * collections.Counter.most_common) is returned.  calls: [n_cand]; bases: char buffer of
+ * bases_cap bytes receiving the inserted characters of each modal string. */
+int  tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len,
+                        const int32_t* cand_pos, int32_t n_cand, const tc_pileup_params_t* params,
+                        tc_insert_call_t* calls, uint8_t* bases, int64_t bases_cap, void* stream);
+
+/* Positions (1-based, ascending) with TC_CF_INS_CANDIDATE set; returns their number in *n_out
+ * (cand_pos capacity `cap`; TC_ERR_CAPACITY if more). */
+int  tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_t ref_len,
+                               int32_t* cand_pos, int32_t cap, int32_t* n_out, void* stream);
+
+/* ---- multi-GPU: read-range sharding (ultra-deep single sample) ----
+ * Sum the count tables of all ranks in place.  `comm` is an ncclComm_t created by the caller
+ * (the Python host layer creates it from a unique id exchanged over torch.distributed). */
+int  tc_allreduce_counts(tc_ctx_t* ctx, int32_t* counts_dev, int64_t n_elems, void* comm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUECONSENSE_B200_H */

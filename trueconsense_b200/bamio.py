@@ -1,0 +1,159 @@
+"""BAM <-> flat read arrays (ctypes over libtchost.so, csrc/host/bamio.c).
+
+This is the decode half of what ``pysam.AlignmentFile`` does for
+TrueConsense/indexing.py:96; pysam/htslib are not installed in this image, so
+the repo carries its own BGZF/BAM reader and writer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import build
+from .reads import ReadBatch
+
+
+class TcHostReads(C.Structure):
+    """ctypes mirror of ``tc_hostreads_t`` (include/tc_host.h)."""
+
+    _fields_ = [
+        ("n_reads", C.c_int64), ("n_seq_words", C.c_int64), ("n_cigar_ops", C.c_int64),
+        ("pos", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)), ("mapq", C.POINTER(C.c_uint8)),
+        ("l_seq", C.POINTER(C.c_int32)), ("seq_off", C.POINTER(C.c_uint32)), ("cigar_off", C.POINTER(C.c_uint32)),
+        ("seq4", C.POINTER(C.c_uint32)), ("qual", C.POINTER(C.c_uint8)), ("cigar", C.POINTER(C.c_uint32)),
+        ("qname_hash", C.POINTER(C.c_uint64)), ("mpos", C.POINTER(C.c_int32)), ("isize", C.POINTER(C.c_int32)),
+        ("tid", C.POINTER(C.c_int32)), ("mtid", C.POINTER(C.c_int32)),
+        ("n_ref", C.c_int32), ("ref_len", C.POINTER(C.c_int32)), ("ref_names", C.POINTER(C.c_char)),
+        ("ref_names_len", C.c_int64),
+        ("n_records", C.c_int64), ("n_dropped_unplaced", C.c_int64), ("aligned_bases", C.c_int64),
+        ("sorted", C.c_int32), ("max_ref_span", C.c_int32),
+        ("t_inflate_s", C.c_double), ("t_parse_s", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def host_lib() -> C.CDLL:
+    """Load (building if necessary) libtchost.so."""
+    global _lib
+    if _lib is None:
+        path = build.HOST_LIB
+        if not os.path.exists(path) or os.environ.get("TC_REBUILD"):
+            build.build_host()
+        lib = C.CDLL(path)
+        lib.tc_bam_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(TcHostReads), C.c_char_p, C.c_int]
+        lib.tc_bam_read.restype = C.c_int
+        lib.tc_hostreads_free.argtypes = [C.POINTER(TcHostReads)]
+        lib.tc_hostreads_free.restype = None
+        lib.tc_bam_write.argtypes = [C.c_char_p, C.POINTER(TcHostReads), C.c_char_p, C.c_int32, C.c_int,
+                                     C.c_char_p, C.c_int]
+        lib.tc_bam_write.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _wrap(ptr, n, dtype):
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+
+
+def batch_from_hostreads(hr: TcHostReads, lib: C.CDLL) -> ReadBatch:
+    """Zero-copy numpy views over the C-owned arrays; freed when the batch is collected."""
+    n = int(hr.n_reads)
+    nw = int(hr.n_seq_words)
+    nc = int(hr.n_cigar_ops)
+    names = []
+    if hr.n_ref > 0 and hr.ref_names_len > 0:
+        raw = C.string_at(hr.ref_names, hr.ref_names_len)
+        names = [s.decode() for s in raw.split(b"\0")[: hr.n_ref]]
+    lens = [int(hr.ref_len[i]) for i in range(hr.n_ref)] if hr.n_ref > 0 else []
+    b = ReadBatch(
+        pos=_wrap(hr.pos, n, np.int32), flag=_wrap(hr.flag, n, np.uint16), mapq=_wrap(hr.mapq, n, np.uint8),
+        l_seq=_wrap(hr.l_seq, n, np.int32), seq_off=_wrap(hr.seq_off, n + 1, np.uint32),
+        cigar_off=_wrap(hr.cigar_off, n + 1, np.uint32), seq4=_wrap(hr.seq4, nw, np.uint32),
+        qual=_wrap(hr.qual, 8 * nw, np.uint8), cigar=_wrap(hr.cigar, nc, np.uint32),
+        qname_hash=_wrap(hr.qname_hash, n, np.uint64), mpos=_wrap(hr.mpos, n, np.int32),
+        isize=_wrap(hr.isize, n, np.int32), tid=_wrap(hr.tid, n, np.int32), mtid=_wrap(hr.mtid, n, np.int32),
+        ref_names=names, ref_lens=lens, aligned_bases=int(hr.aligned_bases), max_ref_span=int(hr.max_ref_span),
+        sorted=bool(hr.sorted),
+        info={"n_records": int(hr.n_records), "n_dropped_unplaced": int(hr.n_dropped_unplaced),
+              "t_inflate_s": float(hr.t_inflate_s), "t_parse_s": float(hr.t_parse_s)},
+    )
+    b._owner = hr
+    weakref.finalize(b, lib.tc_hostreads_free, C.pointer(hr))
+    return b
+
+
+def read_bam(path: str, threads: int = 0) -> ReadBatch:
+    """Decode a BAM into flat arrays (all placed records, file order)."""
+    lib = host_lib()
+    hr = TcHostReads()
+    err = C.create_string_buffer(512)
+    rc = lib.tc_bam_read(os.fsencode(path), threads, C.byref(hr), err, len(err))
+    if rc != 0:
+        raise OSError(f"tc_bam_read({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
+    return batch_from_hostreads(hr, lib)
+
+
+def hostreads_struct(batch: ReadBatch) -> TcHostReads:
+    hr = TcHostReads()
+    hr.n_reads = batch.n_reads
+    hr.n_seq_words = int(batch.seq4.shape[0])
+    hr.n_cigar_ops = int(batch.cigar.shape[0])
+
+    def p(a, ct):
+        return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+    hr.pos = p(batch.pos, C.c_int32); hr.flag = p(batch.flag, C.c_uint16); hr.mapq = p(batch.mapq, C.c_uint8)
+    hr.l_seq = p(batch.l_seq, C.c_int32); hr.seq_off = p(batch.seq_off, C.c_uint32)
+    hr.cigar_off = p(batch.cigar_off, C.c_uint32); hr.seq4 = p(batch.seq4, C.c_uint32)
+    hr.qual = p(batch.qual, C.c_uint8); hr.cigar = p(batch.cigar, C.c_uint32)
+    qh = batch.qname_hash if batch.qname_hash is not None else np.arange(batch.n_reads, dtype=np.uint64)
+    hr._keep = qh
+    hr.qname_hash = p(qh, C.c_uint64)
+    hr.mpos = p(batch.mpos, C.c_int32); hr.isize = p(batch.isize, C.c_int32)
+    hr.tid = p(batch.tid, C.c_int32); hr.mtid = p(batch.mtid, C.c_int32)
+    return hr
+
+
+def write_bam(path: str, batch: ReadBatch, ref_name: str = "ref", ref_len: int | None = None, level: int = 1) -> None:
+    """Write a batch as a coordinate-sorted single-contig BAM (read names are ``q<hash>``)."""
+    lib = host_lib()
+    if ref_len is None:
+        ref_len = batch.ref_lens[0]
+    hr = hostreads_struct(batch)
+    err = C.create_string_buffer(512)
+    rc = lib.tc_bam_write(os.fsencode(path), C.byref(hr), ref_name.encode(), int(ref_len), int(level), err, len(err))
+    if rc != 0:
+        raise OSError(f"tc_bam_write({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
+
+
+def read_fasta_lengths(path: str) -> tuple[list[str], list[int]]:
+    """Names and lengths of the records of a FASTA file — all that
+    TrueConsense/indexing.py:97-98 takes from ``pysam.FastaFile`` (``lengths[0]``)."""
+    names: list[str] = []
+    lens: list[int] = []
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith(">"):
+                names.append(line[1:].split()[0] if len(line) > 1 and line[1:].split() else "")
+                lens.append(0)
+            elif names:
+                lens[-1] += len(line.strip())
+    return names, lens
+
+
+def read_fasta(path: str) -> list[tuple[str, str]]:
+    out: list[tuple[str, list[str]]] = []
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith(">"):
+                out.append((line[1:].split()[0] if line[1:].split() else "", []))
+            elif out:
+                out[-1][1].append(line.strip())
+    return [(n, "".join(parts)) for n, parts in out]
