@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import weakref
 
 import numpy as np
 
@@ -56,10 +55,34 @@ def host_lib() -> C.CDLL:
     return _lib
 
 
-def _wrap(ptr, n, dtype):
-    if n <= 0 or not ptr:
+class _Owner:
+    """Frees the C-owned arrays when the last numpy view onto them is gone."""
+
+    def __init__(self, hr: TcHostReads, lib: C.CDLL):
+        self.hr = hr
+        self._free = lib.tc_hostreads_free
+
+    def __del__(self):
+        try:
+            self._free(C.byref(self.hr))
+        except Exception:
+            pass
+
+
+class _CMem:
+    """Array-interface carrier: ``np.asarray(_CMem(...))`` keeps this object — and through it
+    the owner of the memory — alive as the array's base."""
+
+    def __init__(self, addr: int, n: int, dtype, owner: _Owner):
+        self.__array_interface__ = {"data": (addr, False), "shape": (n,), "typestr": np.dtype(dtype).str, "version": 3}
+        self._owner = owner
+
+
+def _wrap(ptr, n, dtype, owner):
+    addr = C.cast(ptr, C.c_void_p).value
+    if n <= 0 or not addr:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+    return np.asarray(_CMem(addr, n, dtype, owner))
 
 
 def batch_from_hostreads(hr: TcHostReads, lib: C.CDLL) -> ReadBatch:
@@ -72,20 +95,20 @@ def batch_from_hostreads(hr: TcHostReads, lib: C.CDLL) -> ReadBatch:
         raw = C.string_at(hr.ref_names, hr.ref_names_len)
         names = [s.decode() for s in raw.split(b"\0")[: hr.n_ref]]
     lens = [int(hr.ref_len[i]) for i in range(hr.n_ref)] if hr.n_ref > 0 else []
+    own = _Owner(hr, lib)
     b = ReadBatch(
-        pos=_wrap(hr.pos, n, np.int32), flag=_wrap(hr.flag, n, np.uint16), mapq=_wrap(hr.mapq, n, np.uint8),
-        l_seq=_wrap(hr.l_seq, n, np.int32), seq_off=_wrap(hr.seq_off, n + 1, np.uint32),
-        cigar_off=_wrap(hr.cigar_off, n + 1, np.uint32), seq4=_wrap(hr.seq4, nw, np.uint32),
-        qual=_wrap(hr.qual, 8 * nw, np.uint8), cigar=_wrap(hr.cigar, nc, np.uint32),
-        qname_hash=_wrap(hr.qname_hash, n, np.uint64), mpos=_wrap(hr.mpos, n, np.int32),
-        isize=_wrap(hr.isize, n, np.int32), tid=_wrap(hr.tid, n, np.int32), mtid=_wrap(hr.mtid, n, np.int32),
+        pos=_wrap(hr.pos, n, np.int32, own), flag=_wrap(hr.flag, n, np.uint16, own), mapq=_wrap(hr.mapq, n, np.uint8, own),
+        l_seq=_wrap(hr.l_seq, n, np.int32, own), seq_off=_wrap(hr.seq_off, n + 1, np.uint32, own),
+        cigar_off=_wrap(hr.cigar_off, n + 1, np.uint32, own), seq4=_wrap(hr.seq4, nw, np.uint32, own),
+        qual=_wrap(hr.qual, 8 * nw, np.uint8, own), cigar=_wrap(hr.cigar, nc, np.uint32, own),
+        qname_hash=_wrap(hr.qname_hash, n, np.uint64, own), mpos=_wrap(hr.mpos, n, np.int32, own),
+        isize=_wrap(hr.isize, n, np.int32, own), tid=_wrap(hr.tid, n, np.int32, own), mtid=_wrap(hr.mtid, n, np.int32, own),
         ref_names=names, ref_lens=lens, aligned_bases=int(hr.aligned_bases), max_ref_span=int(hr.max_ref_span),
         sorted=bool(hr.sorted),
         info={"n_records": int(hr.n_records), "n_dropped_unplaced": int(hr.n_dropped_unplaced),
               "t_inflate_s": float(hr.t_inflate_s), "t_parse_s": float(hr.t_parse_s)},
     )
-    b._owner = hr
-    weakref.finalize(b, lib.tc_hostreads_free, C.pointer(hr))
+    b._owner = own
     return b
 
 
