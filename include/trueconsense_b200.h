@@ -152,6 +152,11 @@ int  tc_ctx_destroy(tc_ctx_t* ctx);
 const char* tc_last_error(const tc_ctx_t* ctx);
 /* number of kernel launches this context has issued so far (bench.py's gpu_launches) */
 int64_t tc_launch_count(const tc_ctx_t* ctx);
+/* Measurement aid (no counterpart in the reference): when enabled, tc_pileup_counts brackets its
+ * dominant kernel (the pileup kernel proper, without memsets / scan / copies) with CUDA events on
+ * the launching stream; tc_last_pileup_kernel_ms returns the duration of the most recent one. */
+int  tc_ctx_set_timing(tc_ctx_t* ctx, int enabled);
+float tc_last_pileup_kernel_ms(tc_ctx_t* ctx);
 
 /* Copy a host read batch into context-owned device memory and fill *dev with device
  * pointers (valid until the next tc_reads_upload on this context or tc_ctx_destroy).

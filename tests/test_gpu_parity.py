@@ -1,0 +1,415 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, via ctypes) against the CPU oracle
+on the same seeded inputs, against the committed golden vectors generated from the reference,
+and through size-independent properties at larger sizes.  Bit-exact everywhere (integer / byte /
+index work; the FP64 threshold tests of the call kernel must reproduce CPython's doubles).
+"""
+import json
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, load_golden_counts, load_golden_json
+
+pytestmark = pytest.mark.gpu
+
+MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
+KERNELS = [1]      # pileup kernel variants built into the library
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from trueconsense_b200 import build, gpu
+
+    build.build_host()
+    if not os.path.exists(build.CUDA_LIB):
+        build.build_cuda()
+    return gpu.Context(0)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import call, pileup
+
+    pileup.build()
+    return pileup, call
+
+
+def _mini_batch(name):
+    from trueconsense_b200 import bamio
+
+    return bamio.read_bam(f"{GOLD}/{name}.bam")
+
+
+# ---------------------------------------------------------------------------- (1) pileup
+@pytest.mark.parametrize("name", MINIS)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pileup_golden_and_oracle(ctx, orc, name, kernel):
+    from trueconsense_b200 import gpu
+
+    pileup, _ = orc
+    b = _mini_batch(name)
+    exp = load_golden_counts(name)
+    L = exp.shape[1]
+    got = ctx.pileup_counts(b, L, gpu.buildindex_params(kernel))
+    assert np.array_equal(got[:7], exp), "GPU count table differs from the reference-generated golden table"
+    assert np.array_equal(got, pileup.pileup_counts(b, L))
+    assert not got[7].any()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pileup_quirk_batch_direct(ctx, orc, kernel):
+    from oracle import fixtures
+    from trueconsense_b200 import gpu
+
+    pileup, _ = orc
+    b = fixtures.quirk_batch()
+    got = ctx.pileup_counts(b, fixtures.QUIRK_REF_LEN, gpu.buildindex_params(kernel))
+    assert np.array_equal(got, pileup.pileup_counts(b, fixtures.QUIRK_REF_LEN))
+
+
+SYNTH_CASES = {
+    "shotgun_indels": dict(n_reads=6000, read_len=120, read_len_jitter=30, indel_rate=0.03, indel_maxlen=3, softclip_rate=0.2,
+                           softclip_max=12, n_rate=0.01, iupac_rate=0.01, refskip_rate=0.05, special_flag_rate=0.05, sub_rate=0.02),
+    "paired": dict(n_reads=8000, read_len=150, paired=True, softclip_rate=0.05, softclip_max=10, special_flag_rate=0.05),
+    "amplicon_deep": dict(n_reads=30000, read_len=400, read_len_jitter=20, n_amplicons=3, amplicon_jitter=2, indel_rate=1 / 30,
+                          softclip_rate=0.05, softclip_max=20, n_rate=0.001),
+    "long_reads": dict(n_reads=400, read_len=3000, read_len_jitter=800, indel_rate=1 / 40, indel_maxlen=2, softclip_rate=0.2,
+                       softclip_max=60),
+    "tiny": dict(n_reads=3, read_len=50),
+    "one_read": dict(n_reads=1, read_len=10),
+}
+
+
+def _synth(case, L=5000, seed=7):
+    from trueconsense_b200 import synth
+
+    ref, feats = synth.make_genome(L, seed, "sars2")
+    a = feats[0]["start"] - 1
+    V = synth.Variant
+    vs = [V(a + 50, synth.VAR_INS, 3, 5, 0.9), V(a + 120, synth.VAR_INS, 7, 6, 0.7), V(a + 200, synth.VAR_DEL, 3, 0, 0.8),
+          V(a + 260, synth.VAR_DEL, 1, 0, 0.2), V(a + 330, synth.VAR_INS, 1, 9, 0.56), V(a + 400, synth.VAR_SUB, 1, 4, 0.5)]
+    p = synth.SynthParams(seed=seed, ref_len=L, variants=vs, **SYNTH_CASES[case])
+    return ref, feats, synth.generate_reads(p, ref)
+
+
+@pytest.mark.parametrize("case", list(SYNTH_CASES))
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pileup_synthetic_vs_oracle(ctx, orc, case, kernel):
+    from trueconsense_b200 import gpu
+
+    pileup, _ = orc
+    ref, _, b = _synth(case)
+    got = ctx.pileup_counts(b, len(ref), gpu.buildindex_params(kernel))
+    exp = pileup.pileup_counts(b, len(ref), threads=4)
+    assert np.array_equal(got, exp)
+    # size-independent properties
+    assert got[0].sum() == b.count_aligned_bases(0x4)
+    assert np.all(got[1:6].sum(axis=0) <= got[0])
+
+
+def test_pileup_empty_and_device_io(ctx):
+    import torch
+
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    empty = ReadBatch.from_records([])
+    got = ctx.pileup_counts(empty, 100)
+    assert got.shape == (8, 100) and not got.any()
+    ref, _, b = _synth("paired")
+    host = ctx.pileup_counts(b, len(ref))
+    dev_reads = ctx.upload(b)
+    out = torch.empty((8, len(ref)), dtype=torch.int32, device="cuda")
+    ctx.pileup_counts(dev_reads, len(ref), out=out)
+    assert np.array_equal(out.cpu().numpy(), host)
+
+
+def test_pileup_min_base_quality(ctx, orc):
+    from trueconsense_b200 import gpu
+
+    pileup, _ = orc
+    ref, _, b = _synth("shotgun_indels")
+    p = gpu.buildindex_params(1)
+    p.min_base_quality = 13
+    got = ctx.pileup_counts(b, len(ref), p)
+    exp = pileup.pileup_counts(b, len(ref), min_base_quality=13)
+    assert np.array_equal(got, exp)
+
+
+def test_pileup_samtools_stepper_filters(ctx, orc):
+    from trueconsense_b200 import gpu
+
+    pileup, _ = orc
+    ref, _, b = _synth("paired")
+    p = gpu.PileupParams(flag_filter=0x704, min_mapq=10, min_base_quality=0, ignore_orphans=1, max_depth=10_000_000, kernel=0)
+    got = ctx.pileup_counts(b, len(ref), p)
+    exp = pileup.pileup_counts(b, len(ref), flag_filter=0x704, min_mapq=10, ignore_orphans=1)
+    assert np.array_equal(got, exp)
+    assert got[0].sum() < b.count_aligned_bases(0x4)
+
+
+def test_pileup_errors(ctx):
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    unsorted = ReadBatch.from_records([dict(pos=50, cigar="10M", seq="A" * 10), dict(pos=10, cigar="10M", seq="A" * 10)])
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(unsorted, 100)
+    assert ei.value.code == -3
+    beyond = ReadBatch.from_records([dict(pos=95, cigar="10M", seq="A" * 10)])
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(beyond, 100)
+    assert ei.value.code == -7
+    ok = ReadBatch.from_records([dict(pos=90, cigar="10M", seq="A" * 10)])
+    p = gpu.buildindex_params()
+    p.max_depth = 2
+    many = ReadBatch.from_records([dict(pos=5, cigar="10M", seq="A" * 10)] * 5)
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(many, 100, p)
+    assert ei.value.code == -4
+    assert ctx.pileup_counts(ok, 100)[0, 90:].tolist() == [1] * 10
+
+
+# ---------------------------------------------------------------------------- (3) depth
+@pytest.mark.parametrize("case", ["shotgun_indels", "paired", "amplicon_deep"])
+def test_depth_equals_coverage_row(ctx, case):
+    ref, _, b = _synth(case)
+    counts = ctx.pileup_counts(b, len(ref))
+    depth = ctx.depth(b, len(ref))
+    assert np.array_equal(depth, counts[0])
+
+
+# ---------------------------------------------------------------------------- (4) call
+def test_call_vs_oracle_random_tables(ctx, orc):
+    from oracle import fixtures
+
+    _, call = orc
+    rng = np.random.default_rng(11)
+    for it in range(40):
+        L = int(rng.integers(1, 400))
+        depth = int(rng.choice([10, 40, 100, 1000]))
+        counts = np.zeros((8, L), np.int64)
+        counts[:] = fixtures.random_counts(rng, L, depth)
+        mincov = int(rng.choice([0, 1, 5, 10, 30]))
+        amb = bool(it & 1)
+        exp = call.call_table(counts, mincov, amb)
+        got = ctx.call(counts.astype(np.int32), L, mincov, amb)
+        for k in ("call_char", "flags", "xrun", "rank_letter", "rank_count", "ambig_char"):
+            assert np.array_equal(getattr(got, k), exp[k]), (k, it)
+
+
+def test_call_long_xruns(ctx, orc):
+    """X-runs crossing the per-thread chunks of the reverse scan, and runs reaching the end."""
+    _, call = orc
+    rng = np.random.default_rng(3)
+    for L in (1, 2, 1023, 1024, 1025, 5000, 30011):
+        counts = np.zeros((8, L), np.int64)
+        counts[0] = 50
+        counts[1] = 50
+        x = rng.random(L) < 0.97
+        if L > 10:
+            x[L // 2] = False
+        counts[1, x] = 0
+        counts[5, x] = 50
+        exp = call.call_table(counts, 10, True)
+        got = ctx.call(counts.astype(np.int32), L, 10, True)
+        assert np.array_equal(got.xrun, exp["xrun"]), L
+        assert np.array_equal(got.flags, exp["flags"]), L
+
+
+def test_is_ambiguous_kat(ctx):
+    kat = load_golden_json("kat.json")["is_ambiguous"]
+    cases = [c for c in kat if c["status"] == "ok"]
+    letters = np.array([[ord(c["ranks"][k][0]) for c in cases] for k in range(4)], dtype=np.uint8)
+    counts = np.array([[c["ranks"][k][1] for c in cases] for k in range(4)], dtype=np.int32)
+    cov = np.array([c["cov"] for c in cases], dtype=np.int32)
+    got = ctx.is_ambiguous(letters, counts, cov)
+    for g, c in zip(got, cases):
+        exp = c["result"]
+        assert (bool(g), chr(g) if g else None) == (exp[0], exp[1]), c
+
+
+def test_ieee_thresholds_on_device(ctx):
+    """(55/100)*100 = 55.00000000000001; integer math gets these wrong."""
+    c = np.zeros((8, 4), np.int32)
+    c[0] = [100, 10, 100, 100]
+    c[1] = [55, 6, 85, 100]          # A
+    c[3] = [45, 5, 0, 0]             # C
+    c[5] = [0, 0, 15, 0]             # X
+    c[6] = [0, 0, 0, 55]             # I
+    got = ctx.call(c, 4, 1, True)
+    assert got.ambig_char[0] == 0 and chr(got.ambig_char[1]) == "M"
+    assert got.flags[2] & 0x04          # 15 % deletions -> minority deletion
+    assert got.flags[3] & 0x08          # (55/100)*100 > 55 -> insertion candidate
+
+
+# ---------------------------------------------------------------------------- (2) insertions
+def _oracle_modal(pileup, b, pos1):
+    cols = pileup.pileup_columns(b, region=(pos1 - 1, pos1), **pileup.EXTRACTINSERTS)
+    if not cols or cols[0][1] == "":
+        return None, 0
+    strings = [s.upper() for s in cols[0][1]]
+    top = next(iter(dict(Counter(strings).most_common())))
+    return top, len(strings)
+
+
+@pytest.mark.parametrize("name", MINIS)
+def test_extract_inserts_golden_batches(ctx, orc, name):
+    pileup, call = orc
+    b = _mini_batch(name)
+    L = load_golden_counts(name).shape[1]
+    rng = np.random.default_rng(1)
+    cands = call.insert_candidates(np.vstack([load_golden_counts(name), np.zeros((1, L), np.int32)]).astype(np.int64), 1)
+    positions = sorted(set(cands[:40]) | set(int(x) for x in rng.integers(1, L + 1, 25)) | {1, L})
+    got = ctx.extract_inserts(b, L, positions)
+    for g in got:
+        exp, n = _oracle_modal(pileup, b, g["pos"])
+        assert g["string"] == exp, g
+        assert g["n_entries"] == n
+
+
+def test_extract_inserts_depth_cap_binds(ctx, orc):
+    """> 8000 reads over the candidate columns: the cap keeps the first 8000 fetched reads plus the
+    first read of every later start coordinate (htslib bam_plp_push)."""
+    pileup, _ = orc
+    ref, _, b = _synth("amplicon_deep")
+    L = len(ref)
+    counts = ctx.pileup_counts(b, L)
+    assert counts[0].max() > 9000
+    table = ctx.call(counts, L, 30, True)
+    cands = ctx.list_insert_candidates(table.flags, L)
+    assert len(cands) >= 2
+    deep = [int(p) for p in np.argsort(counts[0])[-5:] + 1]
+    positions = sorted(set(int(c) for c in cands) | set(deep))
+    got = ctx.extract_inserts(b, L, positions)
+    for g in got:
+        exp, n = _oracle_modal(pileup, b, g["pos"])
+        assert (g["string"], g["n_entries"]) == (exp, n), g
+    assert max(g["n_entries"] for g in got) <= 8000 + 400
+
+
+def test_extract_inserts_ties_and_quality(ctx, orc):
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    S = "ACGTACGTACGTACGTACGT"
+    recs = [
+        dict(pos=0, cigar="5M1I5M", seq="ACGTA" + "T" + "CGTAC"),
+        dict(pos=0, cigar="5M1I5M", seq="ACGTA" + "G" + "CGTAC"),
+        dict(pos=0, cigar="5M1I5M", seq="ACGTA" + "G" + "CGTAC", flag=16),
+        dict(pos=0, cigar="5M1I5M", seq="ACGTA" + "T" + "CGTAC"),
+        dict(pos=0, cigar="5M2D5M", seq=S[:10]),
+        dict(pos=0, cigar="10M", seq=S[:10], qual=5),                    # filtered by min_base_quality 13
+        dict(pos=1, cigar="10M", seq=S[:10], flag=0x400),                # duplicate: dropped by the stepper
+        dict(pos=1, cigar="10M", seq=S[:10], flag=1),                    # orphan
+        dict(pos=2, cigar="3M4N3M", seq=S[:6]),
+        dict(pos=12, cigar="4M", seq="AC=N"),
+    ]
+    b = ReadBatch.from_records(recs)
+    got = ctx.extract_inserts(b, 40, list(range(1, 18)))
+    for g in got:
+        exp, n = _oracle_modal(pileup, b, g["pos"])
+        assert (g["string"], g["n_entries"]) == (exp, n), g
+    assert got[4]["string"] == "A+1T"      # tie between +1T and +1G: first encountered wins
+
+
+# ---------------------------------------------------------------------------- public API vs golden
+@pytest.mark.parametrize("name", MINIS)
+def test_api_buildindex_listinserts_consensus_golden(ctx, name):
+    from trueconsense_b200 import Coverage, Events, Sequences, indexing
+
+    meta = load_golden_json(f"{name}.json")
+    bam, fa, gff = (f"{GOLD}/{name}.{e}" for e in ("bam", "fasta", "gff"))
+    df = indexing.BuildIndex(bam, fa)
+    assert list(df.columns) == ["coverage", "A", "T", "C", "G", "X", "I"]
+    assert df.index[0] == 1 and df.index.name is None and str(df.index.dtype) == "int64"
+    assert all(str(t) == "int64" for t in df.dtypes)
+    exp = load_golden_counts(name)
+    assert np.array_equal(np.stack([df[c].to_numpy() for c in df.columns]), exp)
+    index = df.to_dict("index")
+    handle = indexing.Readbam(bam)
+    has, pos = Events.ListInserts(index, meta["mincov"], handle)
+    assert [has, None if pos is None else {str(k): v for k, v in pos.items()}] == meta["list_inserts"]
+    assert np.array_equal(Coverage.DepthFromBam(handle), exp[0])
+    gdf = indexing.Gffindex(gff).df
+    gdf["seqid"] = name
+    gdict = gdf.to_dict("index")
+    for amb in (True, False):
+        for inc in (True, False):
+            e = meta[f"consensus_amb{int(amb)}_ins{int(inc)}"]
+            if e["status"] == "raise":
+                with pytest.raises(Exception) as ei:
+                    Sequences.BuildConsensus(meta["mincov"], df.to_dict("index"), gdict, amb, handle, inc)
+                assert type(ei.value).__name__ == e["exc"]
+            else:
+                cons, newgff = Sequences.BuildConsensus(meta["mincov"], df.to_dict("index"), gdict, amb, handle, inc)
+                assert cons == e["consensus"]
+                assert {str(k): [v["start"], v["end"]] for k, v in newgff.items()} == e["gff"]
+
+
+def test_walk_cases_golden(ctx, orc):
+    """The GPU call table + host walk against the reference's BuildConsensus on 600 random cases
+    (consensus, corrected GFF, or the exception type)."""
+    from trueconsense_b200 import Sequences
+
+    _, call = orc
+    cases = load_golden_json("walk_cases.json")
+    for c in cases:
+        counts = np.zeros((8, c["L"]), dtype=np.int64)
+        counts[:7] = np.array(c["counts"], dtype=np.int64)
+        gff = {int(k): v for k, v in c["gff"].items()}
+        cols = {int(k): v for k, v in c["columns"].items()}
+        inserts = call.list_inserts(counts, c["mincov"], lambda p: cols.get(p - 1))
+        for inc in (True, False):
+            exp = c[f"ins{int(inc)}"]
+            if exp["status"] == "raise":
+                with pytest.raises(Exception) as ei:
+                    Sequences.consensus_from_inserts(c["mincov"], counts, gff, c["include_ambig"], inserts, inc)
+                assert type(ei.value).__name__ == exp["exc"], c
+            else:
+                cons, newgff = Sequences.consensus_from_inserts(c["mincov"], counts, gff, c["include_ambig"], inserts, inc)
+                assert cons == exp["consensus"]
+                assert {str(k): [v["start"], v["end"]] for k, v in newgff.items()} == exp["gff"]
+
+
+def test_scalar_api_kat(ctx):
+    from trueconsense_b200 import Ambig, Events, Sequences
+
+    kat = load_golden_json("kat.json")
+    for case in kat["ranking"]:
+        got = [list(Sequences.GetNucleotide({1: case["col"]}, 1, k)) for k in range(1, 6)]
+        assert got == case["ranks"]
+    for case in kat["minority_del"]:
+        idx = {1: dict(coverage=case["cov"], A=0, T=0, C=0, G=0, X=case["X"], I=0)}
+        if case["status"] == "raise":
+            with pytest.raises(ZeroDivisionError):
+                Events.MinorityDel(idx, 1)
+        else:
+            assert Events.MinorityDel(idx, 1) == case["result"]
+    assert Ambig.IsAmbiguous(("A", 55), ("C", 45), ("T", 0), ("G", 0), 100) == (False, None)
+    assert Ambig.IsAmbiguous(("A", 6), ("C", 5), ("T", 0), ("G", 0), 10) == (True, "M")
+    assert Ambig.IsAmbiguous(("A", 33), ("C", 33), ("G", 33), ("T", 0), 99) == (True, "V")
+
+
+# ---------------------------------------------------------------------------- larger sizes: properties
+def test_config2_slice_properties(ctx, orc):
+    """BASELINE configs[1] at 2 % (40k ONT reads, 16 M aligned bases): exact against the
+    multi-threaded oracle, plus the invariants that hold at any size."""
+    from trueconsense_b200 import gpu, synth
+
+    pileup, _ = orc
+    w = synth.config(1, scale=0.02)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    g1 = ctx.pileup_counts(b, L, gpu.buildindex_params(1))
+    for k in KERNELS[1:]:
+        assert np.array_equal(g1, ctx.pileup_counts(b, L, gpu.buildindex_params(k)))
+    assert np.array_equal(g1, pileup.pileup_counts(b, L, threads=8))
+    assert g1[0].sum() == b.count_aligned_bases(0x4) == b.aligned_bases
+    assert np.array_equal(ctx.depth(b, L), g1[0])
+    # read-range sharding is additive (what the multi-GPU allreduce relies on)
+    half = b.n_reads // 2
+    parts = ctx.pileup_counts(b.slice(0, half), L).astype(np.int64) + ctx.pileup_counts(b.slice(half, b.n_reads), L)
+    assert np.array_equal(parts, g1)

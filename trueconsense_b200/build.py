@@ -3,9 +3,8 @@
 * ``libtchost.so``  — host C: BGZF/BAM io + synthetic reads (gcc, zlib, OpenMP)
 * ``libtcb200.so``  — the CUDA hot path behind the C-ABI of include/trueconsense_b200.h
                       (nvcc, sm_100a only)
-* ``oracle/_build/liboracle.so`` — the CPU restatement used by tests / bench cpu_baseline only
-
-``python -m trueconsense_b200.build [host|cuda|oracle|all]``
+``python -m trueconsense_b200.build [host|cuda|all]``  (the oracle under oracle/ builds itself:
+``oracle.pileup.build()``; nothing here touches it)
 """
 from __future__ import annotations
 
@@ -21,7 +20,6 @@ INCLUDE = os.path.join(ROOT, "include")
 
 HOST_LIB = os.path.join(PKG, "libtchost.so")
 CUDA_LIB = os.path.join(PKG, "libtcb200.so")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 
 CUDA_ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -77,23 +75,13 @@ def build_cuda(force: bool = False) -> str:
     return CUDA_LIB
 
 
-def build_oracle(force: bool = False) -> str:
-    odir = os.path.join(ROOT, "oracle")
-    srcs = sorted(os.path.join(odir, f) for f in os.listdir(odir) if f.endswith(".c"))
-    os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
-    if force or _newer(ORACLE_LIB, srcs):
-        _run(["gcc", "-O2", "-g", "-fPIC", "-shared", "-fopenmp", "-Wall", "-o", ORACLE_LIB] + srcs + ["-lm"])
-    return ORACLE_LIB
-
-
 def build_all(force: bool = False) -> None:
     build_host(force)
     build_cuda(force)
-    build_oracle(force)
 
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     force = "--force" in sys.argv
-    {"host": build_host, "cuda": build_cuda, "oracle": build_oracle, "all": build_all}[what](force)
+    {"host": build_host, "cuda": build_cuda, "all": build_all}[what](force)
     print("built", what)

@@ -1,0 +1,139 @@
+// tc_common.cuh — context, error handling, staging and small device helpers shared by the
+// kernels behind include/trueconsense_b200.h.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "trueconsense_b200.h"
+
+#define TC_API extern "C" __attribute__((visibility("default")))
+
+// grow-only device buffers owned by a context
+enum tc_slot {
+    SLOT_POS = 0, SLOT_FLAG, SLOT_MAPQ, SLOT_LSEQ, SLOT_SEQOFF, SLOT_CIGOFF, SLOT_SEQ4, SLOT_QUAL, SLOT_CIGAR,
+    SLOT_QHASH, SLOT_MPOS, SLOT_ISIZE,
+    SLOT_COUNTS, SLOT_DIFF, SLOT_STATUS, SLOT_SPAN_END, SLOT_CALL_A, SLOT_CALL_B, SLOT_CALL_C, SLOT_CALL_D,
+    SLOT_CALL_E, SLOT_CALL_F, SLOT_INS_A, SLOT_INS_B, SLOT_INS_C, SLOT_INS_D, SLOT_INS_E, SLOT_INS_F, SLOT_INS_G,
+    SLOT_TMP_A, SLOT_TMP_B, SLOT_TMP_C, SLOT_TILES, SLOT_SEGS, SLOT_COUNT
+};
+
+struct tc_buf { void* p; size_t cap; };
+
+struct tc_ctx {
+    int device;
+    int sm_count;
+    char err[512];
+    int64_t launches;
+    tc_buf bufs[SLOT_COUNT];
+    void* host_status;      // pinned, 256 bytes
+    int timing;             // bracket the pileup kernel with events
+    cudaEvent_t ev0, ev1;
+    int ev_valid;
+};
+
+// device-side status block written by kernels, read back once per call
+struct tc_status {
+    int err;            // first TC_ERR_* raised on the device (0 = none)
+    int max_cov;        // maximum of the coverage row
+    int n_zero_span;    // reads with no reference span
+    int max_span;       // longest reference span
+    unsigned long long aligned; // pileup entries produced (coverage sum) — bookkeeping
+    int reserved[10];
+};
+
+int tc_fail(tc_ctx* ctx, int code, const char* fmt, ...);
+int tc_cuda_fail(tc_ctx* ctx, cudaError_t e, const char* what);
+void* tc_dev_buf(tc_ctx* ctx, int slot, size_t bytes);       // NULL on failure (ctx->err set)
+bool tc_is_device_ptr(const void* p);
+// returns a device pointer for `p` (n bytes): p itself if it already is one, else a staged copy in `slot`
+const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cudaStream_t s, int* rc);
+
+#define TC_CUDA(call)                                                       \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) return tc_cuda_fail(ctx, e__, #call);       \
+    } while (0)
+
+#define TC_LAUNCH_CHECK()                                                   \
+    do {                                                                    \
+        ctx->launches++;                                                    \
+        cudaError_t e__ = cudaGetLastError();                               \
+        if (e__ != cudaSuccess) return tc_cuda_fail(ctx, e__, "kernel launch"); \
+    } while (0)
+
+// device view of a read batch (device pointers only)
+struct dreads {
+    int64_t n;
+    const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const int32_t* l_seq;
+    const uint32_t* seq_off; const uint32_t* cigar_off; const uint32_t* seq4; const uint8_t* qual;
+    const uint32_t* cigar; const uint64_t* qname_hash; const int32_t* mpos; const int32_t* isize;
+};
+
+// which arrays a pass needs on the device
+#define NEED_QUAL  1
+#define NEED_MATE  2
+int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s);
+
+// ---------------------------------------------------------------- device helpers
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+
+__device__ __forceinline__ bool op_consumes_ref(uint32_t op) {
+    // M, D, N, =, X  -> bits 0,2,3,7,8
+    return (0x18Du >> op) & 1u;
+}
+__device__ __forceinline__ bool op_is_match(uint32_t op) { return (0x181u >> op) & 1u; }          // M, =, X
+__device__ __forceinline__ bool op_consumes_query_skip(uint32_t op) { return op == OP_I || op == OP_S; }
+
+// 4-bit base code q of a read whose packed words start at w (BAM byte stream inside the words)
+__device__ __forceinline__ uint32_t seq_code(const uint32_t* __restrict__ w, int q) {
+    uint32_t word = __ldg(w + (q >> 3));
+    uint32_t byte = (word >> (8 * ((q >> 1) & 3))) & 0xffu;
+    return (q & 1) ? (byte & 15u) : (byte >> 4);
+}
+
+// count-table row of a base code: A=1, C=2, G=4, T=8 -> rows A,C,G,T ; anything else -> -1
+__device__ __forceinline__ int code_row(uint32_t code) {
+    // TC_ROW_A=1, TC_ROW_T=2, TC_ROW_C=3, TC_ROW_G=4
+    switch (code) {
+        case 1: return TC_ROW_A;
+        case 2: return TC_ROW_C;
+        case 4: return TC_ROW_G;
+        case 8: return TC_ROW_T;
+        default: return -1;
+    }
+}
+
+// indel reported on the last column of reference-consuming op k (htslib resolve_cigar2's peek)
+__device__ __forceinline__ int peek_indel(const uint32_t* __restrict__ cig, int n, int k) {
+    if (k + 1 >= n) return 0;
+    uint32_t op = cig[k] & 15u;
+    uint32_t c2 = cig[k + 1];
+    uint32_t op2 = c2 & 15u;
+    int indel = 0;
+    if (op2 == OP_D && op != OP_D) {
+        indel = -(int)(c2 >> 4);
+        for (int j = k + 2; j < n; ++j) {
+            uint32_t c = cig[j];
+            if ((c & 15u) == OP_D) indel -= (int)(c >> 4); else break;
+        }
+    } else if (op2 == OP_I) {
+        indel = (int)(c2 >> 4);
+        for (int j = k + 2; j < n; ++j) {
+            uint32_t c = cig[j]; uint32_t o = c & 15u;
+            if (o == OP_I) indel += (int)(c >> 4);
+            else if (o != OP_P) break;
+        }
+    } else if (op2 == OP_P && k + 2 < n) {
+        int l3 = 0;
+        for (int j = k + 2; j < n; ++j) {
+            uint32_t c = cig[j]; uint32_t o = c & 15u;
+            if (o == OP_I) l3 += (int)(c >> 4);
+            else if (op_consumes_ref(o)) break;
+        }
+        if (l3 > 0) indel = l3;
+    }
+    return indel;
+}

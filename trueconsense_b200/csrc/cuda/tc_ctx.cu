@@ -1,0 +1,184 @@
+// tc_ctx.cu — context lifecycle, error text, grow-only device buffers, host<->device staging.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+static char g_create_err[512] = "";
+
+int tc_fail(tc_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int tc_cuda_fail(tc_ctx* ctx, cudaError_t e, const char* what) {
+    return tc_fail(ctx, TC_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+void* tc_dev_buf(tc_ctx* ctx, int slot, size_t bytes) {
+    tc_buf* b = &ctx->bufs[slot];
+    if (bytes == 0) bytes = 16;
+    if (b->cap >= bytes) return b->p;
+    if (b->p) { cudaFree(b->p); b->p = NULL; b->cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;       // a little slack so slowly growing inputs do not realloc every call
+    cap = (cap + 255) & ~(size_t)255;
+    void* p = NULL;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+        tc_fail(ctx, TC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+        cudaGetLastError();
+        return NULL;
+    }
+    b->p = p; b->cap = cap;
+    return p;
+}
+
+bool tc_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cudaStream_t s, int* rc) {
+    *rc = TC_OK;
+    if (!p) return NULL;
+    if (tc_is_device_ptr(p)) return p;
+    void* d = tc_dev_buf(ctx, slot, bytes);
+    if (!d) { *rc = TC_ERR_NOMEM; return NULL; }
+    if (bytes) {
+        cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { *rc = tc_cuda_fail(ctx, e, "cudaMemcpyAsync H2D"); return NULL; }
+    }
+    return d;
+}
+
+int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s) {
+    if (!in) return tc_fail(ctx, TC_ERR_ARG, "reads is NULL");
+    if (in->n_reads < 0 || in->n_seq_words < 0 || in->n_cigar_ops < 0) return tc_fail(ctx, TC_ERR_ARG, "negative sizes in tc_reads_t");
+    if (in->n_reads >= (int64_t)0x7fffffff) return tc_fail(ctx, TC_ERR_ARG, "more than 2^31-1 reads in one batch; shard the input");
+    int64_t n = in->n_reads;
+    memset(out, 0, sizeof(*out));
+    out->n = n;
+    if (n == 0) return TC_OK;
+    if (!in->pos || !in->flag || !in->l_seq || !in->seq_off || !in->cigar_off || (!in->cigar && in->n_cigar_ops) ||
+        (!in->seq4 && in->n_seq_words))
+        return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: a required array is NULL");
+    int rc;
+#define STAGE(field, slot, type, count)                                                              \
+    out->field = (const type*)tc_stage_in(ctx, slot, in->field, sizeof(type) * (size_t)(count), s, &rc); \
+    if (rc) return rc;
+    STAGE(pos, SLOT_POS, int32_t, n)
+    STAGE(flag, SLOT_FLAG, uint16_t, n)
+    STAGE(l_seq, SLOT_LSEQ, int32_t, n)
+    STAGE(seq_off, SLOT_SEQOFF, uint32_t, n + 1)
+    STAGE(cigar_off, SLOT_CIGOFF, uint32_t, n + 1)
+    STAGE(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words)
+    STAGE(cigar, SLOT_CIGAR, uint32_t, in->n_cigar_ops)
+    if (in->mapq) { STAGE(mapq, SLOT_MAPQ, uint8_t, n) }
+    if (need & NEED_QUAL) {
+        if (!in->qual && in->n_seq_words) return tc_fail(ctx, TC_ERR_ARG, "this pass applies a base-quality filter but reads->qual is NULL");
+        STAGE(qual, SLOT_QUAL, uint8_t, 8 * in->n_seq_words)
+    } else if (in->qual && tc_is_device_ptr(in->qual)) {
+        out->qual = in->qual;
+    }
+    if (need & NEED_MATE) {
+        if (in->qname_hash) { STAGE(qname_hash, SLOT_QHASH, uint64_t, n) }
+        if (in->mpos) { STAGE(mpos, SLOT_MPOS, int32_t, n) }
+        if (in->isize) { STAGE(isize, SLOT_ISIZE, int32_t, n) }
+    }
+#undef STAGE
+    return TC_OK;
+}
+
+// ---------------------------------------------------------------- C-ABI: lifecycle
+TC_API int tc_abi_version(void) { return TC_ABI_VERSION; }
+
+TC_API int tc_ctx_create(int device, tc_ctx_t** out) {
+    if (!out) return tc_fail(NULL, TC_ERR_ARG, "out is NULL");
+    *out = NULL;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return tc_fail(NULL, TC_ERR_NO_DEVICE, "no CUDA device available (%s); there is no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return tc_cuda_fail(NULL, e, "cudaGetDevice");
+    }
+    if (device >= n) return tc_fail(NULL, TC_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return tc_cuda_fail(NULL, e, "cudaSetDevice");
+    tc_ctx* ctx = (tc_ctx*)calloc(1, sizeof(tc_ctx));
+    if (!ctx) return tc_fail(NULL, TC_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { free(ctx); return tc_cuda_fail(NULL, e, "cudaGetDeviceProperties"); }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        int rc = tc_fail(NULL, TC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major, prop.minor);
+        free(ctx);
+        return rc;
+    }
+    e = cudaMallocHost(&ctx->host_status, 256);
+    if (e != cudaSuccess) { free(ctx); return tc_cuda_fail(NULL, e, "cudaMallocHost"); }
+    *out = ctx;
+    return TC_OK;
+}
+
+TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
+    if (!ctx) return TC_OK;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < SLOT_COUNT; ++i)
+        if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
+    if (ctx->host_status) cudaFreeHost(ctx->host_status);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    free(ctx);
+    return TC_OK;
+}
+
+TC_API int tc_ctx_set_timing(tc_ctx_t* ctx, int enabled) {
+    if (!ctx) return TC_ERR_ARG;
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (enabled && !ctx->ev0) {
+        TC_CUDA(cudaEventCreate(&ctx->ev0));
+        TC_CUDA(cudaEventCreate(&ctx->ev1));
+    }
+    ctx->timing = enabled ? 1 : 0;
+    ctx->ev_valid = 0;
+    return TC_OK;
+}
+
+TC_API float tc_last_pileup_kernel_ms(tc_ctx_t* ctx) {
+    if (!ctx || !ctx->ev_valid) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+    return ms;
+}
+
+TC_API const char* tc_last_error(const tc_ctx_t* ctx) { return ctx ? ctx->err : g_create_err; }
+
+TC_API int64_t tc_launch_count(const tc_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* dev, void* stream) {
+    if (!ctx || !host || !dev) return tc_fail(ctx, TC_ERR_ARG, "NULL argument");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    dreads d;
+    int need = (host->qual ? NEED_QUAL : 0) | NEED_MATE;
+    int rc = tc_resolve_reads(ctx, host, &d, need, (cudaStream_t)stream);
+    if (rc) return rc;
+    *dev = *host;
+    dev->pos = d.pos; dev->flag = d.flag; dev->mapq = d.mapq; dev->l_seq = d.l_seq; dev->seq_off = d.seq_off;
+    dev->cigar_off = d.cigar_off; dev->seq4 = d.seq4; dev->qual = d.qual; dev->cigar = d.cigar;
+    dev->qname_hash = d.qname_hash; dev->mpos = d.mpos; dev->isize = d.isize;
+    return TC_OK;
+}

@@ -1,0 +1,307 @@
+"""ctypes binding of the C-ABI in include/trueconsense_b200.h (libtcb200.so).
+
+There is no CPU fallback: if the library cannot be loaded or no CUDA device is usable, the
+calls raise.  Arguments may be numpy arrays (host) or torch CUDA tensors (device); the library
+detects which from the pointer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build
+from .reads import ReadBatch, TcReads
+
+TC_NROWS = 8
+ROWS = ("coverage", "A", "T", "C", "G", "X", "I")
+
+CF_LOWCOV, CF_PRIMARY_X, CF_MINORITY_DEL, CF_INS_CANDIDATE = 0x01, 0x02, 0x04, 0x08
+CF_COV_GT_MINCOV, CF_XRUN_OFF_END, CF_ZERO_COV, CF_AMBIG = 0x10, 0x20, 0x40, 0x80
+
+ERR_NAMES = {-1: "TC_ERR_CUDA", -2: "TC_ERR_ARG", -3: "TC_ERR_UNSORTED", -4: "TC_ERR_DEPTH_CAP", -5: "TC_ERR_NOMEM",
+             -6: "TC_ERR_NO_DEVICE", -7: "TC_ERR_RANGE", -8: "TC_ERR_CAPACITY"}
+
+
+class TcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class PileupParams(C.Structure):
+    _fields_ = [("flag_filter", C.c_uint32), ("min_mapq", C.c_int32), ("min_base_quality", C.c_int32),
+                ("ignore_orphans", C.c_int32), ("max_depth", C.c_int64), ("kernel", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CallParams(C.Structure):
+    _fields_ = [("mincov", C.c_int32), ("include_ambig", C.c_int32), ("ambig_maxdist", C.c_double),
+                ("minority_del_pct", C.c_double), ("insert_pct", C.c_double)]
+
+
+class CallTable(C.Structure):
+    _fields_ = [("call_char", C.c_void_p), ("flags", C.c_void_p), ("xrun", C.c_void_p), ("rank_letter", C.c_void_p),
+                ("rank_count", C.c_void_p), ("ambig_char", C.c_void_p)]
+
+
+class InsertCall(C.Structure):
+    _fields_ = [("pos", C.c_int32), ("n_entries", C.c_int32), ("mode_count", C.c_int32), ("first_read", C.c_int32),
+                ("head", C.c_int32), ("indel", C.c_int32), ("bases_off", C.c_int64)]
+
+
+def buildindex_params(kernel: int = 0) -> PileupParams:
+    """pysam arguments of TrueConsense/indexing.py:100: stepper="nofilter" (htslib still drops
+    UNMAP), max_depth=10000000, min_base_quality=0."""
+    return PileupParams(flag_filter=0x4, min_mapq=0, min_base_quality=0, ignore_orphans=0, max_depth=10_000_000,
+                        kernel=kernel, reserved=0)
+
+
+def extractinserts_params() -> PileupParams:
+    """pysam defaults used by TrueConsense/Events.py:66."""
+    return PileupParams(flag_filter=0x4 | 0x100 | 0x200 | 0x400, min_mapq=0, min_base_quality=13, ignore_orphans=1,
+                        max_depth=8000, kernel=0, reserved=0)
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load libtcb200.so (built in-tree by ``trueconsense_b200.build``).  Raises if it is missing:
+    there is nothing to fall back to."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            path = build.CUDA_LIB
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"{path} is missing — the CUDA extension is the only implementation of the hot path. "
+                    "Build it with `python -m trueconsense_b200.build cuda` (needs nvcc).")
+            l = C.CDLL(path)
+            vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+            l.tc_abi_version.restype = C.c_int
+            l.tc_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+            l.tc_ctx_destroy.argtypes = [vp]
+            l.tc_last_error.argtypes = [vp]
+            l.tc_last_error.restype = C.c_char_p
+            l.tc_launch_count.argtypes = [vp]
+            l.tc_launch_count.restype = i64
+            l.tc_ctx_set_timing.argtypes = [vp, C.c_int]
+            l.tc_ctx_set_timing.restype = C.c_int
+            l.tc_last_pileup_kernel_ms.argtypes = [vp]
+            l.tc_last_pileup_kernel_ms.restype = C.c_float
+            l.tc_reads_upload.argtypes = [vp, C.POINTER(TcReads), C.POINTER(TcReads), vp]
+            l.tc_pileup_counts.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), vp, vp]
+            l.tc_depth.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), vp, vp]
+            l.tc_call.argtypes = [vp, vp, i32, C.POINTER(CallParams), C.POINTER(CallTable), vp]
+            l.tc_is_ambiguous.argtypes = [vp, vp, vp, vp, i64, C.c_double, vp, vp]
+            l.tc_extract_inserts.argtypes = [vp, C.POINTER(TcReads), i32, vp, i32, C.POINTER(PileupParams),
+                                             C.POINTER(InsertCall), vp, i64, vp]
+            l.tc_list_insert_candidates.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32), vp]
+            l.tc_allreduce_counts.argtypes = [vp, vp, i64, vp, vp]
+            for name in ("tc_ctx_create", "tc_ctx_destroy", "tc_reads_upload", "tc_pileup_counts", "tc_depth", "tc_call",
+                         "tc_is_ambiguous", "tc_extract_inserts", "tc_list_insert_candidates", "tc_allreduce_counts"):
+                getattr(l, name).restype = C.c_int
+            _lib = l
+    return _lib
+
+
+def _ptr(x):
+    """Raw pointer of a numpy array or a torch tensor (None passes through)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr()
+    if isinstance(x, int):
+        return x
+    raise TypeError(type(x))
+
+
+@dataclass
+class CallResult:
+    call_char: np.ndarray
+    flags: np.ndarray
+    xrun: np.ndarray
+    rank_letter: np.ndarray
+    rank_count: np.ndarray
+    ambig_char: np.ndarray
+
+
+class DeviceReads:
+    """A read batch resident in context-owned device memory (see tc_reads_upload)."""
+
+    def __init__(self, struct: TcReads, batch: ReadBatch):
+        self.struct = struct
+        self.n_reads = batch.n_reads
+        self.host = batch
+
+
+class Context:
+    """One ``tc_ctx_t``: a device, its workspace buffers and a launch counter."""
+
+    def __init__(self, device: int = -1):
+        self._lib = lib()
+        h = C.c_void_p()
+        rc = self._lib.tc_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise TcError(rc, self._lib.tc_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise TcError(rc, self._lib.tc_last_error(self._h).decode())
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.tc_launch_count(self._h))
+
+    def set_timing(self, enabled: bool) -> None:
+        self._check(self._lib.tc_ctx_set_timing(self._h, int(enabled)))
+
+    def last_pileup_kernel_ms(self) -> float:
+        """CUDA-event duration of the dominant kernel of the last pileup_counts call (timing on)."""
+        return float(self._lib.tc_last_pileup_kernel_ms(self._h))
+
+    # ------------------------------------------------------------------ reads
+    @staticmethod
+    def _reads_struct(reads) -> TcReads:
+        if isinstance(reads, DeviceReads):
+            return reads.struct
+        if isinstance(reads, ReadBatch):
+            return reads.c_struct()
+        if isinstance(reads, TcReads):
+            return reads
+        raise TypeError(type(reads))
+
+    def upload(self, batch: ReadBatch, stream: int = 0) -> DeviceReads:
+        dev = TcReads()
+        host = batch.c_struct()
+        self._check(self._lib.tc_reads_upload(self._h, C.byref(host), C.byref(dev), stream))
+        return DeviceReads(dev, batch)
+
+    # ------------------------------------------------------------------ (1) pileup
+    def pileup_counts(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):
+        """int32[8][ref_len] count table (rows coverage,A,T,C,G,X,I,pad).  ``out`` may be a numpy
+        array or a torch CUDA int32 tensor; default: a new numpy array."""
+        params = params or buildindex_params()
+        if out is None:
+            out = np.empty((TC_NROWS, ref_len), dtype=np.int32)
+        rs = self._reads_struct(reads)
+        self._check(self._lib.tc_pileup_counts(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), stream))
+        return out
+
+    # ------------------------------------------------------------------ (3) depth
+    def depth(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):
+        params = params or buildindex_params()
+        if out is None:
+            out = np.empty(ref_len, dtype=np.int32)
+        rs = self._reads_struct(reads)
+        self._check(self._lib.tc_depth(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), stream))
+        return out
+
+    # ------------------------------------------------------------------ (4) call
+    def call(self, counts, ref_len: int, mincov: int, include_ambig: bool, stream: int = 0, maxdist: float = 10.0,
+             minority_del_pct: float = 15.0, insert_pct: float = 55.0) -> CallResult:
+        L = int(ref_len)
+        res = CallResult(np.empty(L, np.uint8), np.empty(L, np.uint8), np.empty(L, np.int32), np.empty((4, L), np.uint8),
+                         np.empty((4, L), np.int32), np.empty(L, np.uint8))
+        t = CallTable(_ptr(res.call_char), _ptr(res.flags), _ptr(res.xrun), _ptr(res.rank_letter), _ptr(res.rank_count),
+                      _ptr(res.ambig_char))
+        p = CallParams(int(mincov), int(bool(include_ambig)), maxdist, minority_del_pct, insert_pct)
+        if isinstance(counts, np.ndarray):
+            counts = np.ascontiguousarray(counts, dtype=np.int32)
+            if counts.shape != (TC_NROWS, L):
+                raise ValueError(f"counts must be [{TC_NROWS}][{L}]")
+        self._check(self._lib.tc_call(self._h, _ptr(counts), L, C.byref(p), C.byref(t), stream))
+        return res
+
+    def call_device(self, counts, ref_len: int, mincov: int, include_ambig: bool, table: CallTable, stream: int = 0,
+                    maxdist: float = 10.0, minority_del_pct: float = 15.0, insert_pct: float = 55.0) -> None:
+        """tc_call with caller-provided (device) output pointers; asynchronous."""
+        p = CallParams(int(mincov), int(bool(include_ambig)), maxdist, minority_del_pct, insert_pct)
+        self._check(self._lib.tc_call(self._h, _ptr(counts), int(ref_len), C.byref(p), C.byref(table), stream))
+
+    def is_ambiguous(self, letters: np.ndarray, cnts: np.ndarray, cov: np.ndarray, maxdist: float = 10.0) -> np.ndarray:
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        cnts = np.ascontiguousarray(cnts, dtype=np.int32)
+        cov = np.ascontiguousarray(cov, dtype=np.int32)
+        n = cov.shape[0]
+        out = np.zeros(n, np.uint8)
+        self._check(self._lib.tc_is_ambiguous(self._h, _ptr(letters), _ptr(cnts), _ptr(cov), n, maxdist, _ptr(out), 0))
+        return out
+
+    # ------------------------------------------------------------------ (2) insertions
+    def list_insert_candidates(self, flags, ref_len: int, cap: int | None = None) -> np.ndarray:
+        cap = int(ref_len) if cap is None else cap
+        out = np.empty(max(cap, 1), np.int32)
+        n = C.c_int32(0)
+        self._check(self._lib.tc_list_insert_candidates(self._h, _ptr(flags), int(ref_len), _ptr(out), cap, C.byref(n), 0))
+        return out[: n.value].copy()
+
+    def extract_inserts(self, reads, ref_len: int, positions, params: PileupParams | None = None):
+        """ExtractInserts for the given 1-based positions.  Returns a list of dicts with the modal
+        upper-cased string of each column (``None`` when pysam would have returned ``""``)."""
+        params = params or extractinserts_params()
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        n = int(pos.shape[0])
+        if n == 0:
+            return []
+        calls = (InsertCall * n)()
+        cap = 1 << 16
+        rs = self._reads_struct(reads)
+        while True:
+            bases = np.zeros(cap, np.uint8)
+            rc = self._lib.tc_extract_inserts(self._h, C.byref(rs), int(ref_len), _ptr(pos), n, C.byref(params), calls,
+                                              _ptr(bases), cap, 0)
+            if rc == -8 and cap < (1 << 30):
+                cap *= 16
+                continue
+            self._check(rc)
+            break
+        out = []
+        for c in calls:
+            if c.n_entries == 0:
+                out.append({"pos": c.pos, "n_entries": 0, "string": None, "mode_count": 0, "first_read": -1})
+                continue
+            s = chr(c.head)
+            if c.indel > 0:
+                s += f"+{c.indel}" + bytes(bases[c.bases_off:c.bases_off + c.indel]).decode("ascii")
+            elif c.indel < 0:
+                s += f"-{-c.indel}" + "N" * (-c.indel)
+            out.append({"pos": c.pos, "n_entries": c.n_entries, "string": s, "mode_count": c.mode_count,
+                        "first_read": c.first_read})
+        return out
+
+
+_default_ctx: dict[int, Context] = {}
+_ctx_lock = threading.Lock()
+
+
+def default_context(device: int = -1) -> Context:
+    """A lazily created per-device context shared by the module-level API (BuildIndex & co)."""
+    with _ctx_lock:
+        c = _default_ctx.get(device)
+        if c is None:
+            c = Context(device)
+            _default_ctx[device] = c
+        return c

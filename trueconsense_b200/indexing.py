@@ -1,0 +1,158 @@
+"""Pileup index building with the reference's API (TrueConsense/indexing.py).
+
+``BuildIndex(bamfile, ref)`` returns the same DataFrame (seven int64 columns
+``coverage,A,T,C,G,X,I``, int64 index 1..len(ref[0]), ``index.name is None``) the reference
+builds from a pysam pileup plus a per-string Python classifier (indexing.py:75-154).  Here the
+BAM is decoded into flat arrays on the host (csrc/host/bamio.c) and the whole pileup is one pass
+of the CUDA kernels behind ``tc_pileup_counts``.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import pandas as pd
+
+from . import bamio, gpu
+from .reads import ReadBatch
+
+COLUMNS = ["coverage", "A", "T", "C", "G", "X", "I"]
+
+
+class BamHandle:
+    """What ``Readbam`` returns: the decoded reads of a BAM plus the attributes of
+    ``pysam.AlignmentFile`` the reference touches (``references``; Events.py:63)."""
+
+    def __init__(self, filename: str, reads: ReadBatch | None = None):
+        self.filename = filename
+        self._reads = reads
+        self._dev = None
+        self._lock = threading.Lock()
+        self._insert_cache: dict = {}
+
+    @property
+    def reads(self) -> ReadBatch:
+        with self._lock:
+            if self._reads is None:
+                self._reads = bamio.read_bam(self.filename)
+            return self._reads
+
+    @property
+    def references(self):
+        return tuple(self.reads.ref_names)
+
+    @property
+    def lengths(self):
+        return tuple(self.reads.ref_lens)
+
+    @property
+    def ref_len(self) -> int:
+        return int(self.reads.ref_lens[0])
+
+    def contig0(self) -> ReadBatch:
+        """Reads placed on the first reference (the only one the reference implementation is
+        meaningful for: indexing.py:98,139 and Events.py:63 use lengths[0] / references[0])."""
+        b = self.reads
+        if b.tid is not None and b.n_reads and np.any(b.tid != 0):
+            raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference "
+                             "(its DataFrame index would hold duplicate positions)")
+        return b
+
+    def device_reads(self):
+        """Upload once per handle; later passes (ExtractInserts) reuse the device copy."""
+        ctx = gpu.default_context()
+        with self._lock:
+            if self._dev is None or self._dev[0] is not ctx:
+                self._dev = (ctx, ctx.upload(self.contig0_nolock()))
+            return self._dev[1]
+
+    def contig0_nolock(self) -> ReadBatch:
+        if self._reads is None:
+            self._reads = bamio.read_bam(self.filename)
+        b = self._reads
+        if b.tid is not None and b.n_reads and np.any(b.tid != 0):
+            raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference")
+        return b
+
+    def pileup(self, *args, **kwargs):
+        raise NotImplementedError("column iteration is not part of this implementation; "
+                                  "use Events.ExtractInserts / indexing.BuildIndex")
+
+    def close(self):
+        pass
+
+
+def Readbam(f):
+    """indexing.py:6-19."""
+    return BamHandle(f)
+
+
+class _GffHeader:
+    def __init__(self, raw_text: str):
+        self.raw_text = raw_text
+
+
+class GffIndex:
+    """Stand-in for AminoExtract's GFFDataFrame (not installed here): ``.df`` with the nine GFF3
+    columns (start/end int64) and ``.header.raw_text`` — all the reference reads
+    (TrueConsense.py:238-241, Outputs.py:66)."""
+
+    GFF_COLUMNS = ["seqid", "source", "type", "start", "end", "score", "strand", "phase", "attributes"]
+
+    def __init__(self, file: str):
+        header, rows = [], []
+        with open(file) as fh:
+            for line in fh:
+                if line.startswith("#"):
+                    if not rows:
+                        header.append(line)
+                    continue
+                if not line.strip():
+                    continue
+                f = line.rstrip("\n").split("\t")
+                f += [""] * (9 - len(f))
+                rows.append(f[:9])
+        self.header = _GffHeader("".join(header))
+        df = pd.DataFrame(rows, columns=self.GFF_COLUMNS)
+        df["start"] = df["start"].astype("int64")
+        df["end"] = df["end"].astype("int64")
+        self.df = df
+
+
+def Gffindex(file: str) -> GffIndex:
+    """indexing.py:22-36."""
+    return GffIndex(file)
+
+
+def read_override_index(f):
+    """indexing.py:39-52."""
+    return pd.read_csv(f, sep=",", compression="gzip", index_col=0)
+
+
+def Override_index_positions(index, override_data):
+    """indexing.py:55-72."""
+    index.loc[override_data.index, :] = override_data[:]
+    return index
+
+
+def frame_from_counts(counts: np.ndarray) -> pd.DataFrame:
+    """int32[8][L] count table -> the reference's index frame."""
+    L = counts.shape[1]
+    df = pd.DataFrame({c: counts[r].astype(np.int64) for r, c in enumerate(COLUMNS)},
+                      index=pd.Index(np.arange(1, L + 1, dtype=np.int64)))
+    df.index.name = None
+    return df
+
+
+def BuildIndex(bamfile, ref):
+    """indexing.py:75-154."""
+    handle = bamfile if isinstance(bamfile, BamHandle) else BamHandle(bamfile)
+    _, lens = bamio.read_fasta_lengths(ref)
+    if not lens:
+        raise ValueError(f"no sequences in {ref}")
+    ref_length = int(lens[0])
+    reads = handle.contig0()
+    if not reads.sorted:
+        raise ValueError("Unsorted input. Pileup aborts")
+    counts = gpu.default_context().pileup_counts(reads, ref_length)
+    return frame_from_counts(counts)
