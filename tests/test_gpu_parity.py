@@ -15,7 +15,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 pytestmark = pytest.mark.gpu
 
 MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
-KERNELS = [1]      # pileup kernel variants built into the library
+KERNELS = [1, 2]      # pileup kernel variants: 1 scatter (smem atomics), 2 SWAR column kernel
 
 
 @pytest.fixture(scope="module")

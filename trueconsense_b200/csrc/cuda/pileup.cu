@@ -217,12 +217,16 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality;
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
     const bool per_entry = p->min_base_quality > 0;
+    int variant = p->kernel;
+    if (variant == 0) variant = (!per_entry && tc_pileup_swar_supported(a)) ? 2 : 1;
+    if (variant == 2 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernel has no base-quality filter; use kernel=1");
+    if (variant == 2 && !tc_pileup_swar_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernel needs 16-byte aligned seq4 / cigar arrays; use kernel=1");
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
-        int variant = p->kernel;
-        if (variant == 0) variant = 1;
-        if (variant == 2 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernel has no base-quality filter; use kernel=1");
         if (variant == 2) {
+            // coverage ends, span statistics and the sortedness / range checks: one thread per read
+            depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
+            TC_LAUNCH_CHECK();
             rc = tc_pileup_swar_launch(ctx, a, s);
             if (rc) return rc;
         } else {
@@ -248,6 +252,14 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     if (!out_dev) TC_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, cudaMemcpyDeviceToHost, s));
     rc = fetch_status(ctx, d_status, &st, s);
     if (rc) return rc;
+    if (st.err == TC_ERR_CAPACITY && variant == 2 && p->kernel == 0) {
+        // a read larger than the SWAR kernel's staging buffers: the scatter kernel has no such limit
+        tc_pileup_params_t q = *p;
+        q.kernel = 1;
+        return tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
+    }
+    if (st.err == TC_ERR_CAPACITY)
+        return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the SWAR kernel's staging buffers; use kernel=1 (or 0)");
     if (per_entry) {
         // coverage was counted entry by entry, so max_cov is not the live depth; fall back to the
         // trivial bound (every read live at once)
