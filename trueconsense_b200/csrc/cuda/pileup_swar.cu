@@ -278,46 +278,57 @@ __global__ void __launch_bounds__(T, 2) swar_main_kernel(pileup_args a, swar_wor
             if (y > lq && nd > 0) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); nd = 0; }   // CIGAR longer than SEQ: scatter kernel
             __syncwarp();
 
-            // ---- expand: one row word (8 columns) per iteration, warp-uniform trip count; every row word of
-            // the read is written exactly once (rows were zeroed by the previous column sum)
+            // ---- expand, pass A: one row word (8 columns) per iteration, warp-uniform trip count.  Each word is
+            // written under the shift in force at its first column; shift changes inside a word are ignored here.
+            const int o0 = b_first >> 3;
+            const uint32_t* sq = seq_s + SEQ_PAD;
+            if (act) sq += (a.r.seq_off[r] - sbase_al);
+            uint32_t* row = rows + tid * RS + o0;
             {
-                const int o0 = b_first >> 3;
                 const int words = nd > 0 ? ((seg_end - 1) >> 3) - o0 + 1 : 0;
                 const int itmax = __reduce_max_sync(0xffffffffu, words);
-                const uint32_t* sq = seq_s + SEQ_PAD;
-                if (act) sq += (a.r.seq_off[r] - sbase_al);
-                uint32_t* row = rows + tid * RS + o0;
-                int colbase = o0 * 8, zu = 0, idx = 0, sh = 0, di = 0;
+                int colbase = o0 * 8, zu = 0, dsh = 0, di = 0;
                 int nb = INT_MAX, ngap = 0, nD = 0;
-                uint32_t whi = 0;
                 bool started = false;
                 if (nd > 0) { const uint32_t d = cs[0]; nb = (int)(d & 1023u); ngap = (int)((d >> 10) & 511u); nD = (int)d >> 19; }
                 for (int it = 0; it < itmax; ++it) {
                     if (it < words) {
+                        while (nb <= colbase) {                 // shift changes at or before this word's first column
+                            dsh = nD; zu = nb + ngap; started = true;
+                            if (++di < nd) { const uint32_t d = cs[di]; nb = (int)(d & 1023u); ngap = (int)((d >> 10) & 511u); nD = (int)d >> 19; }
+                            else nb = INT_MAX;
+                        }
                         uint32_t v = 0;
                         if (started) {
-                            const uint32_t wlo2 = sq[idx + 1];
-                            v = __funnelshift_l(wlo2, whi, sh);
-                            whi = wlo2; ++idx;
+                            const int idx = (dsh >> 3) + o0 + it;
+                            v = __funnelshift_l(sq[idx + 1], sq[idx], (dsh & 7) * 4);
                             if (zu > colbase) { const int kz = zu - colbase; v = kz >= 8 ? 0u : (v & (0xffffffffu >> (4 * kz))); }
-                        }
-                        while (nb < colbase + 8) {              // a shift change inside this row word
-                            const int kb = nb - colbase;
-                            const int g = kb + ngap;
-                            const int i2 = (nD >> 3) + o0 + it;
-                            sh = (nD & 7) * 4;
-                            const uint32_t a2 = sq[i2], b2 = sq[i2 + 1];
-                            const uint32_t v2 = __funnelshift_l(b2, a2, sh);
-                            const uint32_t m_new = g >= 8 ? 0u : (0xffffffffu >> (4 * g));
-                            v = (v & ~(0xffffffffu >> (4 * kb))) | (v2 & m_new);
-                            zu = nb + ngap;
-                            whi = b2; idx = i2 + 1; started = true;
-                            if (++di < nd) { const uint32_t d = cs[di]; nb = (int)(d & 1023u); ngap = (int)((d >> 10) & 511u); nD = (int)d >> 19; }
-                            else if (di == nd) { nb = seg_end; ngap = 511; nD = 0; }      // end of the read: zeros from here on
-                            else nb = INT_MAX;
                         }
                         row[it] = v;
                         colbase += 8;
+                    }
+                }
+            }
+            // ---- expand, pass B: one shift change per iteration.  A change at column b (not on a word boundary)
+            // replaces the nibbles from b on in its row word: `gap` zero columns, then the bases under the new shift.
+            {
+                const int npatch = nd > 0 ? nd + 1 : 0;         // + the end of the read
+                const int itmax = __reduce_max_sync(0xffffffffu, npatch);
+                for (int it = 0; it < itmax; ++it) {
+                    if (it < npatch) {
+                        int b, gap, dn;
+                        if (it < nd) { const uint32_t d = cs[it]; b = (int)(d & 1023u); gap = (int)((d >> 10) & 511u); dn = (int)d >> 19; }
+                        else { b = seg_end; gap = 511; dn = 0; }
+                        const int kb = b & 7;
+                        if (kb) {
+                            const int o = b >> 3;
+                            const int g = kb + gap;
+                            const int idx = (dn >> 3) + o;
+                            const uint32_t v2 = __funnelshift_l(sq[idx + 1], sq[idx], (dn & 7) * 4);
+                            const uint32_t m_new = g >= 8 ? 0u : (0xffffffffu >> (4 * g));
+                            uint32_t* wp = rows + tid * RS + o;
+                            *wp = (*wp & ~(0xffffffffu >> (4 * kb))) | (v2 & m_new);
+                        }
                     }
                 }
             }
