@@ -228,11 +228,11 @@ def run_ours(args):
     h_counts = np.empty((gpu.TC_NROWS, L), dtype=np.int32)
 
     def e2e_step():
-        d = ctx.upload(pinned, stream)                       # H2D of every read array (pinned memory)
-        ctx.pileup_counts(d, L, out=counts_dev, stream=stream)
+        # every read array the pileup needs goes host -> device inside tc_pileup_counts (pinned memory)
+        ctx.pileup_counts(pinned, L, out=counts_dev, stream=stream)
         res = ctx.call(counts_dev, L, w.mincov, True, stream=stream)     # D2H of the call table
         cands = ctx.list_insert_candidates(res.flags, L)
-        ins = ctx.extract_inserts(d, L, cands)
+        ins = ctx.extract_inserts(pinned, L, cands)          # H2D of the reads over the candidate columns (with QUAL)
         torch.cuda.current_stream().synchronize()
         h = counts_dev.cpu().numpy()                         # D2H of the count table
         return h, res, ins
@@ -241,16 +241,16 @@ def run_ours(args):
         e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xfer0 = ctx.transfer_bytes()
     e0.record()
     for _ in range(args.steps):
         h, res, ins = e2e_step()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    h2d = sum(int(getattr(pinned, n).nbytes) for n in ("pos", "flag", "mapq", "l_seq", "seq_off", "cigar_off", "seq4", "qual",
-                                                        "cigar", "qname_hash", "mpos", "isize") if getattr(pinned, n) is not None)
-    d2h = int(h.nbytes + res.call_char.nbytes + res.flags.nbytes + res.xrun.nbytes + res.rank_letter.nbytes +
-              res.rank_count.nbytes + res.ambig_char.nbytes)
+    h2d, d2h_lib = (b - a_ for a_, b in zip(xfer0, ctx.transfer_bytes()))
+    h2d //= args.steps
+    d2h = d2h_lib // args.steps + int(h.nbytes)
 
     # ---------------- max over ranks
     t = torch.tensor([ms_total, e2e_ms, float(bases), float(launches)], dtype=torch.float64, device="cuda")

@@ -155,6 +155,8 @@ int64_t tc_launch_count(const tc_ctx_t* ctx);
 /* Measurement aid (no counterpart in the reference): when enabled, tc_pileup_counts brackets its
  * dominant kernel (the pileup kernel proper, without memsets / scan / copies) with CUDA events on
  * the launching stream; tc_last_pileup_kernel_ms returns the duration of the most recent one. */
+/* bytes this context has copied host->device / device->host so far (bench.py's e2e accounting) */
+int  tc_transfer_bytes(const tc_ctx_t* ctx, int64_t* h2d, int64_t* d2h);
 int  tc_ctx_set_timing(tc_ctx_t* ctx, int enabled);
 float tc_last_pileup_kernel_ms(tc_ctx_t* ctx);
 

@@ -427,3 +427,54 @@ def test_config2_slice_properties(ctx, orc):
     half = b.n_reads // 2
     parts = ctx.pileup_counts(b.slice(0, half), L).astype(np.int64) + ctx.pileup_counts(b.slice(half, b.n_reads), L)
     assert np.array_equal(parts, g1)
+
+
+def test_extract_inserts_sliced_upload_equals_full_upload(ctx):
+    """Large host batches upload only the reads over the candidate columns; same answers."""
+    ref, _, b = _synth("amplicon_deep")
+    L = len(ref)
+    counts = ctx.pileup_counts(b, L)
+    cands = [int(c) for c in ctx.list_insert_candidates(ctx.call(counts, L, 30, True).flags, L)]
+    positions = sorted(set(cands) | {1, 700, 701, 2500, L})
+    full = ctx._extract_inserts_raw(b, L, np.asarray(positions, np.int32), __import__("trueconsense_b200").gpu.extractinserts_params())
+    old = ctx.SLICE_THRESHOLD
+    try:
+        type(ctx).SLICE_THRESHOLD = 0
+        sliced = ctx.extract_inserts(b, L, positions)
+    finally:
+        type(ctx).SLICE_THRESHOLD = old
+    assert sliced == full
+
+
+# ---------------------------------------------------------------------------- CLI end to end
+@pytest.mark.parametrize("name", ["quirk"] + list(MINIS))
+def test_cli_outputs_equal_reference_cli(ctx, name, tmp_path, monkeypatch):
+    """main() writes the files the reference's CLI wrote for the same BAM / FASTA / GFF
+    (tests/golden/cli_*, generated by oracle/make_golden.py from the unmodified reference)."""
+    import json
+
+    from trueconsense_b200 import TrueConsense
+
+    status = json.load(open(f"{GOLD}/cli_{name}.status.json"))
+    meta = load_golden_json(f"{name}.json")
+    out = str(tmp_path / f"cli_{name}")
+    argv = ["--input", f"{GOLD}/{name}.bam", "--reference", f"{GOLD}/{name}.fasta", "--features", f"{GOLD}/{name}.gff",
+            "--coverage-level", str(meta["mincov"]), "--samplename", name, "--output", out + ".fasta",
+            "--variants", out + ".vcf", "--output-gff", out + ".gff", "--depth-of-coverage", out + ".cov.tsv", "--threads", "2"]
+    monkeypatch.setattr("sys.argv", ["TrueConsense", "<golden>"])
+    if status["status"] == "raise":
+        with pytest.raises(Exception) as ei:
+            TrueConsense.main(argv)
+        assert type(ei.value).__name__ == status["exc"]
+    else:
+        TrueConsense.main(argv)
+    for ext in ("fasta", "gff", "cov.tsv", "vcf"):
+        gold = f"{GOLD}/cli_{name}.{ext}"
+        if not os.path.exists(gold):
+            assert not os.path.exists(f"{out}.{ext}"), ext
+            continue
+        got = open(f"{out}.{ext}").read()
+        if ext == "vcf":
+            got = "".join("##fileDate=<date>\n" if l.startswith("##fileDate=") else l for l in got.splitlines(keepends=True))
+            got = got.replace(GOLD + os.sep, "")
+        assert got == open(gold).read(), ext

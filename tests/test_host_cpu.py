@@ -1,0 +1,267 @@
+"""CPU-only tests (no GPU): host logic, the BAM reader/writer, repository layout, and that the
+C-ABI library loads and exports every symbol include/*.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT, load_golden_json
+
+
+# ---------------------------------------------------------------------------- C-ABI surface
+def _declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    from trueconsense_b200 import build
+
+    path = build.build_cuda()           # nvcc cross-compiles sm_100a without a GPU
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols("trueconsense_b200.h")
+    assert "tc_pileup_counts" in declared and "tc_extract_inserts" in declared and len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/trueconsense_b200.h but not exported"
+    lib.tc_abi_version.restype = ctypes.c_int
+    assert lib.tc_abi_version() == 1
+
+
+def test_cuda_library_is_sm100a_only():
+    from trueconsense_b200 import build
+
+    out = subprocess.run(["cuobjdump", "--list-elf", build.build_cuda()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_host_library_exports_every_declared_symbol():
+    from trueconsense_b200 import build
+
+    lib = ctypes.CDLL(build.build_host())
+    for name in _declared_symbols("tc_host.h"):
+        assert hasattr(lib, name), name
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device the product raises; it never computes on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from trueconsense_b200 import gpu
+
+    with pytest.raises(gpu.TcError) as ei:
+        gpu.Context(0)
+    assert ei.value.code == -6
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "trueconsense_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "pileup_oracle" not in text, f
+    code = ("import sys; sys.path.insert(0, %r); import trueconsense_b200.indexing, trueconsense_b200.Sequences, "
+            "trueconsense_b200.Events, trueconsense_b200.Ambig, trueconsense_b200.Coverage, trueconsense_b200.TrueConsense; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
+
+
+# ---------------------------------------------------------------------------- BAM io
+def test_bam_roundtrip_and_independent_reader(tmp_path, host_libs):
+    from oracle import bam_py
+    from trueconsense_b200 import bamio, synth
+
+    w = synth.config(0, scale=0.01)
+    b = synth.generate_reads(w.params, w.ref)
+    assert b.sorted and np.all(np.diff(b.pos.astype(np.int64)) >= 0)
+    path = str(tmp_path / "x.bam")
+    bamio.write_bam(path, b, "ref", len(w.ref), level=6)
+    c = bamio.read_bam(path)
+    p = bam_py.read_bam(path)
+    assert c.ref_names == ["ref"] and c.ref_lens == [len(w.ref)] and c.sorted
+    for name in ("pos", "flag", "mapq", "l_seq", "seq_off", "cigar_off", "seq4", "qual", "cigar", "mpos", "isize"):
+        assert np.array_equal(getattr(b, name), getattr(c, name)), name
+        assert np.array_equal(getattr(c, name), getattr(p, name)), name
+    assert np.array_equal(c.qname_hash, p.qname_hash)
+    assert c.aligned_bases == b.aligned_bases == b.count_aligned_bases(0)
+    # mates share their name hash
+    paired = (c.flag & 1) != 0
+    assert paired.any()
+    _, counts = np.unique(c.qname_hash[paired], return_counts=True)
+    assert set(counts.tolist()) <= {1, 2} and (counts == 2).sum() > 10
+
+
+def test_bam_reader_golden_fixtures(host_libs):
+    from oracle import bam_py
+    from trueconsense_b200 import bamio
+
+    for name in ("quirk", "mini_illumina", "mini_ont", "mini_long"):
+        c = bamio.read_bam(f"{GOLD}/{name}.bam")
+        p = bam_py.read_bam(f"{GOLD}/{name}.bam")
+        for arr in ("pos", "flag", "mapq", "l_seq", "seq_off", "cigar_off", "seq4", "qual", "cigar"):
+            assert np.array_equal(getattr(c, arr), getattr(p, arr)), (name, arr)
+        meta = load_golden_json(f"{name}.json")
+        assert c.n_reads == meta["n_reads"]
+
+
+def test_bam_reader_errors(tmp_path, host_libs):
+    from trueconsense_b200 import bamio
+
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"this is not a bam file, not even gzip" * 4)
+    with pytest.raises(OSError):
+        bamio.read_bam(str(bad))
+    with pytest.raises(OSError):
+        bamio.read_bam(str(tmp_path / "missing.bam"))
+
+
+def test_readbatch_slice_and_records():
+    from trueconsense_b200.reads import ReadBatch
+
+    recs = [dict(pos=i, cigar="3S10M2I5M1D4M", seq="ACGT" * 6, qual=list(range(24))) for i in range(10)]
+    b = ReadBatch.from_records(recs)
+    assert b.cigar_string(3) == "3S10M2I5M1D4M" and b.seq_string(3) == "ACGT" * 6
+    assert b.ref_spans().tolist() == [20] * 10
+    s = b.slice(4, 7)
+    s.validate()
+    assert s.n_reads == 3 and s.pos.tolist() == [4, 5, 6] and s.cigar_string(0) == b.cigar_string(4)
+    assert s.seq_string(2) == b.seq_string(6)
+    assert b.algorithmic_bytes(100) == 10 * (12 + 4 * 6 + 16) + 3200
+
+
+# ---------------------------------------------------------------------------- host walk bookkeeping
+def test_gff_tracker_matches_plain_correct_gff():
+    """The incremental stop-codon tracker of the host walk gives the same GFF updates as the plain
+    re-scan (both restate TrueConsense/ORFs.py:111-192; the plain one is the oracle's)."""
+    import copy
+
+    from oracle import call
+    from trueconsense_b200 import ORFs
+
+    rng = np.random.default_rng(9)
+    for case in range(300):
+        L = int(rng.integers(8, 90))
+        gff = {}
+        for k in range(int(rng.integers(1, 4))):
+            s = int(rng.integers(1, L))
+            e = int(rng.integers(s, L + 1))
+            gff[k] = {"start": s, "end": e, "strand": "+" if rng.random() < 0.8 else "-", "attributes": f"ID=f{k}"}
+        inserts = None
+        if rng.random() < 0.5:
+            inserts = {int(p): {str(int(rng.integers(1, 10))): "".join(rng.choice(list("ACGT"), int(rng.integers(1, 14))))}
+                       for p in rng.choice(np.arange(1, L + 1), size=min(3, L), replace=False)}
+        new_a, new_b, new_c = copy.deepcopy(gff), copy.deepcopy(gff), copy.deepcopy(gff)
+        tracker = ORFs.GffTracker(gff, new_b)
+        cons_a = []
+        for p in range(1, L + 1):
+            ch = str(rng.choice(list("ACGTacgt-N"), p=[.18, .14, .14, .18, .03, .03, .03, .03, .2, .04]))
+            cov = int(rng.choice([0, 5, 50]))
+            cons_a.append(ch); tracker.append(ch)
+            last = ch
+            if inserts and p in inserts and rng.random() < 0.7 and cov > 10:
+                s_ins = list(inserts[p].values())[0]
+                cons_a.append(s_ins); tracker.append(s_ins)
+                last = s_ins
+            new_a = call.correct_gff(gff, new_a, cons_a, p, inserts, 10, cov)
+            tracker.correct(p, last, inserts, 10, cov)
+            new_c = ORFs.CorrectGFF(gff, new_c, cons_a, p, inserts, 10, cov)
+            assert {k: (v["start"], v["end"]) for k, v in new_a.items()} == {k: (v["start"], v["end"]) for k, v in new_b.items()}, (case, p)
+            assert {k: (v["start"], v["end"]) for k, v in new_a.items()} == {k: (v["start"], v["end"]) for k, v in new_c.items()}, (case, p)
+
+
+def test_orf_helpers():
+    from trueconsense_b200 import ORFs
+
+    g = {0: {"start": 4, "end": 24, "strand": "+"}}
+    assert ORFs.in_orf(4, g) and ORFs.in_orf(23, g) and not ORFs.in_orf(24, g) and not ORFs.in_orf(3, g)
+    assert ORFs.SolveTripletLength([1, 2, 3], [0]) is False
+    assert ORFs.SolveTripletLength([1, 2], [0]) is True
+    assert ORFs.SolveTripletLength([1], [0, 9]) is True
+    assert ORFs.SolveTripletLength([1, 2, 3, 4], [0, 9]) is True
+    assert ORFs.split_to_codons("ATGAAAT") == ["ATG", "AAA", "T"]
+    h = {0: {"start": 10}, 1: {"start": 3}}
+    ORFs.CorrectStartPositions(h, "3", 5)
+    assert h[0]["start"] == 13 and h[1]["start"] == 3
+
+
+def test_synthetic_configs_shapes(host_libs):
+    from trueconsense_b200 import synth
+
+    for idx, scale in ((0, 0.02), (1, 0.001), (2, 0.001), (3, 0.0001), (4, 0.002)):
+        w = synth.config(idx, scale=scale)
+        b = synth.generate_reads(w.params, w.ref)
+        b.validate()
+        assert b.n_reads > 0 and b.sorted and b.aligned_bases == b.count_aligned_bases(0)
+        assert int(b.pos.max()) < len(w.ref) and int((b.pos.astype(np.int64) + b.ref_spans()).max()) <= len(w.ref)
+    # deterministic for a fixed seed, independent of the thread count
+    w = synth.config(1, scale=0.002)
+    a1 = synth.generate_reads(w.params, w.ref, threads=1)
+    a8 = synth.generate_reads(w.params, w.ref, threads=8)
+    assert np.array_equal(a1.seq4, a8.seq4) and np.array_equal(a1.cigar, a8.cigar) and np.array_equal(a1.qual, a8.qual)
+
+
+# ---------------------------------------------------------------------------- CLI surface and writers
+def test_cli_argument_surface(tmp_path, capsys, monkeypatch):
+    """Same flags, validators and exit behaviour as TrueConsense/TrueConsense.py:25-209."""
+    from trueconsense_b200 import TrueConsense
+
+    bam = tmp_path / "a.bam"; fa = tmp_path / "r.fasta"; gff = tmp_path / "f.gff"; txt = tmp_path / "a.txt"
+    for p in (bam, fa, gff, txt):
+        p.write_text("x")
+    base = ["-i", str(bam), "-ref", str(fa), "-gff", str(gff), "-cov", "30", "-name", "s", "-o", str(tmp_path / "c.fa")]
+    a = TrueConsense.GetArgs(base + ["-vcf", "v.vcf", "-doc", "d.tsv", "-ogff", "o.gff", "-t", "3", "-noambig"])
+    assert (a.input, a.reference, a.features, a.coverage_level, a.samplename) == (str(bam), str(fa), str(gff), 30, "s")
+    assert (a.variants, a.depth_of_coverage, a.output_gff, a.threads, a.noambiguity, a.index_override) == ("v.vcf", "d.tsv", "o.gff", 3, True, None)
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.GetArgs(["-i", str(tmp_path / "missing.bam")] + base[2:])
+    assert e.value.code == -1
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.GetArgs(base[:2] + ["-ref", str(tmp_path / "missing.fa")] + base[4:])
+    assert e.value.code == 1
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.GetArgs(["-i", str(txt)] + base[2:])          # wrong extension -> parser.error
+    assert e.value.code == 2
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.GetArgs(base[:-2])                             # --output is required
+    assert e.value.code == 2
+    monkeypatch.setattr("sys.argv", ["TrueConsense"])
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.main([])
+    assert e.value.code == 1
+    with pytest.raises(SystemExit) as e:
+        TrueConsense.GetArgs(["--version"])
+    assert e.value.code == 0
+    capsys.readouterr()
+
+
+def test_gff_writer_and_fasta_reader(tmp_path):
+    from trueconsense_b200 import Outputs, indexing
+
+    g = indexing.Gffindex(f"{GOLD}/mini_ont.gff")
+    df = g.df
+    df["seqid"] = "mini_ont"
+    out = tmp_path / "o.gff"
+    Outputs.WriteGFF(g.header, df.to_dict("index"), str(out), "mini_ont")
+    # the reference CLI run on the same GFF moved no coordinate of this fixture's features except through
+    # CorrectGFF; lines whose coordinates are unchanged must be byte-identical
+    gold = open(f"{GOLD}/cli_mini_ont.gff").read().splitlines()
+    mine = out.read_text().splitlines()
+    assert mine[:2] == gold[:2] and len(mine) == len(gold)
+    assert all(a.split("\t")[:3] == b.split("\t")[:3] and a.split("\t")[5:] == b.split("\t")[5:] for a, b in zip(mine, gold))
+    feat = {"seqid": "s", "source": "x", "type": "CDS", "start": 1, "end": 9, "score": ".", "strand": "+", "phase": 0,
+            "attributes": "ID=a;Name=b;", "Extra": 5}
+    assert Outputs._gff_line(feat) == "s\tx\tCDS\t1\t9\t.\t+\t0\tID=a;Name=b;extra=5\n"
+    with pytest.raises(ValueError):
+        Outputs._gff_line(dict(feat, attributes="ID=a=b"))
+    fa = tmp_path / "r.fa"
+    fa.write_text(">chr1 some description\nACGT\nacgt\n>chr2\nTTTT\n")
+    assert Outputs._first_fasta_record(str(fa)) == ("chr1", list("ACGTacgt"))

@@ -222,7 +222,7 @@ TC_API int tc_call(tc_ctx_t* ctx, const int32_t* counts, int32_t ref_len, const 
     bool any_host = false;
     for (int i = 0; i < 6; ++i) {
         if (outs[i].user && outs[i].dev != outs[i].user) {
-            TC_CUDA(cudaMemcpyAsync(outs[i].user, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, s));
+            TC_D2H(outs[i].user, outs[i].dev, outs[i].bytes, s);
             any_host = true;
         }
     }
@@ -247,7 +247,7 @@ TC_API int tc_is_ambiguous(tc_ctx_t* ctx, const uint8_t* letters, const int32_t*
     is_ambiguous_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dl, dc, dv, n, maxdist, d_out);
     TC_LAUNCH_CHECK();
     if (!out_dev) {
-        TC_CUDA(cudaMemcpyAsync(out_char, d_out, (size_t)n, cudaMemcpyDeviceToHost, s));
+        TC_D2H(out_char, d_out, (size_t)n, s);
         TC_CUDA(cudaStreamSynchronize(s));
     }
     return TC_OK;
@@ -266,14 +266,14 @@ TC_API int tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_
     list_candidates_kernel<<<1, 1024, 0, s>>>(df, ref_len, d_out + 1, cap, d_out);
     TC_LAUNCH_CHECK();
     int32_t n = 0;
-    TC_CUDA(cudaMemcpyAsync(ctx->host_status, d_out, 4, cudaMemcpyDeviceToHost, s));
+    TC_D2H(ctx->host_status, d_out, 4, s);
     TC_CUDA(cudaStreamSynchronize(s));
     n = *(int32_t*)ctx->host_status;
     *n_out = n;
     if (n > cap) return tc_fail(ctx, TC_ERR_CAPACITY, "%d insertion candidates, capacity %d", n, cap);
     if (n > 0) {
         if (tc_is_device_ptr(cand_pos)) TC_CUDA(cudaMemcpyAsync(cand_pos, d_out + 1, 4 * (size_t)n, cudaMemcpyDeviceToDevice, s));
-        else TC_CUDA(cudaMemcpyAsync(cand_pos, d_out + 1, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+        else TC_D2H(cand_pos, d_out + 1, 4 * (size_t)n, s);
         TC_CUDA(cudaStreamSynchronize(s));
     }
     return TC_OK;

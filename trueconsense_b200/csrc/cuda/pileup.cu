@@ -170,7 +170,7 @@ __global__ void depth_diff_kernel(pileup_args a) {
 
 
 static int fetch_status(tc_ctx* ctx, tc_status* d_status, tc_status* out, cudaStream_t s) {
-    TC_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s));
+    TC_D2H(ctx->host_status, d_status, sizeof(tc_status), s);
     TC_CUDA(cudaStreamSynchronize(s));
     memcpy(out, ctx->host_status, sizeof(tc_status));
     return TC_OK;
@@ -249,7 +249,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         TC_LAUNCH_CHECK();
     }
     tc_status st;
-    if (!out_dev) TC_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, cudaMemcpyDeviceToHost, s));
+    if (!out_dev) TC_D2H(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, s);
     rc = fetch_status(ctx, d_status, &st, s);
     if (rc) return rc;
     if (st.err == TC_ERR_CAPACITY && variant == 2 && p->kernel == 0) {
@@ -308,7 +308,7 @@ TC_API int tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, con
     }
     coverage_scan_kernel<<<1, 1024, 0, s>>>(d_diff, d_depth, L, d_status);
     TC_LAUNCH_CHECK();
-    if (!out_dev) TC_CUDA(cudaMemcpyAsync(depth, d_depth, sizeof(int32_t) * (size_t)L, cudaMemcpyDeviceToHost, s));
+    if (!out_dev) TC_D2H(depth, d_depth, sizeof(int32_t) * (size_t)L, s);
     tc_status st;
     rc = fetch_status(ctx, d_status, &st, s);
     if (rc) return rc;

@@ -27,6 +27,7 @@ struct tc_ctx {
     int sm_count;
     char err[512];
     int64_t launches;
+    int64_t h2d_bytes, d2h_bytes;
     tc_buf bufs[SLOT_COUNT];
     void* host_status;      // pinned, 256 bytes
     int timing;             // bracket the pileup kernel with events
@@ -55,6 +56,13 @@ const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cuda
     do {                                                                    \
         cudaError_t e__ = (call);                                           \
         if (e__ != cudaSuccess) return tc_cuda_fail(ctx, e__, #call);       \
+    } while (0)
+
+// device -> host copy with byte accounting
+#define TC_D2H(dst, src, bytes, s)                                                            \
+    do {                                                                                      \
+        TC_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (s)));          \
+        ctx->d2h_bytes += (int64_t)(bytes);                                                   \
     } while (0)
 
 #define TC_LAUNCH_CHECK()                                                   \

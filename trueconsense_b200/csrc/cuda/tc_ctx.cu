@@ -54,6 +54,7 @@ const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cuda
     if (bytes) {
         cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { *rc = tc_cuda_fail(ctx, e, "cudaMemcpyAsync H2D"); return NULL; }
+        ctx->h2d_bytes += (int64_t)bytes;
     }
     return d;
 }
@@ -142,6 +143,13 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     free(ctx);
+    return TC_OK;
+}
+
+TC_API int tc_transfer_bytes(const tc_ctx_t* ctx, int64_t* h2d, int64_t* d2h) {
+    if (!ctx) return TC_ERR_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
     return TC_OK;
 }
 

@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
             l.tc_last_error.restype = C.c_char_p
             l.tc_launch_count.argtypes = [vp]
             l.tc_launch_count.restype = i64
+            l.tc_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+            l.tc_transfer_bytes.restype = C.c_int
             l.tc_ctx_set_timing.argtypes = [vp, C.c_int]
             l.tc_ctx_set_timing.restype = C.c_int
             l.tc_last_pileup_kernel_ms.argtypes = [vp]
@@ -175,6 +177,12 @@ class Context:
     def launches(self) -> int:
         return int(self._lib.tc_launch_count(self._h))
 
+    def transfer_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes copied by this context so far."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.tc_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.tc_ctx_set_timing(self._h, int(enabled)))
 
@@ -258,14 +266,49 @@ class Context:
         self._check(self._lib.tc_list_insert_candidates(self._h, _ptr(flags), int(ref_len), _ptr(out), cap, C.byref(n), 0))
         return out[: n.value].copy()
 
+    SLICE_THRESHOLD = 100_000
+
     def extract_inserts(self, reads, ref_len: int, positions, params: PileupParams | None = None):
         """ExtractInserts for the given 1-based positions.  Returns a list of dicts with the modal
-        upper-cased string of each column (``None`` when pysam would have returned ``""``)."""
+        upper-cased string of each column (``None`` when pysam would have returned ``""``).
+
+        For large HOST batches only the reads that can reach a candidate column travel to the device
+        (this pass is the only one that needs QUAL, 8x the size of the packed bases): reads are
+        start-sorted, so the reads overlapping column c lie in pos (c - max_span, c]; candidates whose
+        read ranges overlap share one upload."""
         params = params or extractinserts_params()
         pos = np.ascontiguousarray(positions, dtype=np.int32)
-        n = int(pos.shape[0])
-        if n == 0:
+        if pos.shape[0] == 0:
             return []
+        if not isinstance(reads, ReadBatch) or reads.n_reads <= self.SLICE_THRESHOLD:
+            return self._extract_inserts_raw(reads, ref_len, pos, params)
+        batch = reads
+        if batch.max_ref_span < 0:
+            batch.max_ref_span = int(batch.ref_spans().max()) if batch.n_reads else 0
+        ms = max(int(batch.max_ref_span), 1)
+        cols = pos.astype(np.int64) - 1
+        lo = np.searchsorted(batch.pos, cols - ms + 1, side="left")
+        hi = np.searchsorted(batch.pos, cols + 1, side="left")
+        out: list = [None] * len(pos)
+        groups: list[tuple[int, int, list[int]]] = []      # (first read, end read, candidate indices)
+        for i in np.argsort(lo, kind="stable"):
+            i = int(i)
+            if groups and lo[i] <= groups[-1][1]:
+                r0, r1, members = groups[-1]
+                groups[-1] = (r0, max(r1, int(hi[i])), members + [i])
+            else:
+                groups.append((int(lo[i]), int(hi[i]), [i]))
+        for r0, r1, members in groups:
+            members.sort(key=lambda i: int(pos[i]))
+            res = self._extract_inserts_raw(batch.slice(r0, r1), ref_len, np.ascontiguousarray(pos[members]), params)
+            for i, item in zip(members, res):
+                if item["first_read"] >= 0:
+                    item["first_read"] += r0
+                out[i] = item
+        return out
+
+    def _extract_inserts_raw(self, reads, ref_len: int, pos: np.ndarray, params: PileupParams):
+        n = int(pos.shape[0])
         calls = (InsertCall * n)()
         cap = 1 << 16
         rs = self._reads_struct(reads)

@@ -83,7 +83,10 @@ class BamHandle:
 
 
 def Readbam(f):
-    """indexing.py:6-19."""
+    """indexing.py:6-19.  A handle passed in is returned as is, so one decoded copy of the BAM can
+    serve BuildIndex, ListInserts and WriteOutputs."""
+    if isinstance(f, BamHandle):
+        return f
     return BamHandle(f)
 
 
