@@ -107,9 +107,9 @@ def make_sample(scale: float, sample: int):
     return w, batch
 
 
-def hot_path(ctx, reads, L, mincov, counts_dev, table, flags_dev, stream):
+def hot_path(ctx, reads, L, mincov, counts_dev, table, flags_dev, stream, params=None):
     """One pass: pileup -> call -> insertion candidates -> insertion calls.  Returns the calls."""
-    ctx.pileup_counts(reads, L, out=counts_dev, stream=stream)
+    ctx.pileup_counts(reads, L, params, out=counts_dev, stream=stream)
     ctx.call_device(counts_dev, L, mincov, True, table, stream=stream)
     cands = ctx.list_insert_candidates(flags_dev, L)
     return ctx.extract_inserts(reads, L, cands)
@@ -207,8 +207,9 @@ def run_ours(args):
     dev = ctx.upload(pinned, stream)
     torch.cuda.synchronize()
     ctx.set_timing(True)
+    params = gpu.buildindex_params(args.kernel)
     for _ in range(args.warmup):
-        calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream)
+        calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -217,7 +218,7 @@ def run_ours(args):
     kernel_ms = []
     ev0.record()
     for _ in range(args.steps):
-        calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream)
+        calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
         kernel_ms.append(ctx.last_pileup_kernel_ms())
     ev1.record()
     barrier()
@@ -229,7 +230,7 @@ def run_ours(args):
 
     def e2e_step():
         # every read array the pileup needs goes host -> device inside tc_pileup_counts (pinned memory)
-        ctx.pileup_counts(pinned, L, out=counts_dev, stream=stream)
+        ctx.pileup_counts(pinned, L, params, out=counts_dev, stream=stream)
         res = ctx.call(counts_dev, L, w.mincov, True, stream=stream)     # D2H of the call table
         cands = ctx.list_insert_candidates(res.flags, L)
         ins = ctx.extract_inserts(pinned, L, cands)          # H2D of the reads over the candidate columns (with QUAL)
@@ -302,6 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", type=int, default=0, help="pileup kernel variant (0 = library's choice; A/B measurements only)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 2 M reads of configs[1] (tests only)")
     ap.add_argument("--cpu-reads", type=float, default=150_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--ref-reads", type=float, default=400_000, help="reads per step of the --impl reference arm")

@@ -15,7 +15,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 pytestmark = pytest.mark.gpu
 
 MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
-KERNELS = [1, 2]      # pileup kernel variants: 1 scatter (smem atomics), 2 SWAR column kernel
+KERNELS = [1, 2, 3]   # pileup kernel variants: 1 scatter (smem atomics), 2 SWAR CTA tiles, 3 SWAR warp streams
 
 
 @pytest.fixture(scope="module")
@@ -45,7 +45,7 @@ def _pileup(ctx, b, L, kernel):
     try:
         return ctx.pileup_counts(b, L, gpu.buildindex_params(kernel))
     except gpu.TcError as e:
-        if kernel == 2 and e.code == -8:
+        if kernel in (2, 3) and e.code == -8:
             return ctx.pileup_counts(b, L, gpu.buildindex_params(0))
         raise
 
@@ -91,6 +91,8 @@ SYNTH_CASES = {
                           softclip_rate=0.05, softclip_max=20, n_rate=0.001),
     "long_reads": dict(n_reads=400, read_len=3000, read_len_jitter=800, indel_rate=1 / 40, indel_maxlen=2, softclip_rate=0.2,
                        softclip_max=60),
+    "mid_reads": dict(n_reads=3000, read_len=700, read_len_jitter=100, indel_rate=1 / 40, indel_maxlen=3, softclip_rate=0.2,
+                      softclip_max=30, n_rate=0.002),
     "tiny": dict(n_reads=3, read_len=50),
     "one_read": dict(n_reads=1, read_len=10),
 }

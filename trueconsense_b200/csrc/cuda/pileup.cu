@@ -218,16 +218,17 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
     const bool per_entry = p->min_base_quality > 0;
     int variant = p->kernel;
-    if (variant == 0) variant = (!per_entry && tc_pileup_swar_supported(a)) ? 2 : 1;
-    if (variant == 2 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernel has no base-quality filter; use kernel=1");
-    if (variant == 2 && !tc_pileup_swar_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernel needs 16-byte aligned seq4 / cigar arrays; use kernel=1");
+    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? 3 : 1;
+    if (variant < 1 || variant > 3) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
+    if (variant != 1 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels have no base-quality filter; use kernel=1");
+    if (variant != 1 && !tc_pileup_swar_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
-        if (variant == 2) {
+        if (variant != 1) {
             // coverage ends, span statistics and the sortedness / range checks: one thread per read
             depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
             TC_LAUNCH_CHECK();
-            rc = tc_pileup_swar_launch(ctx, a, s);
+            rc = variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_swar_launch(ctx, a, s);
             if (rc) return rc;
         } else {
             int n_chunks = (int)((a.r.n + SC_CHUNK - 1) / SC_CHUNK);
@@ -252,14 +253,14 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     if (!out_dev) TC_D2H(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, s);
     rc = fetch_status(ctx, d_status, &st, s);
     if (rc) return rc;
-    if (st.err == TC_ERR_CAPACITY && variant == 2 && p->kernel == 0) {
-        // a read larger than the SWAR kernel's staging buffers: the scatter kernel has no such limit
+    if (st.err == TC_ERR_CAPACITY && variant != 1 && p->kernel == 0) {
+        // a read larger than the SWAR kernels' windows / staging buffers: the scatter kernel has no such limit
         tc_pileup_params_t q = *p;
         q.kernel = 1;
         return tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
     }
     if (st.err == TC_ERR_CAPACITY)
-        return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the SWAR kernel's staging buffers; use kernel=1 (or 0)");
+        return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the SWAR kernels' windows or staging buffers; use kernel=1 (or 0)");
     if (per_entry) {
         // coverage was counted entry by entry, so max_cov is not the live depth; fall back to the
         // trivial bound (every read live at once)

@@ -24,3 +24,7 @@ __device__ __forceinline__ bool read_passes(const pileup_args& a, int64_t r) {
 // variant 2 (pileup_swar.cu): enqueue the SWAR column kernel(s); fills every row except coverage
 int tc_pileup_swar_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);
 bool tc_pileup_swar_supported(const pileup_args& a);
+
+// variant 3 (pileup_warp.cu): barrier-free warp-per-read-stream SWAR kernel; fills every row except coverage
+int tc_pileup_warp_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);
+bool tc_pileup_warp_supported(const pileup_args& a);
