@@ -40,7 +40,9 @@ constexpr int MIN_SLACK = 64;
 constexpr int HI_PLANES = 7;            // bit-sliced planes above "eights": 15 + 16*127 = 2047 reads per run
 constexpr int RUN_CAP = 2047;
 // per op: bit0 = M/=/X, bit1 = consumes reference, bit2 = consumes query (MIDNSHP=X -> 0..8)
-constexpr unsigned long long OPFLAGS = 7ull | (4ull << 3) | (2ull << 6) | (2ull << 9) | (4ull << 12) | (7ull << 21) | (7ull << 24);
+constexpr uint32_t OPFLAGS = 7u | (4u << 3) | (2u << 6) | (2u << 9) | (4u << 12) | (7u << 21) | (7u << 24);
+// clamped shift: ops 11..15 (not defined by BAM) index past the table and read 0
+__device__ __forceinline__ uint32_t op_flags(uint32_t op) { return __funnelshift_rc(OPFLAGS, 0u, 3u * op) & 7u; }
 
 template <int WC> struct geom {
     static constexpr int ROWW = WC * 8;             // window / row width in reference columns
@@ -71,10 +73,28 @@ __device__ __forceinline__ uint32_t clear_multibit(uint32_t w) {
 
 struct walk_out { int nd, b_first, last_end; };
 
-// One lane = one read.  cs: the read's staged CIGAR ops (overwritten by head-fragment descriptors),
-// x: start column inside the window, lq: l_seq, row: the lane's row, xi: the warp's packed X|I counters.
-template <int ROWW, bool EXOTIC>
-__device__ __forceinline__ walk_out walk_read(uint32_t* cs, int nops, int x, const int lq, uint32_t* row, int* xi, int* err) {
+extern __shared__ __align__(16) uint32_t smem[];
+
+// Shared memory is addressed through 32-bit shared-window byte addresses and explicit ld/st/red.shared:
+// the lane-private rows, descriptor lists and counters are indexed with data-dependent offsets in every
+// inner loop, and this keeps each access at one address add + one LDS/STS/ATOMS.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Walk, general form (pads / zero-length ops present in the sub-tile): one op per iteration with the full
+// look-ahead state of htslib's resolve_cigar2.  One lane = one read.  cs: word offset of the read's staged
+// CIGAR ops (overwritten by head-fragment descriptors), x: start column inside the window, lq: l_seq,
+// row: word offset of the lane's row, xi: word offset of the warp's packed X|I counters.
+template <int ROWW>
+__device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nops, int x, const int lq, const uint32_t row, const uint32_t xi, int* err) {
     const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
     int y = 0, nd = 0, b_first = INT_MAX, last_end = 0;
     int pend = 0, lastcol = 0;
@@ -82,50 +102,103 @@ __device__ __forceinline__ walk_out walk_read(uint32_t* cs, int nops, int x, con
     const int kmax = __reduce_max_sync(FULL, nops);
     for (int k = 0; k < kmax; ++k) {
         if (k < nops) {
-            const uint32_t c = cs[k];
+            const uint32_t c = lds(cs + 4 * k);
             const uint32_t op = c & 15u;
             const int l = (int)(c >> 4);
-            const uint32_t fl = (uint32_t)(OPFLAGS >> (3u * op)) & 7u;
+            const uint32_t fl = op_flags(op);
             const int e = x + l;
-            if ((fl & 1u) && has_seq && l > 0) {
+            if ((fl & 1u) && has_seq && l > 0 && (y + l > lq || e > ROWW)) { atomicCAS(err, 0, TC_ERR_CAPACITY); nops = 0; }   // CIGAR longer than SEQ
+            else if ((fl & 1u) && has_seq && l > 0) {
                 const int D = y - x;
                 const int fw8 = (x + 7) & ~7;
-                if (fw8 < e) row[fw8 >> 3] = (uint32_t)e | ((uint32_t)D << 11);
+                if (fw8 < e) sts(row + (fw8 >> 1), (uint32_t)e | ((uint32_t)D << 11));
                 if (x & 7) {
                     const int fe = min(e, (x | 7) + 1);
-                    cs[nd++] = (uint32_t)x | ((uint32_t)(fe - x) << 11) | ((uint32_t)D << 14);
+                    sts(cs + 4 * nd, (uint32_t)x | ((uint32_t)(fe - x) << 11) | ((uint32_t)D << 14));
+                    ++nd;
                 }
                 b_first = min(b_first, x);
                 last_end = e;
             }
             if (op == OP_D && e <= ROWW)
-                for (int col = x; col < e; ++col) atomicAdd(&xi[col], 1);
-            if (EXOTIC) {
-                // general look-ahead state of htslib's resolve_cigar2 (pads, zero-length ops)
-                if (op == OP_I) {
-                    if (pend && l > 0) {
-                        if (lastcol >= 0 && lastcol < ROWW) atomicAdd(&xi[lastcol], last_was_d ? 0xffff : 0x10000);
-                        pend = 0;
-                    }
-                } else if (op == OP_P) {
-                    if (pend == 1) pend = 2;
-                } else if (!(fl & 2u)) {
-                    if (pend == 1) pend = 0;
+                for (int col = x; col < e; ++col) reds(xi + 4 * col, 1u);
+            if (op == OP_I) {
+                if (pend && l > 0) {
+                    if (lastcol >= 0 && lastcol < ROWW) reds(xi + 4 * lastcol, last_was_d ? 0xffffu : 0x10000u);
+                    pend = 0;
                 }
-                if (fl & 2u) { pend = 1; last_was_d = (op == OP_D); lastcol = e - 1; }
-            } else {
-                // no pads, no zero-length ops: an insertion counts iff the op before it consumes the reference;
-                // after a deletion that column reads "*+n.." and is no longer an X (one add does both)
-                if (op == OP_I && pend && x >= 1 && x <= ROWW) atomicAdd(&xi[x - 1], last_was_d ? 0xffff : 0x10000);
-                pend = (int)(fl & 2u);
-                last_was_d = (op == OP_D);
+            } else if (op == OP_P) {
+                if (pend == 1) pend = 2;
+            } else if (!(fl & 2u)) {
+                if (pend == 1) pend = 0;
             }
+            if (fl & 2u) { pend = 1; last_was_d = (op == OP_D); lastcol = e - 1; }
             x = (fl & 2u) ? e : x;
             y += (fl & 4u) ? l : 0;
             if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); nops = 0; nd = 0; b_first = INT_MAX; }
         }
     }
-    if (y > lq && b_first != INT_MAX) { atomicCAS(err, 0, TC_ERR_CAPACITY); }    // CIGAR longer than SEQ: scatter kernel
+    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end;
+    return o;
+}
+
+// Walk, common form (no pads, no zero-length ops anywhere in the sub-tile).  Lanes are kept in step on
+// their M/=/X ops: every outer iteration first lets each lane consume the ops in front of its next match op
+// (typically one I or D), then all lanes emit one match op together — so the match body runs once per
+// match op of the longest read instead of once per op.  Without pads an insertion counts iff the op before
+// it consumes the reference, and after a deletion that column reads "*+n..", no longer an X (one add does both).
+template <int ROWW>
+__device__ __forceinline__ walk_out walk_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi, int* err) {
+    const bool has_seq = lq != 0;
+    int y = 0, nd = 0, b_first = INT_MAX, last_end = 0, k = 0;
+    bool prev_ref = false, prev_d = false;
+    while (__any_sync(FULL, k < nops)) {
+        uint32_t c = 0;
+        bool at_m = false;
+        while (k < nops) {
+            c = lds(cs + 4 * k);
+            const uint32_t op = c & 15u;
+            const uint32_t fl = op_flags(op);
+            if (fl & 1u) { at_m = true; break; }
+            const int l = (int)(c >> 4);
+            const int e = x + l;
+            // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
+            // column x-1 (+1 I, and -1 X when that column belongs to a deletion)
+            const bool is_d = (op == OP_D), is_i = (op == OP_I);
+            const bool ev = (is_d && e <= ROWW) || (is_i && prev_ref && x >= 1 && x <= ROWW);
+            if (ev) reds(xi + 4 * (is_d ? x : x - 1), is_d ? 1u : (prev_d ? 0xffffu : 0x10000u));
+            if (is_d && l > 1 && e <= ROWW) for (int col = x + 1; col < e; ++col) reds(xi + 4 * col, 1u);
+            prev_ref = (fl & 2u) != 0;
+            prev_d = is_d;
+            x = (fl & 2u) ? e : x;
+            y += (fl & 4u) ? l : 0;
+            ++k;
+        }
+        if (at_m) {
+            const int l = (int)(c >> 4);
+            const int e = x + l;
+            // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
+            if (e > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+            else {
+                if (has_seq) {
+                    const int D = y - x;
+                    const int fw8 = (x + 7) & ~7;
+                    if (fw8 < e) sts(row + (fw8 >> 1), (uint32_t)e | ((uint32_t)D << 11));
+                    if (x & 7) {
+                        const int fe = min(e, (x | 7) + 1);
+                        sts(cs + 4 * nd, (uint32_t)x | ((uint32_t)(fe - x) << 11) | ((uint32_t)D << 14));
+                    ++nd;
+                    }
+                    b_first = min(b_first, x);
+                    last_end = e;
+                }
+                x = e; y += l;
+                prev_ref = true; prev_d = false;
+                ++k;
+            }
+        }
+        if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+    }
     walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end;
     return o;
 }
@@ -134,7 +207,6 @@ template <int WC>
 __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pileup_args a) {
     using G = geom<WC>;
     constexpr int ROWW = G::ROWW, RS = G::RS, NW = G::NW;
-    extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31;
     const int L = a.L;
 
@@ -149,13 +221,14 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         return;
     }
 
-    uint32_t* rows = smem + (threadIdx.x >> 5) * G::WARP_WORDS;     // [32][RS]
-    uint32_t* seq_s = rows + 32 * RS;                               // index SEQ_PAD <-> word sbase_al
-    uint32_t* cig_s = seq_s + G::SEQ_WORDS;
-    int* xi = (int*)(cig_s + G::CIG_WORDS);                         // [ROWW]  X count | I count << 16
-    for (int i = lane; i < 32 * RS; i += 32) rows[i] = 0;
-    for (int i = lane; i < ROWW; i += 32) xi[i] = 0;
-    if (lane < G::SEQ_PAD) seq_s[lane] = 0;
+    // the warp's slice of shared memory, as shared-window byte addresses
+    const uint32_t rows = (uint32_t)__cvta_generic_to_shared(smem) + 4u * (threadIdx.x >> 5) * G::WARP_WORDS;   // [32][RS]
+    const uint32_t seq_s = rows + 4u * 32 * RS;                 // seq_s + 4 * SEQ_PAD <-> SEQ word sbase_al
+    const uint32_t cig_s = seq_s + 4u * G::SEQ_WORDS;
+    const uint32_t xi = cig_s + 4u * G::CIG_WORDS;              // [ROWW]  X count | I count << 16
+    for (int i = lane; i < 32 * RS; i += 32) sts(rows + 4 * i, 0u);
+    for (int i = lane; i < ROWW; i += 32) sts(xi + 4 * i, 0u);
+    if (lane < G::SEQ_PAD) sts(seq_s + 4 * lane, 0u);
     __syncwarp();
 
     const int64_t n_reads = a.r.n;
@@ -174,7 +247,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         for (int p = 0; p < HI_PLANES; ++p) hi[j][p] = 0;
     }
     int w0 = INT_MIN, run_reads = 0;
-    uint32_t* row = rows + lane * RS;
+    const uint32_t row = rows + 4u * lane * RS;
 
     auto flush = [&]() {
         __syncwarp();
@@ -205,14 +278,14 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             for (int p = 0; p < HI_PLANES; ++p) hi[j][p] = 0;
         }
         for (int i = lane; i < ROWW; i += 32) {
-            const int v = xi[i];
+            const uint32_t v = lds(xi + 4 * i);
             if (v) {
-                const int xv = v & 0xffff, iv = (int)((uint32_t)v >> 16);
+                const int xv = (int)(v & 0xffffu), iv = (int)(v >> 16);
                 if (w0 + i < L) {
                     if (xv) atomicAdd(&a.counts[(size_t)TC_ROW_X * L + w0 + i], xv);
                     if (iv) atomicAdd(&a.counts[(size_t)TC_ROW_I * L + w0 + i], iv);
                 }
-                xi[i] = 0;
+                sts(xi + 4 * i, 0u);
             }
         }
         __syncwarp();
@@ -260,33 +333,57 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             const int nv = (int)((send - sbase_al + 3) >> 2);
             const uint32_t cend = __shfl_sync(FULL, co_next, n - 1);
             const int ncv = (int)((cend - cbase_al + 3) >> 2);
-            uint32_t zacc = 0, exacc = 0;
+            // the next sub-tile starts where this one ends and is about as large: pull its lines (and the
+            // metadata lines two sub-tiles ahead) towards L2 while this one is being processed
+            {
+                const int64_t s_lo = (int64_t)send - 1, s_len = (int64_t)send - sbase_al;
+                for (int64_t o = 32 * lane; o < s_len && s_lo + o < n_seq_words; o += 1024) prefetch_l2(a.r.seq4 + s_lo + o);
+                const int64_t c_len = (int64_t)cend - cbase_al;
+                for (int64_t o = 32 * lane; o < c_len && (int64_t)cend + o < n_ops_total; o += 1024) prefetch_l2(a.r.cigar + cend + o);
+                const int64_t rm = r + n + 64;
+                if (rm < n_reads) {
+                    if (lane == 0) prefetch_l2(a.r.pos + rm);
+                    if (lane == 1) prefetch_l2(a.r.seq_off + rm);
+                    if (lane == 2) prefetch_l2(a.r.cigar_off + rm);
+                    if (lane == 3) prefetch_l2(a.r.l_seq + rm);
+                    if (lane == 4) prefetch_l2(a.r.flag + rm);
+                }
+            }
+            uint32_t dirty = 0, exacc = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
+            const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
             if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
-                uint4* dst = reinterpret_cast<uint4*>(seq_s + G::SEQ_PAD);
-                for (int i = lane; i < nv; i += 128) {
+                int t = 0;
+                for (int i = lane; i < nv; i += 128, t += 4) {
                     uint4 v[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) {
-                        zacc |= multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
+                        const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
+                        dirty |= (z != 0 ? 1u : 0u) << (t + u);
                         v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
                         v[u].z = __byte_perm(v[u].z, 0, 0x0123); v[u].w = __byte_perm(v[u].w, 0, 0x0123);
-                        dst[i + 32 * u] = v[u];
+                        sts4(sdst + 16 * (i + 32 * u), v[u]);
                     }
                 }
             } else {            // the last sub-tile of the batch: do not read past the array
-                for (int i = lane; i < 4 * nv; i += 32) {
-                    const int64_t wi = (int64_t)sbase_al + i;
-                    const uint32_t w = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
-                    zacc |= multibit(w);
-                    seq_s[G::SEQ_PAD + i] = __byte_perm(w, 0, 0x0123);
+                int t = 0;
+                for (int i = lane; i < nv; i += 32, ++t) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int64_t wi = (int64_t)sbase_al + 4 * i + u;
+                        w[u] = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
+                    }
+                    const uint32_t z = multibit(w[0]) | multibit(w[1]) | multibit(w[2]) | multibit(w[3]);
+                    dirty |= (z != 0 ? 1u : 0u) << t;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
                 }
             }
             if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
                 const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
-                uint4* cdst = reinterpret_cast<uint4*>(cig_s);
                 for (int i = lane; i < ncv; i += 64) {
                     uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
                     const bool b1 = i + 32 < ncv;
@@ -295,57 +392,69 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                              (uint32_t)((v0.z & 15u) == OP_P) | (uint32_t)(v0.z < 16u) | (uint32_t)((v0.w & 15u) == OP_P) | (uint32_t)(v0.w < 16u) |
                              (uint32_t)((v1.x & 15u) == OP_P) | (uint32_t)(v1.x < 16u) | (uint32_t)((v1.y & 15u) == OP_P) | (uint32_t)(v1.y < 16u) |
                              (uint32_t)((v1.z & 15u) == OP_P) | (uint32_t)(v1.z < 16u) | (uint32_t)((v1.w & 15u) == OP_P) | (uint32_t)(v1.w < 16u);
-                    cdst[i] = v0;
-                    if (b1) cdst[i + 32] = v1;
+                    sts4(cig_s + 16 * i, v0);
+                    if (b1) sts4(cig_s + 16 * (i + 32), v1);
                 }
             } else {
                 for (int i = lane; i < 4 * ncv; i += 32) {
                     const int64_t oi = (int64_t)cbase_al + i;
                     const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
                     exacc |= (uint32_t)((c & 15u) == OP_P) | (uint32_t)(c < 16u);
-                    cig_s[i] = c;
+                    sts(cig_s + 4 * i, c);
                 }
             }
             cig_exotic = __any_sync(FULL, exacc != 0);
-            __syncwarp();
-            if (__any_sync(FULL, zacc != 0)) {      // rare: some base is N / IUPAC — clear those codes (they only count towards coverage)
-                for (int i = lane; i < 4 * nv; i += 32) seq_s[G::SEQ_PAD + i] = clear_multibit(seq_s[G::SEQ_PAD + i]);
-                __syncwarp();
+            // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
+            // Only the vectors that hold one are revisited, one per lane and iteration.
+            while (__any_sync(FULL, dirty != 0)) {
+                if (dirty) {
+                    const int t = __ffs(dirty) - 1;
+                    dirty &= dirty - 1;
+                    const uint32_t q = sdst + 16 * (lane + 32 * t);
+                    uint4 v = lds4(q);
+                    v.x = clear_multibit(v.x); v.y = clear_multibit(v.y); v.z = clear_multibit(v.z); v.w = clear_multibit(v.w);
+                    sts4(q, v);
+                }
             }
+            __syncwarp();
         }
 
         // ---- walk
         const bool act = lane < n && passes;
-        uint32_t* cs = cig_s + (co - cbase_al);
+        const uint32_t cs = cig_s + 4u * (co - cbase_al);
         const int nops = act ? (int)(co_next - co) : 0;
         const int x0 = p - w0;
         walk_out wo;
-        if (cig_exotic) wo = walk_read<ROWW, true>(cs, nops, x0, lq, row, xi, &a.status->err);
-        else wo = walk_read<ROWW, false>(cs, nops, x0, lq, row, xi, &a.status->err);
+        if (cig_exotic) wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
+        else wo = walk_read_common<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
 
         // ---- expand A: one row word per iteration; a non-zero word starts a new regime (end column, shift)
-        const uint32_t* sq = seq_s + G::SEQ_PAD + (so - sbase_al);
+        const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
         {
             const bool any_m = wo.b_first != INT_MAX;
             const int o0 = any_m ? wo.b_first >> 3 : 0;
             const int words = any_m ? ((wo.last_end - 1) >> 3) - o0 + 1 : 0;
             const int itmax = __reduce_max_sync(FULL, words);
-            uint32_t* rp = row + o0;
-            const uint32_t* sp = sq + o0;
-            int ue = 0, dw = 0, sh4 = 0, colbase = o0 * 8;
+            // Every lane runs all itmax iterations, no branches: past its own last word a lane points at its
+            // row's pad word (always zero: no new regime, and the regime in force has ended, so it stores zero).
+            // Source addresses under a regime that has ended stay inside the warp's shared-memory slice.
+            uint32_t rp = row + 4u * o0;            // the row word of this iteration
+            const uint32_t rpad = row + 4u * WC;
+            uint32_t sp = sq + 4u * o0;             // the SEQ word under it (+ 4 * (D >> 3) of the regime in force)
+            int sh4 = 0, rem4 = 0, left = words;    // rem4: 4 * (columns the regime still covers from this word's first column)
+#pragma unroll 4
             for (int it = 0; it < itmax; ++it) {
-                if (it < words) {
-                    const uint32_t t = rp[it];
-                    if (t) { ue = (int)(t & 0x7ffu); const int D = (int)t >> 11; dw = D >> 3; sh4 = (D & 7) << 2; }
-                    const int nrem = ue - colbase;
-                    uint32_t v = 0;
-                    if (nrem > 0) {
-                        const uint32_t* s = sp + it + dw;
-                        v = __funnelshift_l(s[1], s[0], sh4) & ~__funnelshift_rc(0xffffffffu, 0u, min(nrem, 8) * 4);
-                    }
-                    rp[it] = v;
-                    colbase += 8;
+                const uint32_t rq = left > 0 ? rp : rpad;
+                const uint32_t t = lds(rq);
+                if (t) {
+                    const int D = (int)t >> 11;
+                    rem4 = 4 * ((int)(t & 0x7ffu) - 8 * (o0 + it));
+                    sp = sq + 4u * (o0 + it) + (uint32_t)((D >> 3) << 2);
+                    sh4 = (D & 7) << 2;
                 }
+                const uint32_t v = __funnelshift_l(lds(sp + 4), lds(sp), sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4, 0));
+                sts(rq, v);
+                rem4 -= 32; rp += 4; sp += 4; --left;
             }
         }
         // ---- expand B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row
@@ -353,14 +462,14 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             const int itmax = __reduce_max_sync(FULL, wo.nd);
             for (int it = 0; it < itmax; ++it) {
                 if (it < wo.nd) {
-                    const uint32_t d = cs[it];
+                    const uint32_t d = lds(cs + 4 * it);
                     const int b = (int)(d & 0x7ffu), flen = (int)((d >> 11) & 7u), D = (int)d >> 14;
                     const int o = b >> 3, kb = b & 7;
                     const int q0 = 8 * o + D;
-                    const uint32_t* s = sq + (q0 >> 3);
-                    const uint32_t v = __funnelshift_l(s[1], s[0], (q0 & 7) << 2);
+                    const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
+                    const uint32_t v = __funnelshift_l(lds(s + 4), lds(s), (q0 & 7) << 2);
                     const uint32_t m = (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, 4 * (kb + flen));
-                    row[o] |= v & m;
+                    sts(row + 4 * o, lds(row + 4 * o) | (v & m));
                 }
             }
         }
@@ -369,13 +478,13 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         // ---- column sum: lane owns row words lane + 32 j, all 32 rows
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
-            uint32_t* col = rows + lane + 32 * j;
+            const uint32_t col = rows + 4u * (lane + 32 * j);
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
                 if (blk * 16 < n) {
                     uint32_t xw[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) { xw[q] = col[(blk * 16 + q) * RS]; col[(blk * 16 + q) * RS] = 0; }
+                    for (int q = 0; q < 16; ++q) { xw[q] = lds(col + 4u * (blk * 16 + q) * RS); sts(col + 4u * (blk * 16 + q) * RS, 0u); }
                     uint32_t twosA, twosB, foursA, foursB, eightsA, eightsB, sixteens;
                     csa(twosA, ones[j], ones[j], xw[0], xw[1]);
                     csa(twosB, ones[j], ones[j], xw[2], xw[3]);
