@@ -83,6 +83,11 @@ typedef struct tc_reads {
     const uint64_t* qname_hash; /* [n] any hash of QNAME that is equal for both mates */
     const int32_t*  mpos;       /* [n] PNEXT (0-based, -1 if unavailable) */
     const int32_t*  isize;      /* [n] TLEN */
+    /* optional: an upper bound of the longest reference span (sum of M,=,X,D,N lengths) of any read, which a
+     * BAM decoder knows for free; 0 = unknown (the library then finds it with one more pass over the CIGARs).
+     * tc_pileup_counts verifies the bound while it walks the CIGARs and fails with TC_ERR_ARG if it is too small. */
+    int32_t max_ref_span;
+    int32_t reserved;
 } tc_reads_t;
 
 /* ---- pileup filters: the arguments of pysam's AlignmentFile.pileup() that the
@@ -190,8 +195,9 @@ int  tc_is_ambiguous(tc_ctx_t* ctx, const uint8_t* letters, const int32_t* cnts,
 /* ---- (2) insertions: ExtractInserts, Events.py:47-82, for n_cand 1-based positions ----
  * For every candidate the column at pos-1 is piled up under `params` (the pysam defaults of
  * Events.py:66: samtools stepper, min_base_quality 13, max_depth 8000), every entry becomes a
- * fixed-width key (head char, indel, packed inserted bases), keys are radix-sorted and
- * run-length encoded, and the most common upper-cased string (ties: first encountered,
+ * fixed-width key (head char, indel, packed inserted bases), keys are counted (shared-memory hash
+ * table per column; params->kernel == 2, or a column with thousands of distinct strings: radix sort +
+ * run-length encoding) and the most common upper-cased string (ties: first encountered,
  * collections.Counter.most_common) is returned.  calls: [n_cand]; bases: char buffer of
  * bases_cap bytes receiving the inserted characters of each modal string. */
 int  tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len,

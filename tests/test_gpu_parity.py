@@ -480,3 +480,62 @@ def test_cli_outputs_equal_reference_cli(ctx, name, tmp_path, monkeypatch):
             got = "".join("##fileDate=<date>\n" if l.startswith("##fileDate=") else l for l in got.splitlines(keepends=True))
             got = got.replace(GOLD + os.sep, "")
         assert got == open(gold).read(), ext
+
+
+def test_extract_inserts_sorted_form_equals_hash_form(ctx):
+    """The shared-memory hash count and the radix sort + run-length form give the same calls."""
+    from trueconsense_b200 import gpu
+
+    ref, _, b = _synth("amplicon_deep")
+    L = len(ref)
+    counts = ctx.pileup_counts(b, L)
+    cands = [int(c) for c in ctx.list_insert_candidates(ctx.call(counts, L, 30, True).flags, L)]
+    positions = np.asarray(sorted(set(cands) | {1, 350, 700, 701, 1200, 2500, L}), np.int32)
+    p_hash = gpu.extractinserts_params()
+    p_sort = gpu.extractinserts_params()
+    p_sort.kernel = 2
+    a = ctx._extract_inserts_raw(b, L, positions, p_hash)
+    s_ = ctx._extract_inserts_raw(b, L, positions, p_sort)
+    assert a == s_
+    assert any(x["n_entries"] > 0 for x in a)
+
+
+def test_span_bound_hint(ctx, orc):
+    """tc_reads_t.max_ref_span: with a bound the span pass is folded into the pileup kernel; same table, same
+    errors; a bound that is too small is rejected."""
+    import copy
+
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    for case in ("amplicon_deep", "paired", "shotgun_indels", "mid_reads"):
+        ref, _, b = _synth(case)
+        assert b.max_ref_span > 0
+        nb = copy.copy(b)
+        nb.max_ref_span = -1
+        with_hint = _pileup(ctx, b, len(ref), 3)
+        without = _pileup(ctx, nb, len(ref), 3)
+        assert np.array_equal(with_hint, without)
+        assert np.array_equal(with_hint, pileup.pileup_counts(b, len(ref), threads=4))
+        assert np.array_equal(ctx.depth(b, len(ref)), with_hint[0])
+    ref, _, b = _synth("paired")
+    small = copy.copy(b)
+    small.max_ref_span = 20
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(small, len(ref))
+    assert ei.value.code == -2
+    # the checks the span pass used to make
+    unsorted = ReadBatch.from_records([dict(pos=50, cigar="10M", seq="A" * 10), dict(pos=10, cigar="10M", seq="A" * 10)])
+    unsorted.max_ref_span = 10
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(unsorted, 100)
+    assert ei.value.code == -3
+    beyond = ReadBatch.from_records([dict(pos=95, cigar="10M", seq="A" * 10)])
+    beyond.max_ref_span = 10
+    with pytest.raises(gpu.TcError) as ei:
+        ctx.pileup_counts(beyond, 100)
+    assert ei.value.code == -7
+    zero = ReadBatch.from_records([dict(pos=5, cigar="4S", seq="ACGT"), dict(pos=7, cigar="10M", seq="A" * 10)])
+    zero.max_ref_span = 10
+    assert ctx.pileup_counts(zero, 100)[0, 7:17].tolist() == [1] * 10

@@ -3,51 +3,66 @@
 // For every candidate position the reference piles up one column with pysam's DEFAULT arguments
 // (Events.py:66): samtools stepper (flag filter 0x704, orphans skipped), max_depth 8000,
 // min_base_quality 13; upper-cases the strings and takes collections.Counter's mode (ties: first
-// encountered).  Here, per candidate column c (one CTA each):
-//   select   reads the region fetch would return and the stepper would pass, in file order;
-//            htslib's depth cap (bam_plp_push: a read is dropped when it starts on the column the
-//            engine is waiting to emit and more than max_depth reads are live) reduces, for a
-//            single-column fetch where every fetched read is still live, to
+// encountered).  Here every candidate column c owns the slots [off, off + (hi - lo)) of an entry table,
+// one slot per read whose start lies in (c - longest span, c], and the work is spread over the whole
+// GPU in tiles of INS_TILE reads:
+//   select   (ins_select_kernel, one CTA per tile) reads the region fetch would return and the stepper
+//            would pass; for each the CIGAR walk to the column, the base-quality test and a 63-bit key
+//            hashing exactly the characters pysam would print, upper-cased (head character, sign and
+//            length of the indel, inserted bases); per tile: number of selected reads, last selected read.
+//   admit    (ins_admit_kernel, one CTA per tile) htslib's depth cap (bam_plp_push: a read is dropped
+//            when it starts on the column the engine is waiting to emit and more than max_depth reads
+//            are live) reduces, for a single-column fetch where every fetched read is still live, to
 //            "admitted  <=>  first selected read at its start coordinate, or fewer than max_depth
-//            selected reads before it";
-//   emit     for every admitted read covering c: CIGAR walk to the column, base-quality test,
-//            and a 64-bit key hashing exactly the characters pysam would print, upper-cased
-//            (head character, sign and length of the indel, inserted bases);
-//   count    keys are radix-sorted per candidate (cub::DeviceSegmentedRadixSort, stable) and
-//            run-length encoded; the longest run wins, ties go to the run whose first entry came
-//            first in the file.  Every member of every run is compared with its run head
-//            character by character, so a hash collision is reported (TC_ERR_RANGE) and can never
-//            silently change a count.
+//            selected reads before it": a rank from the tile prefix; slots that are not admitted
+//            entries get the sentinel key.
+//   count    (ins_count_kernel, one CTA per candidate) the keys are counted in a shared-memory hash table
+//            (count, first slot); the largest count wins, ties go to the key first encountered in file
+//            order.  Every entry is then compared character by character with the first entry of its
+//            key, so a hash collision is reported (TC_ERR_RANGE) and can never silently change a count.
+//            A column with more distinct strings than the table holds falls back to the sorted form:
+//            cub::DeviceSegmentedRadixSort (stable) + run-length encoding (ins_mode_kernel).
 // Not emulated (deviations): htslib's mate-overlap quality rewriting.
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "tc_common.cuh"
 
+constexpr int INS_TILE = 256;               // reads per tile == threads per CTA of the select / admit kernels
+constexpr uint64_t KEY_NONE = ~0ull;        // slot without an admitted entry (real keys have bit 63 clear)
+constexpr int INS_TBL = 4096;               // hash table slots per candidate column (count kernel)
+
 struct ins_args {
     dreads r;
-    const int32_t* span_end;        // [n] pos + reference span
     const int32_t* cand;            // [n_cand] 1-based positions
     int n_cand;
     uint32_t flag_filter; int min_mapq, min_bq, ignore_orphans; long long max_depth;
-    int32_t* range;                 // [n_cand][2] lo, hi read indices
-    const int64_t* seg_off;         // [n_cand+1] entry storage offsets
-    uint64_t* ent_key; uint32_t* ent_idx;           // unsorted keys / entry ids
-    uint32_t* ent_read; int32_t* ent_indel; int32_t* ent_qpos; uint8_t* ent_head;
-    int32_t* seg_count;             // [n_cand] emitted entries
+    int32_t span_hint;              // > 0: caller's upper bound of the longest reference span (tc_reads_t.max_ref_span)
+    int32_t* range;                 // [n_cand][2] lo, hi read indices: the reads with pos in (c - longest span, c]
+    const int64_t* seg_off;         // [n_cand+1] slot offsets; read r of candidate ci owns slot seg_off[ci] + r - lo
+    const int32_t* tile_cand;       // [n_tiles] candidate of every tile
+    const int32_t* tile_first;      // [n_cand+1] first tile of every candidate
+    int32_t* tile_sel;              // [n_tiles] selected reads in the tile
+    int32_t* tile_last;             // [n_tiles] last selected read of the tile, -1 if none
+    uint64_t* ent_key; int32_t* ent_indel; int32_t* ent_qpos; uint8_t* ent_head;
+    uint8_t* ent_sel;               // bit 0: selected (fetched and passed by the stepper), bit 1: yields an entry
+    int32_t* seg_count;             // [n_cand] admitted entries
+    int32_t* overflow;              // [1] some column had more distinct keys than INS_TBL holds
     tc_status* status;
 };
 
-__global__ void span_end_kernel(dreads r, int32_t* __restrict__ span_end, tc_status* status) {
+// longest reference span when the caller gave no bound: one thread per read (also checks the sort order)
+__global__ void max_span_kernel(dreads r, tc_status* status) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r.n) return;
-    if (i > 0 && r.pos[i] < r.pos[i - 1]) atomicCAS(&status->err, 0, TC_ERR_UNSORTED);
     int span = 0;
-    for (uint32_t k = r.cigar_off[i]; k < r.cigar_off[i + 1]; ++k) {
-        uint32_t c = r.cigar[k];
-        if (op_consumes_ref(c & 15u)) span += (int)(c >> 4);
+    if (i < r.n) {
+        if (i > 0 && r.pos[i] < r.pos[i - 1]) atomicCAS(&status->err, 0, TC_ERR_UNSORTED);
+        for (uint32_t k = r.cigar_off[i]; k < r.cigar_off[i + 1]; ++k) {
+            uint32_t c = r.cigar[k];
+            if (op_consumes_ref(c & 15u)) span += (int)(c >> 4);
+        }
     }
-    span_end[i] = r.pos[i] + span;
-    atomicMax(&status->max_span, span);
+    span = __reduce_max_sync(0xffffffffu, span);
+    if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(&status->max_span, span);
 }
 
 // reads that can overlap column c: pos in (c - max_span, c]
@@ -55,7 +70,7 @@ __global__ void cand_range_kernel(ins_args a) {
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= a.n_cand) return;
     const int c = a.cand[ci] - 1;
-    const int ms = max(a.status->max_span, 1);
+    const int ms = max(a.span_hint > 0 ? a.span_hint : a.status->max_span, 1);
     auto lower = [&](int v) {   // first read with pos >= v
         int64_t lo = 0, hi = a.r.n;
         while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a.r.pos[mid] < v) lo = mid + 1; else hi = mid; }
@@ -86,74 +101,41 @@ __device__ __forceinline__ char ins_char(const ins_args& a, uint32_t read, int q
     return base_char_upper(seq_code(a.r.seq4 + a.r.seq_off[read], q), rev);
 }
 
-__global__ void __launch_bounds__(1024) ins_select_emit_kernel(ins_args a) {
-    __shared__ int wsum[32];
-    __shared__ int wmax[32];
-    __shared__ long long sel_base_s;
-    __shared__ int emit_base_s;
-    __shared__ int last_sel_s;
-    const int ci = blockIdx.x;
+// select: one thread per read of the candidate's range
+__global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
+    __shared__ int wlast[INS_TILE / 32];
+    const int tile = blockIdx.x;
+    const int ci = a.tile_cand[tile];
     const int c = a.cand[ci] - 1;
     const int lo = a.range[2 * ci], hi = a.range[2 * ci + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t off = a.seg_off[ci];
-    if (threadIdx.x == 0) { sel_base_s = 0; emit_base_s = 0; last_sel_s = -1; }
-    __syncthreads();
-    for (int t0 = lo; t0 < hi; t0 += 1024) {
-        const int r = t0 + threadIdx.x;
-        bool sel = false; int pos = 0, end = 0;
-        if (r < hi) {
-            pos = a.r.pos[r]; end = a.span_end[r];
-            uint32_t fl = a.r.flag[r];
-            bool pass = !(fl & (a.flag_filter | 4u)) && !(a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[r] < a.min_mapq) &&
-                        !(a.ignore_orphans && (fl & 1u) && !(fl & 2u));
-            bool fetched = pos <= c && (end > c || (end == pos && pos == c));   // BAI query: pos < c+1 && endpos > c
-            sel = pass && fetched;
-        }
-        // nearest earlier selected read (inclusive max-scan of selected indices)
-        int idx = sel ? r : -1;
-        int m = idx;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, m, o); if (lane >= o) m = max(m, t); }
-        int prev_in_warp = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) prev_in_warp = -1;
-        if (lane == 31) wmax[warp] = m;
-        unsigned bal = __ballot_sync(0xffffffffu, sel);
-        int sel_before_w = __popc(bal & ((1u << lane) - 1));
-        if (lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        int prev_sel = last_sel_s, sel_before = 0, sel_total = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < warp) { prev_sel = max(prev_sel, wmax[w]); sel_before += wsum[w]; }
-            sel_total += wsum[w];
-        }
-        prev_sel = max(prev_sel, prev_in_warp);
-        int tile_last = last_sel_s;
-        for (int w = 0; w < 32; ++w) tile_last = max(tile_last, wmax[w]);
-        bool first_at_start = sel && (prev_sel < 0 || a.r.pos[prev_sel] != pos);
-        // a read without reference span is only linked into htslib's list when it opens its start coordinate;
-        // it never yields an entry, and it only counts towards the live total when linked
-        bool zero_span = sel && end == pos;
-        long long rank = sel_base_s + sel_before_w + sel_before;
-        bool admitted = sel && (first_at_start || rank < a.max_depth);
-        // (zero-span reads that are not first at their start are not counted; the approximation only matters
-        //  when such reads sit exactly on a candidate column and the cap binds at the same time)
-        bool emit = false; int indel = 0, qpos = 0; char head = 0; uint64_t key = 0;
-        if (admitted && !zero_span && end > c) {
+    const int r = lo + (tile - a.tile_first[ci]) * INS_TILE + threadIdx.x;
+    bool sel = false, emit = false;
+    if (r < hi) {
+        const int pos = a.r.pos[r];
+        if (r > 0 && pos < a.r.pos[r - 1]) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
+        const uint32_t fl = a.r.flag[r];
+        const bool pass = !(fl & (a.flag_filter | 4u)) && !(a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[r] < a.min_mapq) &&
+                          !(a.ignore_orphans && (fl & 1u) && !(fl & 2u));
+        int indel = 0, qpos = 0; char head = 0; uint64_t key = KEY_NONE;
+        if (pass) {
+            // CIGAR walk up to the column.  BAI query: pos < c+1 && endpos > c, where a read without reference
+            // span has endpos = pos + 1
             const uint32_t c0 = a.r.cigar_off[r];
             const int n = (int)(a.r.cigar_off[r + 1] - c0);
             const uint32_t* cig = a.r.cigar + c0;
-            const bool rev = (a.r.flag[r] & 16u) != 0;
+            const bool rev = (fl & 16u) != 0;
             const int lq = a.r.l_seq[r];
             int x = pos, y = 0;
+            bool found = false;
             for (int k = 0; k < n; ++k) {
-                uint32_t cc = cig[k]; uint32_t op = cc & 15u; int l = (int)(cc >> 4);
+                const uint32_t cc = cig[k]; const uint32_t op = cc & 15u; const int l = (int)(cc >> 4);
                 if (!op_consumes_ref(op)) { if (op == OP_I || op == OP_S) y += l; continue; }
                 if (c < x + l) {
-                    bool match = op_is_match(op);
+                    found = true;
+                    const bool match = op_is_match(op);
                     qpos = match ? y + (c - x) : y;
                     if (c == x + l - 1) indel = peek_indel(cig, n, k);
-                    int qv = (qpos < lq) ? (int)a.r.qual[8ull * a.r.seq_off[r] + qpos] : 0;
+                    const int qv = (qpos < lq) ? (int)a.r.qual[8ull * a.r.seq_off[r] + qpos] : 0;
                     if (qv >= a.min_bq) {
                         emit = true;
                         if (match) head = (qpos < lq) ? base_char_upper(seq_code(a.r.seq4 + a.r.seq_off[r], qpos), rev) : 'N';
@@ -164,47 +146,153 @@ __global__ void __launch_bounds__(1024) ins_select_emit_kernel(ins_args a) {
                 if (op_is_match(op)) y += l;
                 x += l;
             }
+            // a read without reference span is only linked into htslib's list when it sits on the column; it never
+            // yields an entry, and it counts towards the live total like any selected read
+            sel = found || (x == pos && pos == c);
             if (emit) {
                 key = mix_key(0x7463696e73ull, (uint64_t)(uint8_t)head);
                 key = mix_key(key, (uint64_t)(uint32_t)indel);
                 for (int j = 1; j <= indel; ++j) key = mix_key(key, (uint64_t)(uint8_t)ins_char(a, r, qpos, j, rev));
+                key &= 0x7fffffffffffffffull;
             }
         }
-        __syncthreads();
-        unsigned ebal = __ballot_sync(0xffffffffu, emit);
-        int emit_before_w = __popc(ebal & ((1u << lane) - 1));
-        if (lane == 0) wsum[warp] = __popc(ebal);
-        __syncthreads();
-        int emit_before = 0, emit_total = 0;
-        for (int w = 0; w < 32; ++w) { if (w < warp) emit_before += wsum[w]; emit_total += wsum[w]; }
-        if (emit) {
-            int64_t slot = off + emit_base_s + emit_before + emit_before_w;
-            a.ent_key[slot] = key; a.ent_idx[slot] = (uint32_t)slot;
-            a.ent_read[slot] = (uint32_t)r; a.ent_indel[slot] = indel; a.ent_qpos[slot] = qpos; a.ent_head[slot] = (uint8_t)head;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { sel_base_s += sel_total; emit_base_s += emit_total; last_sel_s = tile_last; }
-        __syncthreads();
+        const int64_t slot = a.seg_off[ci] + (r - lo);
+        a.ent_key[slot] = key; a.ent_indel[slot] = indel; a.ent_qpos[slot] = qpos; a.ent_head[slot] = (uint8_t)head;
+        a.ent_sel[slot] = (uint8_t)((sel ? 1 : 0) | (emit ? 2 : 0));
     }
-    if (threadIdx.x == 0) a.seg_count[ci] = emit_base_s;
+    const int nsel = __syncthreads_count(sel);
+    int last = __reduce_max_sync(0xffffffffu, sel ? r : -1);
+    if ((threadIdx.x & 31) == 0) wlast[threadIdx.x >> 5] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < INS_TILE / 32; ++w) last = max(last, wlast[w]);
+        a.tile_sel[tile] = nsel;
+        a.tile_last[tile] = last;
+    }
 }
 
-__device__ __forceinline__ bool same_entry(const ins_args& a, uint32_t e1, uint32_t e2) {
+// admit: the depth cap, from the rank of every selected read among the candidate's selected reads
+__global__ void __launch_bounds__(INS_TILE) ins_admit_kernel(ins_args a) {
+    __shared__ int wsum[INS_TILE / 32], wlast[INS_TILE / 32];
+    __shared__ long long base_s;
+    __shared__ int prev_s;
+    const int tile = blockIdx.x;
+    const int ci = a.tile_cand[tile];
+    const int lo = a.range[2 * ci], hi = a.range[2 * ci + 1];
+    const int t0 = a.tile_first[ci];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {        // selected reads and last selected read of the candidate's earlier tiles
+        long long base = 0; int prev = -1;
+        for (int t = t0 + lane; t < tile; t += 32) { base += a.tile_sel[t]; prev = max(prev, a.tile_last[t]); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { base += __shfl_xor_sync(0xffffffffu, base, o); prev = max(prev, __shfl_xor_sync(0xffffffffu, prev, o)); }
+        if (lane == 0) { base_s = base; prev_s = prev; }
+    }
+    const int r = lo + (tile - t0) * INS_TILE + threadIdx.x;
+    const int64_t slot = a.seg_off[ci] + (r - lo);
+    const uint8_t es = r < hi ? a.ent_sel[slot] : 0;
+    const bool sel = (es & 1) != 0, emit = (es & 2) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    int m = sel ? r : -1;       // nearest selected read at or before this one, within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, m, o); if (lane >= o) m = max(m, t); }
+    int prev = __shfl_up_sync(0xffffffffu, m, 1);
+    if (lane == 0) prev = -1;
+    if (lane == 31) wlast[warp] = m;
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    long long rank = base_s + __popc(bal & ((1u << lane) - 1));
+    prev = max(prev, prev_s);
+    for (int w = 0; w < warp; ++w) { rank += wsum[w]; prev = max(prev, wlast[w]); }
+    bool admitted = false;
+    if (sel) {
+        const bool first_at_start = prev < 0 || a.r.pos[prev] != a.r.pos[r];
+        admitted = first_at_start || rank < a.max_depth;
+    }
+    if (emit && !admitted) a.ent_key[slot] = KEY_NONE;
+    const int n_adm = __syncthreads_count(emit && admitted);
+    if (threadIdx.x == 0 && n_adm) atomicAdd(&a.seg_count[ci], n_adm);
+}
+
+__device__ __forceinline__ bool same_entry(const ins_args& a, int lo, int64_t off, uint32_t e1, uint32_t e2) {
     if (a.ent_head[e1] != a.ent_head[e2] || a.ent_indel[e1] != a.ent_indel[e2]) return false;
-    int indel = a.ent_indel[e1];
-    uint32_t r1 = a.ent_read[e1], r2 = a.ent_read[e2];
-    bool v1 = (a.r.flag[r1] & 16u) != 0, v2 = (a.r.flag[r2] & 16u) != 0;
+    const int indel = a.ent_indel[e1];
+    const uint32_t r1 = (uint32_t)(lo + (int64_t)e1 - off), r2 = (uint32_t)(lo + (int64_t)e2 - off);
+    const bool v1 = (a.r.flag[r1] & 16u) != 0, v2 = (a.r.flag[r2] & 16u) != 0;
     for (int j = 1; j <= indel; ++j)
         if (ins_char(a, r1, a.ent_qpos[e1], j, v1) != ins_char(a, r2, a.ent_qpos[e2], j, v2)) return false;
     return true;
 }
 
-// one CTA per candidate over its sorted keys
+__device__ __forceinline__ void write_call(const ins_args& a, int ci, int m, unsigned long long best, tc_insert_call_t* calls) {
+    const int64_t off = a.seg_off[ci];
+    tc_insert_call_t out;
+    out.pos = a.cand[ci]; out.n_entries = m; out.mode_count = 0; out.first_read = -1; out.head = 0; out.indel = 0; out.bases_off = -1;
+    if (m > 0) {
+        const uint32_t e = (uint32_t)off + (uint32_t)(0xffffffffull - (best & 0xffffffffull));
+        out.mode_count = (int32_t)(best >> 32);
+        out.first_read = (int32_t)(a.range[2 * ci] + (int64_t)e - off);
+        out.head = a.ent_head[e];
+        out.indel = a.ent_indel[e];
+        out.bases_off = (int64_t)e;         // entry id for now; the host turns it into a buffer offset
+    }
+    calls[ci] = out;
+}
+
+// count: one CTA per candidate, keys counted in a shared-memory hash table (linear probing)
+__global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_call_t* __restrict__ calls) {
+    extern __shared__ __align__(16) unsigned char ins_smem[];
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(ins_smem);     // [INS_TBL]
+    unsigned int* tcnt = reinterpret_cast<unsigned int*>(tkey + INS_TBL);           // [INS_TBL]
+    unsigned int* tfirst = tcnt + INS_TBL;                                          // [INS_TBL] first slot (file order) of the key
+    __shared__ unsigned long long best_s;
+    __shared__ int over_s;
+    const int ci = blockIdx.x;
+    const int64_t off = a.seg_off[ci];
+    const int lo = a.range[2 * ci];
+    const int n = a.range[2 * ci + 1] - lo;
+    for (int i = threadIdx.x; i < INS_TBL; i += blockDim.x) { tkey[i] = KEY_NONE; tcnt[i] = 0; tfirst[i] = 0xffffffffu; }
+    if (threadIdx.x == 0) { best_s = 0ull; over_s = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = a.ent_key[off + i];
+        if (k == KEY_NONE) continue;
+        unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
+        int probes = 0;
+        for (;;) {
+            const unsigned long long old = atomicCAS(&tkey[h], KEY_NONE, k);
+            if (old == KEY_NONE || old == k) { atomicAdd(&tcnt[h], 1u); atomicMin(&tfirst[h], (unsigned)i); break; }
+            h = (h + 1) & (INS_TBL - 1);
+            if (++probes >= INS_TBL * 7 / 8) { over_s = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (over_s) { if (threadIdx.x == 0) atomicExch(a.overflow, 1); return; }
+    // every entry against the first entry of its key
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = a.ent_key[off + i];
+        if (k == KEY_NONE) continue;
+        unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
+        while (tkey[h] != k) h = (h + 1) & (INS_TBL - 1);
+        const unsigned f = tfirst[h];
+        if (f != (unsigned)i && !same_entry(a, lo, off, (uint32_t)(off + f), (uint32_t)(off + i))) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+    }
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < INS_TBL; i += blockDim.x)
+        if (tcnt[i]) best = max(best, ((unsigned long long)tcnt[i] << 32) | (0xffffffffull - (unsigned long long)tfirst[i]));
+    atomicMax(&best_s, best);
+    __syncthreads();
+    if (threadIdx.x == 0) write_call(a, ci, a.seg_count[ci], best_s, calls);
+}
+
+// sorted form of the count: one CTA per candidate over its radix-sorted keys (KEY_NONE slots sort last)
 __global__ void __launch_bounds__(1024) ins_mode_kernel(ins_args a, const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
                                                         tc_insert_call_t* __restrict__ calls) {
     __shared__ unsigned long long best_s;
     const int ci = blockIdx.x;
     const int64_t off = a.seg_off[ci];
+    const int lo_read = a.range[2 * ci];
     const int m = a.seg_count[ci];
     if (threadIdx.x == 0) best_s = 0ull;
     __syncthreads();
@@ -216,7 +304,7 @@ __global__ void __launch_bounds__(1024) ins_mode_kernel(ins_args a, const uint64
         while (lo < hi) { int mid = (lo + hi) >> 1; if (skey[off + mid] < k) lo = mid + 1; else hi = mid; }
         const int head = lo;
         if (head != i) {
-            if (!same_entry(a, sidx[off + head], sidx[off + i])) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+            if (!same_entry(a, lo_read, off, sidx[off + head], sidx[off + i])) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
         } else {
             int l2 = i, h2 = m;
             while (l2 < h2) { int mid = (l2 + h2) >> 1; if (skey[off + mid] <= k) l2 = mid + 1; else h2 = mid; }
@@ -229,25 +317,12 @@ __global__ void __launch_bounds__(1024) ins_mode_kernel(ins_args a, const uint64
     }
     atomicMax(&best_s, best);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        tc_insert_call_t out;
-        out.pos = a.cand[ci]; out.n_entries = m; out.mode_count = 0; out.first_read = -1; out.head = 0; out.indel = 0; out.bases_off = -1;
-        if (m > 0) {
-            unsigned long long v = best_s;
-            uint32_t e = (uint32_t)off + (uint32_t)(0xffffffffull - (v & 0xffffffffull));
-            out.mode_count = (int32_t)(v >> 32);
-            out.first_read = (int32_t)a.ent_read[e];
-            out.head = a.ent_head[e];
-            out.indel = a.ent_indel[e];
-            out.bases_off = (int64_t)e;         // entry id for now; the host turns it into a buffer offset
-        }
-        calls[ci] = out;
-    }
+    if (threadIdx.x == 0) write_call(a, ci, m, best_s, calls);
 }
 
-__global__ void seg_end_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ cnt, int64_t* __restrict__ end, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) end[i] = off[i] + cnt[i];
+__global__ void iota_kernel(uint32_t* __restrict__ idx, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (uint32_t)i;
 }
 
 __global__ void ins_bases_kernel(ins_args a, const tc_insert_call_t* __restrict__ calls, const int64_t* __restrict__ entry_of,
@@ -256,7 +331,7 @@ __global__ void ins_bases_kernel(ins_args a, const tc_insert_call_t* __restrict_
     const tc_insert_call_t c = calls[ci];
     if (c.indel <= 0) return;
     const uint32_t e = (uint32_t)entry_of[ci];
-    const uint32_t r = a.ent_read[e];
+    const uint32_t r = (uint32_t)c.first_read;
     const bool rev = (a.r.flag[r] & 16u) != 0;
     for (int j = threadIdx.x; j < c.indel; j += blockDim.x) bases[c.bases_off + j] = (uint8_t)ins_char(a, r, a.ent_qpos[e], j + 1, rev);
 }
@@ -279,72 +354,110 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     const int64_t n = a.r.n;
     for (int i = 0; i < n_cand; ++i) { calls[i].pos = cand_pos[i]; calls[i].n_entries = 0; calls[i].mode_count = 0; calls[i].first_read = -1; calls[i].head = 0; calls[i].indel = 0; calls[i].bases_off = -1; }
     if (n == 0) return TC_OK;
-    int32_t* d_end = (int32_t*)tc_dev_buf(ctx, SLOT_SPAN_END, 4 * (size_t)n);
     tc_status* d_status = (tc_status*)tc_dev_buf(ctx, SLOT_STATUS, sizeof(tc_status));
     int32_t* d_cand = (int32_t*)tc_dev_buf(ctx, SLOT_INS_A, 4 * (size_t)n_cand);
     int32_t* d_range = (int32_t*)tc_dev_buf(ctx, SLOT_INS_B, 8 * (size_t)n_cand);
-    if (!d_end || !d_status || !d_cand || !d_range) return TC_ERR_NOMEM;
+    if (!d_status || !d_cand || !d_range) return TC_ERR_NOMEM;
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     TC_CUDA(cudaMemcpyAsync(d_cand, cand_pos, 4 * (size_t)n_cand, cudaMemcpyHostToDevice, s));
-    span_end_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.r, d_end, d_status);
-    TC_LAUNCH_CHECK();
-    a.span_end = d_end; a.cand = d_cand; a.n_cand = n_cand; a.range = d_range; a.status = d_status;
+    ctx->h2d_bytes += 4 * (int64_t)n_cand;
+    a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
+    if (a.span_hint == 0) {
+        max_span_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.r, d_status);
+        TC_LAUNCH_CHECK();
+    }
+    a.cand = d_cand; a.n_cand = n_cand; a.range = d_range; a.status = d_status;
     a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality; a.ignore_orphans = p->ignore_orphans;
     a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
     cand_range_kernel<<<(n_cand + 127) / 128, 128, 0, s>>>(a);
     TC_LAUNCH_CHECK();
+    // host side of the layout: slot offsets and the tile table (a few integers per candidate)
     int32_t* h_range = (int32_t*)malloc(8 * (size_t)n_cand);
     int64_t* h_off = (int64_t*)malloc(8 * ((size_t)n_cand + 1));
-    if (!h_range || !h_off) { free(h_range); free(h_off); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
-#define INS_FREE() do { free(h_range); free(h_off); } while (0)
-    cudaError_t e = cudaMemcpyAsync(h_range, d_range, 8 * (size_t)n_cand, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e, "range readback"); }
-    h_off[0] = 0;
-    for (int i = 0; i < n_cand; ++i) h_off[i + 1] = h_off[i] + (h_range[2 * i + 1] - h_range[2 * i]);
+    int32_t* h_tfirst = (int32_t*)malloc(4 * ((size_t)n_cand + 1));
+    int32_t* h_tcand = NULL;
+    int64_t* h_entry = NULL;
+    if (!h_range || !h_off || !h_tfirst) { free(h_range); free(h_off); free(h_tfirst); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
+#define INS_FREE() do { free(h_range); free(h_off); free(h_tfirst); free(h_tcand); free(h_entry); } while (0)
+#define INS_CUDA(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e__, what); } } while (0)
+    INS_CUDA(cudaMemcpyAsync(h_range, d_range, 8 * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "range readback");
+    INS_CUDA(cudaStreamSynchronize(s), "range readback");
+    ctx->d2h_bytes += 8 * (int64_t)n_cand;
+    h_off[0] = 0; h_tfirst[0] = 0;
+    for (int i = 0; i < n_cand; ++i) {
+        const int64_t len = h_range[2 * i + 1] - h_range[2 * i];
+        h_off[i + 1] = h_off[i] + len;
+        h_tfirst[i + 1] = h_tfirst[i] + (int32_t)((len + INS_TILE - 1) / INS_TILE);
+    }
     const int64_t total = h_off[n_cand];
+    const int n_tiles = h_tfirst[n_cand];
     if (total >= 0x7fffffffll) { INS_FREE(); return tc_fail(ctx, TC_ERR_CAPACITY, "too many candidate column entries (%lld)", (long long)total); }
-    const size_t T = (size_t)(total > 0 ? total : 1);
-    int64_t* d_off = (int64_t*)tc_dev_buf(ctx, SLOT_INS_C, 8 * ((size_t)n_cand + 1));
-    // one slab: keys, sorted keys, ids, sorted ids, read, indel, qpos, head, counts
-    size_t bytes = T * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 1) + 4 * (size_t)n_cand + 64;
+    h_tcand = (int32_t*)malloc(4 * (size_t)(n_tiles > 0 ? n_tiles : 1));
+    if (!h_tcand) { INS_FREE(); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
+    for (int i = 0; i < n_cand; ++i) for (int t = h_tfirst[i]; t < h_tfirst[i + 1]; ++t) h_tcand[t] = i;
+    const size_t T = (size_t)(total > 0 ? total : 1), NT = (size_t)(n_tiles > 0 ? n_tiles : 1);
+    // one slab: keys, indel, qpos, head, sel per slot; tile tables; per-candidate offsets, counts
+    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + 256;
     uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
     tc_insert_call_t* d_calls = (tc_insert_call_t*)tc_dev_buf(ctx, SLOT_INS_E, sizeof(tc_insert_call_t) * (size_t)n_cand);
-    if (!d_off || !slab || !d_calls) { INS_FREE(); return TC_ERR_NOMEM; }
-    uint64_t* d_key = (uint64_t*)slab; uint64_t* d_skey = d_key + T;
-    uint32_t* d_idx = (uint32_t*)(d_skey + T); uint32_t* d_sidx = d_idx + T;
-    a.ent_read = d_sidx + T; a.ent_indel = (int32_t*)(a.ent_read + T); a.ent_qpos = a.ent_indel + T;
-    a.seg_count = a.ent_qpos + T; a.ent_head = (uint8_t*)(a.seg_count + n_cand);
-    a.ent_key = d_key; a.ent_idx = d_idx; a.seg_off = d_off;
-    e = cudaMemcpyAsync(d_off, h_off, 8 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e, "offset upload"); }
-    ins_select_emit_kernel<<<n_cand, 1024, 0, s>>>(a);
-    ctx->launches++;
-    // segments for the sort: [off[i], off[i] + count[i])
-    int64_t* d_seg_end = (int64_t*)tc_dev_buf(ctx, SLOT_INS_F, 8 * (size_t)n_cand);
-    if (!d_seg_end) { INS_FREE(); return TC_ERR_NOMEM; }
-    seg_end_kernel<<<(n_cand + 127) / 128, 128, 0, s>>>(d_off, a.seg_count, d_seg_end, n_cand);
-    ctx->launches++;
-    size_t tmp_bytes = 0;
-    e = cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_skey, d_idx, d_sidx, (int64_t)total, n_cand, d_off, d_seg_end, 0, 64, s);
-    if (e != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e, "cub sort sizing"); }
-    void* d_tmp = tc_dev_buf(ctx, SLOT_INS_G, tmp_bytes + 16);
-    if (!d_tmp) { INS_FREE(); return TC_ERR_NOMEM; }
-    e = cub::DeviceSegmentedRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_skey, d_idx, d_sidx, (int64_t)total, n_cand, d_off, d_seg_end, 0, 64, s);
-    if (e != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e, "cub segmented radix sort"); }
-    ctx->launches++;
-    ins_mode_kernel<<<n_cand, 1024, 0, s>>>(a, d_skey, d_sidx, d_calls);
-    ctx->launches++;
-    e = cudaMemcpyAsync(calls, d_calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e, "insert calls readback"); }
+    if (!slab || !d_calls) { INS_FREE(); return TC_ERR_NOMEM; }
+    uint64_t* d_key = (uint64_t*)slab;
+    int64_t* d_off = (int64_t*)(d_key + T);
+    a.ent_indel = (int32_t*)(d_off + n_cand + 1); a.ent_qpos = a.ent_indel + T;
+    int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
+    a.tile_sel = d_tfirst + n_cand + 1; a.tile_last = a.tile_sel + NT;
+    a.seg_count = a.tile_last + NT; a.overflow = a.seg_count + n_cand;
+    a.ent_head = (uint8_t*)(a.overflow + 1); a.ent_sel = a.ent_head + T;
+    a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst;
+    INS_CUDA(cudaMemcpyAsync(d_off, h_off, 8 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "offset upload");
+    INS_CUDA(cudaMemcpyAsync(d_tfirst, h_tfirst, 4 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "tile table upload");
+    if (n_tiles) INS_CUDA(cudaMemcpyAsync(d_tcand, h_tcand, 4 * (size_t)n_tiles, cudaMemcpyHostToDevice, s), "tile table upload");
+    INS_CUDA(cudaMemsetAsync(a.seg_count, 0, 4 * ((size_t)n_cand + 1), s), "memset");
+    ctx->h2d_bytes += 12 * ((int64_t)n_cand + 1) + 4 * (int64_t)n_tiles;
+    if (n_tiles) {
+        ins_select_kernel<<<n_tiles, INS_TILE, 0, s>>>(a);
+        ctx->launches++;
+        ins_admit_kernel<<<n_tiles, INS_TILE, 0, s>>>(a);
+        ctx->launches++;
+    }
+    bool sorted_form = p->kernel == 2;
+    const size_t tbl_smem = (size_t)INS_TBL * 16;
+    int32_t h_over = 0;
+    if (!sorted_form) {
+        INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
+        ins_count_kernel<<<n_cand, 1024, tbl_smem, s>>>(a, d_calls);
+        ctx->launches++;
+        INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
+    }
+    INS_CUDA(cudaMemcpyAsync(calls, d_calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "insert calls readback");
+    INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
+    INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
+    ctx->d2h_bytes += (int64_t)sizeof(tc_insert_call_t) * n_cand + (int64_t)sizeof(tc_status) + 4;
+    if (sorted_form || h_over) {
+        // radix sort + run-length encoding over the same slots
+        uint8_t* slab2 = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_C, T * (8 + 4 + 4) + 64);
+        if (!slab2) { INS_FREE(); return TC_ERR_NOMEM; }
+        uint64_t* d_skey = (uint64_t*)slab2; uint32_t* d_idx = (uint32_t*)(d_skey + T); uint32_t* d_sidx = d_idx + T;
+        iota_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_idx, (int64_t)total);
+        ctx->launches++;
+        size_t tmp_bytes = 0;
+        INS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_skey, d_idx, d_sidx, (int64_t)total, n_cand, d_off, d_off + 1, 0, 64, s), "cub sort sizing");
+        void* d_tmp = tc_dev_buf(ctx, SLOT_INS_G, tmp_bytes + 16);
+        if (!d_tmp) { INS_FREE(); return TC_ERR_NOMEM; }
+        INS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_skey, d_idx, d_sidx, (int64_t)total, n_cand, d_off, d_off + 1, 0, 64, s), "cub segmented radix sort");
+        ctx->launches++;
+        ins_mode_kernel<<<n_cand, 1024, 0, s>>>(a, d_skey, d_sidx, d_calls);
+        ctx->launches++;
+        INS_CUDA(cudaMemcpyAsync(calls, d_calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "insert calls readback");
+        INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
+        INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
+    }
     tc_status st; memcpy(&st, ctx->host_status, sizeof(st));
     if (st.err == TC_ERR_UNSORTED) { INS_FREE(); return tc_fail(ctx, TC_ERR_UNSORTED, "Unsorted input. Pileup aborts"); }
     if (st.err) { INS_FREE(); return tc_fail(ctx, st.err, "insertion key collision or device-side failure %d", st.err); }
     // lay the winners' inserted characters out in the caller's buffer
     int64_t need = 0;
-    int64_t* h_entry = (int64_t*)malloc(8 * (size_t)n_cand);
+    h_entry = (int64_t*)malloc(8 * (size_t)n_cand);
     if (!h_entry) { INS_FREE(); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
     for (int i = 0; i < n_cand; ++i) {
         h_entry[i] = calls[i].bases_off;
@@ -358,7 +471,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
             int64_t* d_entry = (int64_t*)tc_dev_buf(ctx, SLOT_TMP_B, 8 * (size_t)n_cand);
             if (!d_bases || !d_entry) rc = TC_ERR_NOMEM;
             else {
-                e = cudaMemcpyAsync(d_entry, h_entry, 8 * (size_t)n_cand, cudaMemcpyHostToDevice, s);
+                cudaError_t e = cudaMemcpyAsync(d_entry, h_entry, 8 * (size_t)n_cand, cudaMemcpyHostToDevice, s);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyHostToDevice, s);
                 if (e == cudaSuccess) {
                     ins_bases_kernel<<<n_cand, 128, 0, s>>>(a, d_calls, d_entry, d_bases);
@@ -367,12 +480,13 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
                 }
                 if (e == cudaSuccess) e = cudaStreamSynchronize(s);
                 if (e != cudaSuccess) rc = tc_cuda_fail(ctx, e, "inserted bases readback");
+                ctx->d2h_bytes += need;
             }
         }
     }
-    free(h_entry);
     INS_FREE();
 #undef INS_FREE
+#undef INS_CUDA
     if (rc == TC_OK) { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) rc = tc_cuda_fail(ctx, le, "insert kernels"); }
     return rc;
 }

@@ -216,6 +216,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality;
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
+    a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
     const bool per_entry = p->min_base_quality > 0;
     int variant = p->kernel;
     if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? 3 : 1;
@@ -225,9 +226,13 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
         if (variant != 1) {
-            // coverage ends, span statistics and the sortedness / range checks: one thread per read
-            depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
-            TC_LAUNCH_CHECK();
+            // coverage ends, span statistics and the sortedness / range checks: one thread per read — unless the
+            // caller bounded the longest span, then variant 3 does all of that while it walks the CIGARs anyway
+            if (variant != 3 || a.span_hint == 0) {
+                a.span_hint = 0;
+                depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
+                TC_LAUNCH_CHECK();
+            }
             rc = variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_swar_launch(ctx, a, s);
             if (rc) return rc;
         } else {
@@ -269,6 +274,8 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
             return tc_fail(ctx, TC_ERR_DEPTH_CAP, "%lld reads with a base-quality filter: the depth cap %lld may bind and is not emulated by the bulk kernel",
                            (long long)a.r.n, (long long)p->max_depth);
     }
+    if (st.err == 0 && reads->max_ref_span > 0 && st.max_span > reads->max_ref_span)
+        return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t.max_ref_span = %d but a read spans %d reference columns", reads->max_ref_span, st.max_span);
     return status_to_rc(ctx, st, p);
 }
 
@@ -302,7 +309,7 @@ TC_API int tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, con
     TC_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(int32_t) * ((size_t)L + 1), s));
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = 0; a.ignore_orphans = p->ignore_orphans;
-    a.counts = nullptr; a.diff = d_diff; a.status = d_status;
+    a.counts = nullptr; a.diff = d_diff; a.status = d_status; a.span_hint = 0;
     if (d.n > 0) {
         depth_diff_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, s>>>(a);
         TC_LAUNCH_CHECK();

@@ -10,6 +10,7 @@ struct pileup_args {
     int32_t* counts;        // [8][L]
     int32_t* diff;          // [L+1]
     tc_status* status;
+    int32_t span_hint;      // tc_reads_t.max_ref_span (0 = unknown: a span pass finds it)
 };
 
 __device__ __forceinline__ bool read_passes(const pileup_args& a, int64_t r) {

@@ -71,7 +71,7 @@ __device__ __forceinline__ uint32_t clear_multibit(uint32_t w) {
     return w & ~(m * 15u);
 }
 
-struct walk_out { int nd, b_first, last_end; };
+struct walk_out { int nd, b_first, last_end, x_end; };
 
 extern __shared__ __align__(16) uint32_t smem[];
 
@@ -138,7 +138,7 @@ __device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nop
             if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); nops = 0; nd = 0; b_first = INT_MAX; }
         }
     }
-    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end;
+    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end; o.x_end = x;
     return o;
 }
 
@@ -199,7 +199,7 @@ __device__ __forceinline__ walk_out walk_read_common(const uint32_t cs, const in
         }
         if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
     }
-    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end;
+    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end; o.x_end = x;
     return o;
 }
 
@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     const int L = a.L;
 
     // which geometry handles this batch: the narrowest whose slack is usable
-    const int ms = (max(a.status->max_span, 1) + 7) & ~7;
+    // the longest reference span: the caller's bound (tc_reads_t.max_ref_span) or what the span pass found
+    const bool fold = a.span_hint > 0;      // no span pass ran: this kernel also does its checks and the coverage ends
+    const int ms = (max(fold ? a.span_hint : a.status->max_span, 1) + 7) & ~7;
     const int slack64 = (512 - ms - 8) & ~7, slack128 = (1024 - ms - 8) & ~7;
     const bool mine = (WC == 64) ? (slack64 >= MIN_SLACK) : (slack64 < MIN_SLACK);
     if (!mine) return;
@@ -248,6 +250,8 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     }
     int w0 = INT_MIN, run_reads = 0;
     const uint32_t row = rows + 4u * lane * RS;
+    int prev_pos = (fold && r > 0 && r < r_end) ? a.r.pos[r - 1] : INT_MIN;     // sort-order check across sub-tiles
+    int my_max_span = 0, my_zero_span = 0;
 
     auto flush = [&]() {
         __syncwarp();
@@ -320,8 +324,13 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 w0 = INT_MIN; run_reads = 0;
                 continue;
             }
-            // a negative position (flagged by the span pass), or one read larger than the staging buffers
+            // a negative position (TC_ERR_RANGE), or one read larger than the staging buffers
             if (inwin0 && lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
+            if (fold && lane == 0) {
+                if (p0 < prev_pos) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
+                if (p0 < 0 && passes) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+            }
+            prev_pos = p0;
             r += 1;
             continue;
         }
@@ -428,6 +437,25 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         if (cig_exotic) wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
         else wo = walk_read_common<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
 
+        // ---- without a span pass: sort order, range, span statistics and the two ends of every read's span in the
+        // coverage difference array (adds to the same column are combined inside the warp first)
+        if (fold) {
+            int pprev = __shfl_up_sync(FULL, p, 1);
+            if (lane == 0) pprev = prev_pos;
+            if (lane < n && p < pprev) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
+            prev_pos = __shfl_sync(FULL, p, n - 1);
+            const int span = act ? wo.x_end - x0 : 0;
+            const bool bad = act && (p >= L || p + span > L);
+            if (bad) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+            const bool has = act && span > 0 && !bad;
+            my_max_span = max(my_max_span, span);
+            my_zero_span += (act && span == 0) ? 1 : 0;
+            const unsigned g0 = __match_any_sync(FULL, has ? p : -1 - lane);
+            if (has && (__ffs(g0) - 1) == lane) atomicAdd(&a.diff[p], __popc(g0));
+            const unsigned g1 = __match_any_sync(FULL, has ? p + span : -1 - lane);
+            if (has && (__ffs(g1) - 1) == lane) atomicAdd(&a.diff[p + span], -__popc(g1));
+        }
+
         // ---- expand A: one row word per iteration; a non-zero word starts a new regime (end column, shift)
         const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
         {
@@ -512,6 +540,14 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         run_reads += n;
     }
     if (run_reads > 0) flush();
+    if (fold) {
+        my_max_span = __reduce_max_sync(FULL, my_max_span);
+        my_zero_span = __reduce_add_sync(FULL, my_zero_span);
+        if (lane == 0) {
+            if (my_max_span > 0) atomicMax(&a.status->max_span, my_max_span);
+            if (my_zero_span > 0) atomicAdd(&a.status->n_zero_span, my_zero_span);
+        }
+    }
 }
 
 }  // namespace

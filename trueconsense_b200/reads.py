@@ -38,6 +38,8 @@ class TcReads(C.Structure):
         ("qname_hash", C.c_void_p),
         ("mpos", C.c_void_p),
         ("isize", C.c_void_p),
+        ("max_ref_span", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -108,6 +110,7 @@ class ReadBatch:
         for name in _ARRAYS:
             a = getattr(self, name)
             setattr(s, name, None if a is None else a.ctypes.data)
+        s.max_ref_span = max(int(self.max_ref_span), 0)      # 0 = unknown
         return s
 
     # ------------------------------------------------------------------ derived quantities
