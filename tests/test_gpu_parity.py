@@ -539,3 +539,32 @@ def test_span_bound_hint(ctx, orc):
     zero = ReadBatch.from_records([dict(pos=5, cigar="4S", seq="ACGT"), dict(pos=7, cigar="10M", seq="A" * 10)])
     zero.max_ref_span = 10
     assert ctx.pileup_counts(zero, 100)[0, 7:17].tolist() == [1] * 10
+
+
+def test_extract_inserts_long_insertions_both_forms(ctx, orc):
+    """Insertions longer than 8 bases use hashed keys (verified entry by entry); '=' bases print strand marks."""
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    rng = np.random.default_rng(5)
+    ins_a, ins_b = "ACGTACGTACGT", "ACGTACGTACGA"
+    recs = []
+    for i in range(60):
+        ins = ins_a if i % 3 else ins_b
+        recs.append(dict(pos=0, cigar="6M12I6M", seq="ACGTAC" + ins + "GTACGT", flag=16 if i % 5 == 0 else 0))
+    for i in range(25):
+        n = int(rng.integers(9, 20))
+        recs.append(dict(pos=0, cigar=f"6M{n}I6M", seq="ACGTAC" + "".join(rng.choice(list("ACGT"), n)) + "GTACGT"))
+    recs += [dict(pos=0, cigar="6M3I6M", seq="ACGTAC" + "A=A" + "GTACGT"), dict(pos=0, cigar="6M3I6M", seq="ACGTAC" + "A=A" + "GTACGT", flag=16),
+             dict(pos=0, cigar="6M3I6M", seq="ACGTAC" + "A=A" + "GTACGT", flag=16), dict(pos=2, cigar="4M9D4M", seq="ACGTACGT")]
+    b = ReadBatch.from_records(recs)
+    positions = np.arange(1, 16, dtype=np.int32)
+    for kernel in (0, 2):
+        p = gpu.extractinserts_params()
+        p.kernel = kernel
+        got = ctx._extract_inserts_raw(b, 40, positions, p)
+        for g in got:
+            exp, n = _oracle_modal(pileup, b, g["pos"])
+            assert (g["string"], g["n_entries"]) == (exp, n), (kernel, g)
+    assert got[5]["string"] == "C+12" + ins_a

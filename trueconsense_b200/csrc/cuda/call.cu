@@ -111,41 +111,63 @@ __global__ void __launch_bounds__(256) call_kernel(call_args a) {
 
 // xrun[j] = number of consecutive PRIMARY_X positions starting at j+1.  One CTA; thread t owns a
 // contiguous chunk, scans it backwards, thread 0 chains the chunk carries, chunks patch their tails.
-__global__ void __launch_bounds__(1024) xrun_kernel(uint8_t* __restrict__ flags, int32_t* __restrict__ xrun, int L) {
-    __shared__ int lead[1024];      // consecutive X from the chunk's first position
-    __shared__ int full[1024];      // chunk is all X
-    __shared__ int carry[1024];     // consecutive X starting right after the chunk
-    const int t = threadIdx.x;
-    const int per = (L + 1023) / 1024;
-    const int a = min(L, t * per), b = min(L, a + per);
-    int run = 0, lastnon = a - 1;   // last non-X position inside the chunk
-    bool seen_non = false;
-    for (int j = b - 1; j >= a; --j) {
-        xrun[j] = run;
-        if (flags[j] & TC_CF_PRIMARY_X) ++run; else { run = 0; if (!seen_non) { seen_non = true; lastnon = j; } }
-    }
-    // after the loop `run` = consecutive X from position a (the chunk's lead)
-    lead[t] = run; full[t] = (b > a && !seen_non) || (b == a);
+// len(WalkForward(p)) (Sequences.py:44-52) = consecutive positions after p whose rank-1 letter is X
+//                                           = nn(p + 1) - (p + 1),  nn(k) = first position >= k that is not X (L if none).
+// nn is a reverse min-scan.  xrun_local_kernel scans inside blocks of XR_BLOCK positions (coalesced, warp
+// shuffles) and leaves every block's first non-X position; xrun_apply_kernel looks up the blocks to the
+// right for runs that leave their block.  Both are ordinary multi-CTA kernels: no serial pass over L.
+constexpr int XR_BLOCK = 256;
+
+__global__ void __launch_bounds__(XR_BLOCK) xrun_local_kernel(const uint8_t* __restrict__ flags, int32_t* __restrict__ nn_local,
+                                                              int32_t* __restrict__ block_first, int L) {
+    __shared__ int wmin[XR_BLOCK / 32];
+    const int j = blockIdx.x * XR_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int INF = 0x7fffffff;
+    int v = (j < L && !(flags[j] & TC_CF_PRIMARY_X)) ? j : INF;
+    // suffix minimum inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v = min(v, t); }
+    if (lane == 0) wmin[warp] = v;
     __syncthreads();
-    if (t == 0) {
-        int c = 0;
-        for (int k = 1023; k >= 0; --k) {
-            carry[k] = c;
-            int ka = min(L, k * per), kb = min(L, ka + per);
-            if (kb > ka) c = full[k] ? lead[k] + c : lead[k];
+    int later = INF;
+    for (int w = warp + 1; w < XR_BLOCK / 32; ++w) later = min(later, wmin[w]);
+    v = min(v, later);
+    if (j < L) nn_local[j] = v;                 // first non-X position in [j, end of block), INF if none
+    if (threadIdx.x == 0) block_first[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(XR_BLOCK) xrun_apply_kernel(uint8_t* __restrict__ flags, const int32_t* __restrict__ nn_local,
+                                                              const int32_t* __restrict__ block_first, int32_t* __restrict__ xrun, int L, int n_blocks) {
+    __shared__ int right_s;
+    const int INF = 0x7fffffff;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {     // first non-X position in any block to the right (L if none)
+        int best = INF;
+        for (int b0 = blockIdx.x + 1; b0 < n_blocks && best == INF; b0 += 32) {
+            const int v = b0 + lane < n_blocks ? block_first[b0 + lane] : INF;
+            const unsigned has = __ballot_sync(0xffffffffu, v != INF);
+            if (has) best = __shfl_sync(0xffffffffu, v, __ffs(has) - 1);
+        }
+        if (lane == 0) right_s = best == INF ? L : best;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * XR_BLOCK + threadIdx.x;
+    if (j >= L) return;
+    const int k = j + 1;                        // nn(k)
+    int nn;
+    if (k >= L) nn = L;
+    else if (k < (blockIdx.x + 1) * XR_BLOCK) { const int v = nn_local[k]; nn = v == INF ? right_s : v; }
+    else {                                      // k is the first position of the next block
+        const int v = block_first[blockIdx.x + 1];
+        if (v != INF) nn = v;
+        else {                                  // rare: the whole next block is X — look further right
+            nn = L;
+            for (int b2 = blockIdx.x + 2; b2 < n_blocks; ++b2) { const int w = block_first[b2]; if (w != INF) { nn = w; break; } }
         }
     }
-    __syncthreads();
-    const int cin = carry[t];
-    // positions whose local run reaches the end of the chunk: j >= lastnon (all of j+1..b-1 are X)
-    int from = seen_non ? lastnon : a;
-    for (int j = max(from, a); j < b; ++j) {
-        if (cin) xrun[j] += cin;
-    }
-    __syncthreads();
-    for (int j = a; j < b; ++j) {
-        if (xrun[j] == L - 1 - j) flags[j] |= TC_CF_XRUN_OFF_END;
-    }
+    xrun[j] = nn - k;
+    if (nn == L) flags[j] |= TC_CF_XRUN_OFF_END;
 }
 
 __global__ void is_ambiguous_kernel(const uint8_t* __restrict__ letters, const int32_t* __restrict__ cnts,
@@ -158,32 +180,24 @@ __global__ void is_ambiguous_kernel(const uint8_t* __restrict__ letters, const i
     out[i] = (uint8_t)is_ambiguous(let, cnt, cov[i], maxdist);
 }
 
-// ordered compaction of the INS_CANDIDATE positions (1-based) — single CTA, L is small
-__global__ void __launch_bounds__(1024) list_candidates_kernel(const uint8_t* __restrict__ flags, int L, int32_t* __restrict__ out,
-                                                               int cap, int32_t* __restrict__ n_out) {
-    __shared__ int wsum[32];
-    __shared__ int base_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < L; b0 += 1024) {
-        int j = b0 + threadIdx.x;
-        int is = (j < L) && (flags[j] & TC_CF_INS_CANDIDATE);
-        unsigned m = __ballot_sync(0xffffffffu, is);
-        int within_w = __popc(m & ((1u << lane) - 1));
-        if (lane == 0) wsum[warp] = __popc(m);
-        __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < warp; ++w) woff += wsum[w];
-        int total = 0;
-        for (int w = 0; w < 32; ++w) total += wsum[w];
-        int slot = base_s + woff + within_w;
-        if (is && slot < cap) out[slot] = j + 1;
-        __syncthreads();
-        if (threadIdx.x == 0) base_s += total;
-        __syncthreads();
+// INS_CANDIDATE positions (1-based): appended in any order by a multi-CTA pass (candidates are rare), then
+// put in ascending order by a rank sort over the few that exist
+__global__ void list_candidates_kernel(const uint8_t* __restrict__ flags, int L, int32_t* __restrict__ out, int cap, int32_t* __restrict__ n_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < L && (flags[j] & TC_CF_INS_CANDIDATE)) {
+        const int slot = atomicAdd(n_out, 1);
+        if (slot < cap) out[slot] = j + 1;
     }
-    if (threadIdx.x == 0) *n_out = base_s;
+}
+
+__global__ void rank_sort_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ n_in, int cap, int32_t* __restrict__ out) {
+    const int n = min(*n_in, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = in[i];
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += in[k] < v;       // positions are distinct
+        out[rank] = v;
+    }
 }
 
 // ---------------------------------------------------------------- C-ABI
@@ -216,7 +230,13 @@ TC_API int tc_call(tc_ctx_t* ctx, const int32_t* counts, int32_t ref_len, const 
     call_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(a);
     TC_LAUNCH_CHECK();
     if (a.xrun) {
-        xrun_kernel<<<1, 1024, 0, s>>>(a.flags, a.xrun, ref_len);
+        const int n_blocks = (ref_len + XR_BLOCK - 1) / XR_BLOCK;
+        int32_t* nn_local = (int32_t*)tc_dev_buf(ctx, SLOT_SEGS, 4 * (L + (size_t)n_blocks) + 64);
+        if (!nn_local) return TC_ERR_NOMEM;
+        int32_t* block_first = nn_local + L;
+        xrun_local_kernel<<<n_blocks, XR_BLOCK, 0, s>>>(a.flags, nn_local, block_first, ref_len);
+        TC_LAUNCH_CHECK();
+        xrun_apply_kernel<<<n_blocks, XR_BLOCK, 0, s>>>(a.flags, nn_local, block_first, a.xrun, ref_len, n_blocks);
         TC_LAUNCH_CHECK();
     }
     bool any_host = false;
@@ -261,20 +281,33 @@ TC_API int tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_
     TC_CUDA(cudaSetDevice(ctx->device));
     int rc;
     const uint8_t* df = (const uint8_t*)tc_stage_in(ctx, SLOT_TMP_A, flags, (size_t)ref_len, s, &rc); if (rc) return rc;
-    int32_t* d_out = (int32_t*)tc_dev_buf(ctx, SLOT_TMP_B, 4 * (size_t)(cap + 1) + 16);
-    if (!d_out) return TC_ERR_NOMEM;
-    list_candidates_kernel<<<1, 1024, 0, s>>>(df, ref_len, d_out + 1, cap, d_out);
+    // layout: [unordered: cap] [count] [sorted: cap]
+    int32_t* d_buf = (int32_t*)tc_dev_buf(ctx, SLOT_TMP_B, 4 * (2 * (size_t)cap + 1) + 64);
+    if (!d_buf) return TC_ERR_NOMEM;
+    int32_t* d_cnt = d_buf + cap;
+    int32_t* d_sorted = d_cnt + 1;
+    TC_CUDA(cudaMemsetAsync(d_cnt, 0, 4, s));
+    list_candidates_kernel<<<(unsigned)((ref_len + 255) / 256), 256, 0, s>>>(df, ref_len, d_buf, cap, d_cnt);
     TC_LAUNCH_CHECK();
-    int32_t n = 0;
-    TC_D2H(ctx->host_status, d_out, 4, s);
+    rank_sort_kernel<<<32, 256, 0, s>>>(d_buf, d_cnt, cap, d_sorted);
+    TC_LAUNCH_CHECK();
+    // the count and the first candidates come back in one copy (there are rarely more than a handful)
+    const int first = cap < 63 ? cap : 63;
+    TC_D2H(ctx->host_status, d_cnt, 4 * (size_t)(1 + first), s);
     TC_CUDA(cudaStreamSynchronize(s));
-    n = *(int32_t*)ctx->host_status;
+    const int32_t n = *(int32_t*)ctx->host_status;
     *n_out = n;
     if (n > cap) return tc_fail(ctx, TC_ERR_CAPACITY, "%d insertion candidates, capacity %d", n, cap);
     if (n > 0) {
-        if (tc_is_device_ptr(cand_pos)) TC_CUDA(cudaMemcpyAsync(cand_pos, d_out + 1, 4 * (size_t)n, cudaMemcpyDeviceToDevice, s));
-        else TC_D2H(cand_pos, d_out + 1, 4 * (size_t)n, s);
-        TC_CUDA(cudaStreamSynchronize(s));
+        if (tc_is_device_ptr(cand_pos)) {
+            TC_CUDA(cudaMemcpyAsync(cand_pos, d_sorted, 4 * (size_t)n, cudaMemcpyDeviceToDevice, s));
+            TC_CUDA(cudaStreamSynchronize(s));
+        } else if (n <= first) {
+            memcpy(cand_pos, (int32_t*)ctx->host_status + 1, 4 * (size_t)n);
+        } else {
+            TC_D2H(cand_pos, d_sorted, 4 * (size_t)n, s);
+            TC_CUDA(cudaStreamSynchronize(s));
+        }
     }
     return TC_OK;
 }

@@ -101,6 +101,15 @@ __device__ __forceinline__ char ins_char(const ins_args& a, uint32_t read, int q
     return base_char_upper(seq_code(a.r.seq4 + a.r.seq_off[read], q), rev);
 }
 
+// 5-bit symbol of the j-th inserted character: the BAM code, 15 ('N') past the end of SEQ, 16 for a reverse-strand '='
+__device__ __forceinline__ uint32_t ins_sym(const ins_args& a, uint32_t read, int qpos, int j, bool rev) {
+    const int lq = a.r.l_seq[read];
+    const int q = qpos + j;
+    if (q >= lq) return 15u;
+    const uint32_t code = seq_code(a.r.seq4 + a.r.seq_off[read], q);
+    return (code == 0 && rev) ? 16u : code;
+}
+
 // select: one thread per read of the candidate's range
 __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
     __shared__ int wlast[INS_TILE / 32];
@@ -150,10 +159,17 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
             // yields an entry, and it counts towards the live total like any selected read
             sel = found || (x == pos && pos == c);
             if (emit) {
-                key = mix_key(0x7463696e73ull, (uint64_t)(uint8_t)head);
-                key = mix_key(key, (uint64_t)(uint32_t)indel);
-                for (int j = 1; j <= indel; ++j) key = mix_key(key, (uint64_t)(uint8_t)ins_char(a, r, qpos, j, rev));
-                key &= 0x7fffffffffffffffull;
+                if (indel <= 8 && indel > -8192) {
+                    // the whole string fits the key: bit 62 = exact, head character, indel + 8192, 5 bits per inserted
+                    // character (BAM code; 16 = the ',' a reverse-strand '=' prints as) — equal keys <=> equal strings
+                    key = (1ull << 62) | ((uint64_t)(uint8_t)head << 54) | ((uint64_t)(uint32_t)(indel + 8192) << 40);
+                    for (int j = 1; j <= indel; ++j) key |= (uint64_t)ins_sym(a, r, qpos, j, rev) << (5 * (j - 1));
+                } else {
+                    key = mix_key(0x7463696e73ull, (uint64_t)(uint8_t)head);
+                    key = mix_key(key, (uint64_t)(uint32_t)indel);
+                    for (int j = 1; j <= indel; ++j) key = mix_key(key, (uint64_t)(uint8_t)ins_char(a, r, qpos, j, rev));
+                    key &= 0x3fffffffffffffffull;       // hashed: bit 62 clear, verified entry by entry in the count
+                }
             }
         }
         const int64_t slot = a.seg_off[ci] + (r - lo);
@@ -255,24 +271,27 @@ __global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_c
     for (int i = threadIdx.x; i < INS_TBL; i += blockDim.x) { tkey[i] = KEY_NONE; tcnt[i] = 0; tfirst[i] = 0xffffffffu; }
     if (threadIdx.x == 0) { best_s = 0ull; over_s = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long k = a.ent_key[off + i];
-        if (k == KEY_NONE) continue;
+    const int n_round = (n + 31) & ~31;     // whole warps stay together for the match
+    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const unsigned long long k = i < n ? a.ent_key[off + i] : KEY_NONE;
+        // lanes holding the same key insert once (most entries of a column print the same string)
+        const unsigned grp = __match_any_sync(0xffffffffu, k);
+        if (k == KEY_NONE || (__ffs(grp) - 1) != (int)(threadIdx.x & 31)) continue;
         unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
         int probes = 0;
         for (;;) {
             const unsigned long long old = atomicCAS(&tkey[h], KEY_NONE, k);
-            if (old == KEY_NONE || old == k) { atomicAdd(&tcnt[h], 1u); atomicMin(&tfirst[h], (unsigned)i); break; }
+            if (old == KEY_NONE || old == k) { atomicAdd(&tcnt[h], (unsigned)__popc(grp)); atomicMin(&tfirst[h], (unsigned)i); break; }
             h = (h + 1) & (INS_TBL - 1);
             if (++probes >= INS_TBL * 7 / 8) { over_s = 1; break; }
         }
     }
     __syncthreads();
     if (over_s) { if (threadIdx.x == 0) atomicExch(a.overflow, 1); return; }
-    // every entry against the first entry of its key
+    // hashed keys (insertions longer than 8): every entry against the first entry of its key
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned long long k = a.ent_key[off + i];
-        if (k == KEY_NONE) continue;
+        if (k == KEY_NONE || (k >> 62)) continue;
         unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
         while (tkey[h] != k) h = (h + 1) & (INS_TBL - 1);
         const unsigned f = tfirst[h];
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(1024) ins_mode_kernel(ins_args a, const uint64
         while (lo < hi) { int mid = (lo + hi) >> 1; if (skey[off + mid] < k) lo = mid + 1; else hi = mid; }
         const int head = lo;
         if (head != i) {
-            if (!same_entry(a, lo_read, off, sidx[off + head], sidx[off + i])) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+            if (!(k >> 62) && !same_entry(a, lo_read, off, sidx[off + head], sidx[off + i])) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
         } else {
             int l2 = i, h2 = m;
             while (l2 < h2) { int mid = (l2 + h2) >> 1; if (skey[off + mid] <= k) l2 = mid + 1; else h2 = mid; }
