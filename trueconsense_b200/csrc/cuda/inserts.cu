@@ -101,13 +101,20 @@ __device__ __forceinline__ char ins_char(const ins_args& a, uint32_t read, int q
     return base_char_upper(seq_code(a.r.seq4 + a.r.seq_off[read], q), rev);
 }
 
-// 5-bit symbol of the j-th inserted character: the BAM code, 15 ('N') past the end of SEQ, 16 for a reverse-strand '='
-__device__ __forceinline__ uint32_t ins_sym(const ins_args& a, uint32_t read, int qpos, int j, bool rev) {
-    const int lq = a.r.l_seq[read];
-    const int q = qpos + j;
-    if (q >= lq) return 15u;
-    const uint32_t code = seq_code(a.r.seq4 + a.r.seq_off[read], q);
-    return (code == 0 && rev) ? 16u : code;
+// what pysam prints for query base q of a read, as a 5-bit symbol: the BAM code, 15 ('N') past the end of SEQ,
+// 16 for a reverse-strand '=' (printed ',' where the forward strand prints '.').  Equal symbols <=> equal characters.
+struct read_syms {
+    const uint32_t* w; int lq; bool rev;
+    __device__ __forceinline__ uint32_t sym(int q) const {
+        if (q >= lq) return 15u;
+        const uint32_t code = seq_code(w, q);
+        return (code == 0 && rev) ? 16u : code;
+    }
+};
+__device__ __forceinline__ read_syms read_syms_of(const ins_args& a, uint32_t read) {
+    read_syms rs;
+    rs.w = a.r.seq4 + a.r.seq_off[read]; rs.lq = a.r.l_seq[read]; rs.rev = (a.r.flag[read] & 16u) != 0;
+    return rs;
 }
 
 // select: one thread per read of the candidate's range
@@ -159,12 +166,26 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
             // yields an entry, and it counts towards the live total like any selected read
             sel = found || (x == pos && pos == c);
             if (emit) {
+                const read_syms rs = read_syms_of(a, r);
+                bool exact = false;
                 if (indel <= 8 && indel > -8192) {
-                    // the whole string fits the key: bit 62 = exact, head character, indel + 8192, 5 bits per inserted
-                    // character (BAM code; 16 = the ',' a reverse-strand '=' prints as) — equal keys <=> equal strings
-                    key = (1ull << 62) | ((uint64_t)(uint8_t)head << 54) | ((uint64_t)(uint32_t)(indel + 8192) << 40);
-                    for (int j = 1; j <= indel; ++j) key |= (uint64_t)ins_sym(a, r, qpos, j, rev) << (5 * (j - 1));
-                } else {
+                    // the whole string fits the key: bit 62 = exact, bit 61 = 0, head character (7 bits), indel + 8192,
+                    // 5 bits per inserted character (BAM code; 16 = the ',' a reverse-strand '=' prints as) —
+                    // equal keys <=> equal strings, no verification needed
+                    exact = true;
+                    key = (1ull << 62) | ((uint64_t)((uint8_t)head & 127u) << 54) | ((uint64_t)(uint32_t)(indel + 8192) << 40);
+                    for (int j = 1; j <= indel; ++j) key |= (uint64_t)rs.sym(qpos + j) << (5 * (j - 1));
+                } else if (indel <= 12) {
+                    // 9..12 inserted characters at 4 bits each (bit 61 = 1), unless one of them is a reverse-strand '='
+                    exact = true;
+                    key = (3ull << 61) | ((uint64_t)((uint8_t)head & 127u) << 54) | ((uint64_t)(uint32_t)indel << 48);
+                    for (int j = 1; j <= indel; ++j) {
+                        const uint32_t sy = rs.sym(qpos + j);
+                        exact = exact && sy < 16u;
+                        key |= (uint64_t)(sy & 15u) << (4 * (j - 1));
+                    }
+                }
+                if (!exact) {
                     key = mix_key(0x7463696e73ull, (uint64_t)(uint8_t)head);
                     key = mix_key(key, (uint64_t)(uint32_t)indel);
                     for (int j = 1; j <= indel; ++j) key = mix_key(key, (uint64_t)(uint8_t)ins_char(a, r, qpos, j, rev));
@@ -234,10 +255,11 @@ __global__ void __launch_bounds__(INS_TILE) ins_admit_kernel(ins_args a) {
 __device__ __forceinline__ bool same_entry(const ins_args& a, int lo, int64_t off, uint32_t e1, uint32_t e2) {
     if (a.ent_head[e1] != a.ent_head[e2] || a.ent_indel[e1] != a.ent_indel[e2]) return false;
     const int indel = a.ent_indel[e1];
-    const uint32_t r1 = (uint32_t)(lo + (int64_t)e1 - off), r2 = (uint32_t)(lo + (int64_t)e2 - off);
-    const bool v1 = (a.r.flag[r1] & 16u) != 0, v2 = (a.r.flag[r2] & 16u) != 0;
+    if (indel <= 0) return true;
+    const read_syms s1 = read_syms_of(a, (uint32_t)(lo + (int64_t)e1 - off)), s2 = read_syms_of(a, (uint32_t)(lo + (int64_t)e2 - off));
+    const int q1 = a.ent_qpos[e1], q2 = a.ent_qpos[e2];
     for (int j = 1; j <= indel; ++j)
-        if (ins_char(a, r1, a.ent_qpos[e1], j, v1) != ins_char(a, r2, a.ent_qpos[e2], j, v2)) return false;
+        if (s1.sym(q1 + j) != s2.sym(q2 + j)) return false;
     return true;
 }
 
