@@ -229,11 +229,11 @@ def run_ours(args):
     h_counts = np.empty((gpu.TC_NROWS, L), dtype=np.int32)
 
     def e2e_step():
-        # every read array the pileup needs goes host -> device inside tc_pileup_counts (pinned memory)
-        ctx.pileup_counts(pinned, L, params, out=counts_dev, stream=stream)
+        d = ctx.upload(pinned, stream, with_qual=False)      # H2D of every read array the pileup needs (pinned memory)
+        ctx.pileup_counts(d, L, params, out=counts_dev, stream=stream)
         res = ctx.call(counts_dev, L, w.mincov, True, stream=stream)     # D2H of the call table
         cands = ctx.list_insert_candidates(res.flags, L)
-        ins = ctx.extract_inserts(pinned, L, cands)          # H2D of the reads over the candidate columns (with QUAL)
+        ins = ctx.extract_inserts(d.with_host_qual(), L, cands)          # H2D of QUAL over the candidate columns only
         torch.cuda.current_stream().synchronize()
         h = counts_dev.cpu().numpy()                         # D2H of the count table
         return h, res, ins

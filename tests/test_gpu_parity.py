@@ -431,21 +431,28 @@ def test_config2_slice_properties(ctx, orc):
     assert np.array_equal(parts, g1)
 
 
-def test_extract_inserts_sliced_upload_equals_full_upload(ctx):
-    """Large host batches upload only the reads over the candidate columns; same answers."""
+def test_extract_inserts_partial_staging_equals_full_upload(ctx):
+    """Host SEQ / QUAL / CIGAR are staged only over the candidate columns; same answers as with everything on
+    the device, for host batches and for device reads that carry a host QUAL array."""
     ref, _, b = _synth("amplicon_deep")
     L = len(ref)
     counts = ctx.pileup_counts(b, L)
     cands = [int(c) for c in ctx.list_insert_candidates(ctx.call(counts, L, 30, True).flags, L)]
     positions = sorted(set(cands) | {1, 700, 701, 2500, L})
-    full = ctx._extract_inserts_raw(b, L, np.asarray(positions, np.int32), __import__("trueconsense_b200").gpu.extractinserts_params())
-    old = ctx.SLICE_THRESHOLD
-    try:
-        type(ctx).SLICE_THRESHOLD = 0
-        sliced = ctx.extract_inserts(b, L, positions)
-    finally:
-        type(ctx).SLICE_THRESHOLD = old
-    assert sliced == full
+    full = ctx.extract_inserts(ctx.upload(b), L, positions)             # everything resident, QUAL included
+    x0 = ctx.transfer_bytes()[0]
+    host = ctx.extract_inserts(b, L, positions)                          # all host pointers
+    x1 = ctx.transfer_bytes()[0]
+    dev = ctx.upload(b, with_qual=False)
+    x2 = ctx.transfer_bytes()[0]
+    mixed = ctx.extract_inserts(dev.with_host_qual(), L, positions)      # device arrays + host QUAL
+    x3 = ctx.transfer_bytes()[0]
+    assert host == full and mixed == full
+    assert x3 - x2 <= b.qual.nbytes + 4096            # nothing but QUAL stretches (and a few integers) travelled
+    assert x1 - x0 < b.qual.nbytes + b.seq4.nbytes + b.cigar.nbytes + 64 * b.n_reads
+    with pytest.raises(RuntimeError):
+        ctx.pileup_counts(b, L)                 # stages host arrays through the context's buffers ...
+        ctx.pileup_counts(dev, L)               # ... so the earlier upload is stale
 
 
 # ---------------------------------------------------------------------------- CLI end to end

@@ -31,7 +31,7 @@ def DepthFromBam(bam, ref_len: int | None = None) -> np.ndarray:
 
     h = _bam_handle(bam)
     L = h.ref_len if ref_len is None else int(ref_len)
-    return gpu.default_context().depth(h.contig0(), L)
+    return gpu.default_context().depth(h.device_reads(), L)
 
 
 def WriteCoverage(depth: np.ndarray, output: str) -> None:

@@ -57,7 +57,7 @@ def ExtractInserts(bam, position):
     h = _bam_handle(bam)
     if not 1 <= position <= h.ref_len:
         return None, None
-    res = gpu.default_context().extract_inserts(h.contig0(), h.ref_len, [position])
+    res = gpu.default_context().extract_inserts(h.device_reads(with_host_qual=True), h.ref_len, [position])
     return _parse_modal(res[0]["string"])
 
 
@@ -88,7 +88,7 @@ def ListInserts(iDict, mincov, bam):
         if h is None:
             raise TypeError("bam must come from trueconsense_b200.indexing.Readbam (or expose .filename)")
         cols = [int(c) for c in cands if c <= h.ref_len]
-        res = ctx.extract_inserts(h.contig0(), h.ref_len, cols) if cols else []
+        res = ctx.extract_inserts(h.device_reads(with_host_qual=True), h.ref_len, cols) if cols else []
         for r in res:
             bases, size = _parse_modal(r["string"])
             if bases is None or size is None:

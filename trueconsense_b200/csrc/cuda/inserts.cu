@@ -38,6 +38,7 @@ struct ins_args {
     uint32_t flag_filter; int min_mapq, min_bq, ignore_orphans; long long max_depth;
     int32_t span_hint;              // > 0: caller's upper bound of the longest reference span (tc_reads_t.max_ref_span)
     int32_t* range;                 // [n_cand][2] lo, hi read indices: the reads with pos in (c - longest span, c]
+    uint32_t* range_off;            // [n_cand][4] seq_off[lo], seq_off[hi], cigar_off[lo], cigar_off[hi]
     const int64_t* seg_off;         // [n_cand+1] slot offsets; read r of candidate ci owns slot seg_off[ci] + r - lo
     const int32_t* tile_cand;       // [n_tiles] candidate of every tile
     const int32_t* tile_first;      // [n_cand+1] first tile of every candidate
@@ -76,8 +77,11 @@ __global__ void cand_range_kernel(ins_args a) {
         while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a.r.pos[mid] < v) lo = mid + 1; else hi = mid; }
         return (int)lo;
     };
-    a.range[2 * ci] = lower(c - ms + 1);
-    a.range[2 * ci + 1] = lower(c + 1);
+    const int lo = lower(c - ms + 1), hi = max(lo, lower(c + 1));
+    a.range[2 * ci] = lo;
+    a.range[2 * ci + 1] = hi;
+    a.range_off[4 * ci] = a.r.seq_off[lo]; a.range_off[4 * ci + 1] = a.r.seq_off[hi];
+    a.range_off[4 * ci + 2] = a.r.cigar_off[lo]; a.range_off[4 * ci + 3] = a.r.cigar_off[hi];
 }
 
 __device__ __forceinline__ uint64_t mix_key(uint64_t h, uint64_t v) {
@@ -390,14 +394,22 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     TC_CUDA(cudaSetDevice(ctx->device));
     ins_args a;
     memset(&a, 0, sizeof(a));
-    int rc = tc_resolve_reads(ctx, reads, &a.r, NEED_QUAL | NEED_MATE, s);
+    // Host-resident SEQ / QUAL / CIGAR are staged range by range once the candidate ranges are known: this pass
+    // reads them only for the reads over the candidate columns, and QUAL alone is 8x the packed bases.  (Without a
+    // span bound the CIGARs of all reads are needed first, so they are staged in full.)
+    const bool bounded = reads->max_ref_span > 0;
+    const int stage = NEED_QUAL | NEED_MATE | DEFER_SEQ | DEFER_QUAL | (bounded ? DEFER_CIGAR : 0);
+    const bool host_seq = reads->seq4 && !tc_is_device_ptr(reads->seq4);
+    const bool host_qual = reads->qual && !tc_is_device_ptr(reads->qual);
+    const bool host_cig = bounded && reads->cigar && !tc_is_device_ptr(reads->cigar);
+    int rc = tc_resolve_reads(ctx, reads, &a.r, stage, s);
     if (rc) return rc;
     const int64_t n = a.r.n;
     for (int i = 0; i < n_cand; ++i) { calls[i].pos = cand_pos[i]; calls[i].n_entries = 0; calls[i].mode_count = 0; calls[i].first_read = -1; calls[i].head = 0; calls[i].indel = 0; calls[i].bases_off = -1; }
     if (n == 0) return TC_OK;
     tc_status* d_status = (tc_status*)tc_dev_buf(ctx, SLOT_STATUS, sizeof(tc_status));
     int32_t* d_cand = (int32_t*)tc_dev_buf(ctx, SLOT_INS_A, 4 * (size_t)n_cand);
-    int32_t* d_range = (int32_t*)tc_dev_buf(ctx, SLOT_INS_B, 8 * (size_t)n_cand);
+    int32_t* d_range = (int32_t*)tc_dev_buf(ctx, SLOT_INS_B, 24 * (size_t)n_cand);       // [n_cand][2] ranges, then [n_cand][4] offsets
     if (!d_status || !d_cand || !d_range) return TC_ERR_NOMEM;
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     TC_CUDA(cudaMemcpyAsync(d_cand, cand_pos, 4 * (size_t)n_cand, cudaMemcpyHostToDevice, s));
@@ -407,13 +419,13 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
         max_span_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.r, d_status);
         TC_LAUNCH_CHECK();
     }
-    a.cand = d_cand; a.n_cand = n_cand; a.range = d_range; a.status = d_status;
+    a.cand = d_cand; a.n_cand = n_cand; a.range = d_range; a.range_off = (uint32_t*)(d_range + 2 * (size_t)n_cand); a.status = d_status;
     a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality; a.ignore_orphans = p->ignore_orphans;
     a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
     cand_range_kernel<<<(n_cand + 127) / 128, 128, 0, s>>>(a);
     TC_LAUNCH_CHECK();
     // host side of the layout: slot offsets and the tile table (a few integers per candidate)
-    int32_t* h_range = (int32_t*)malloc(8 * (size_t)n_cand);
+    int32_t* h_range = (int32_t*)malloc(24 * (size_t)n_cand);
     int64_t* h_off = (int64_t*)malloc(8 * ((size_t)n_cand + 1));
     int32_t* h_tfirst = (int32_t*)malloc(4 * ((size_t)n_cand + 1));
     int32_t* h_tcand = NULL;
@@ -421,9 +433,29 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     if (!h_range || !h_off || !h_tfirst) { free(h_range); free(h_off); free(h_tfirst); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
 #define INS_FREE() do { free(h_range); free(h_off); free(h_tfirst); free(h_tcand); free(h_entry); } while (0)
 #define INS_CUDA(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e__, what); } } while (0)
-    INS_CUDA(cudaMemcpyAsync(h_range, d_range, 8 * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "range readback");
+    INS_CUDA(cudaMemcpyAsync(h_range, d_range, 24 * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "range readback");
     INS_CUDA(cudaStreamSynchronize(s), "range readback");
-    ctx->d2h_bytes += 8 * (int64_t)n_cand;
+    ctx->d2h_bytes += 24 * (int64_t)n_cand;
+    if (host_seq || host_qual || host_cig) {
+        // candidates ascend, so do their ranges: merge the overlapping ones and copy every stretch once
+        const uint32_t* ho = (const uint32_t*)(h_range + 2 * (size_t)n_cand);
+        for (int k = 0; k < 2; ++k) {           // k = 0: SEQ + QUAL word ranges, k = 1: CIGAR op ranges
+            if (k == 0 ? !(host_seq || host_qual) : !host_cig) continue;
+            int i = 0;
+            while (i < n_cand) {
+                uint32_t b0 = ho[4 * i + 2 * k], b1 = ho[4 * i + 2 * k + 1];
+                int j = i + 1;
+                while (j < n_cand && ho[4 * j + 2 * k] <= b1) { if (ho[4 * j + 2 * k + 1] > b1) b1 = ho[4 * j + 2 * k + 1]; ++j; }
+                const size_t len = (size_t)(b1 - b0);
+                if (len) {
+                    if (k == 0 && host_seq) { INS_CUDA(cudaMemcpyAsync((uint32_t*)a.r.seq4 + b0, reads->seq4 + b0, 4 * len, cudaMemcpyHostToDevice, s), "SEQ range upload"); ctx->h2d_bytes += 4 * (int64_t)len; }
+                    if (k == 0 && host_qual) { INS_CUDA(cudaMemcpyAsync((uint8_t*)a.r.qual + 8 * (size_t)b0, reads->qual + 8 * (size_t)b0, 8 * len, cudaMemcpyHostToDevice, s), "QUAL range upload"); ctx->h2d_bytes += 8 * (int64_t)len; }
+                    if (k == 1) { INS_CUDA(cudaMemcpyAsync((uint32_t*)a.r.cigar + b0, reads->cigar + b0, 4 * len, cudaMemcpyHostToDevice, s), "CIGAR range upload"); ctx->h2d_bytes += 4 * (int64_t)len; }
+                }
+                i = j;
+            }
+        }
+    }
     h_off[0] = 0; h_tfirst[0] = 0;
     for (int i = 0; i < n_cand; ++i) {
         const int64_t len = h_range[2 * i + 1] - h_range[2 * i];

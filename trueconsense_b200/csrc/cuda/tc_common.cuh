@@ -83,6 +83,11 @@ struct dreads {
 // which arrays a pass needs on the device
 #define NEED_QUAL  1
 #define NEED_MATE  2
+// host-resident seq4 / cigar / qual: give them full-size device buffers but copy nothing — the caller stages
+// only the ranges its pass will read (tc_extract_inserts: the reads over the candidate columns)
+#define DEFER_SEQ   4
+#define DEFER_CIGAR 8
+#define DEFER_QUAL  16
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s);
 
 // ---------------------------------------------------------------- device helpers

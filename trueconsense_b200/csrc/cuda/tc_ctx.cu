@@ -79,12 +79,17 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
     STAGE(l_seq, SLOT_LSEQ, int32_t, n)
     STAGE(seq_off, SLOT_SEQOFF, uint32_t, n + 1)
     STAGE(cigar_off, SLOT_CIGOFF, uint32_t, n + 1)
-    STAGE(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words)
-    STAGE(cigar, SLOT_CIGAR, uint32_t, in->n_cigar_ops)
+#define STAGE_OR_DEFER(field, slot, type, count, defer)                                               \
+    if ((need & (defer)) && in->field && !tc_is_device_ptr(in->field)) {                                \
+        out->field = (const type*)tc_dev_buf(ctx, slot, sizeof(type) * (size_t)(count));                \
+        if (!out->field) return TC_ERR_NOMEM;                                                           \
+    } else { STAGE(field, slot, type, count) }
+    STAGE_OR_DEFER(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words, DEFER_SEQ)
+    STAGE_OR_DEFER(cigar, SLOT_CIGAR, uint32_t, in->n_cigar_ops, DEFER_CIGAR)
     if (in->mapq) { STAGE(mapq, SLOT_MAPQ, uint8_t, n) }
     if (need & NEED_QUAL) {
         if (!in->qual && in->n_seq_words) return tc_fail(ctx, TC_ERR_ARG, "this pass applies a base-quality filter but reads->qual is NULL");
-        STAGE(qual, SLOT_QUAL, uint8_t, 8 * in->n_seq_words)
+        STAGE_OR_DEFER(qual, SLOT_QUAL, uint8_t, 8 * in->n_seq_words, DEFER_QUAL)
     } else if (in->qual && tc_is_device_ptr(in->qual)) {
         out->qual = in->qual;
     }
@@ -93,6 +98,7 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
         if (in->mpos) { STAGE(mpos, SLOT_MPOS, int32_t, n) }
         if (in->isize) { STAGE(isize, SLOT_ISIZE, int32_t, n) }
     }
+#undef STAGE_OR_DEFER
 #undef STAGE
     return TC_OK;
 }

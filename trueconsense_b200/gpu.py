@@ -141,10 +141,21 @@ class CallResult:
 class DeviceReads:
     """A read batch resident in context-owned device memory (see tc_reads_upload)."""
 
-    def __init__(self, struct: TcReads, batch: ReadBatch):
+    def __init__(self, struct: TcReads, batch: ReadBatch, ctx=None, generation: int = 0):
         self.struct = struct
         self.n_reads = batch.n_reads
         self.host = batch
+        self.ctx = ctx
+        self.generation = generation
+
+    def with_host_qual(self) -> "DeviceReads":
+        """The same device arrays plus the batch's HOST quality array: tc_extract_inserts then copies QUAL
+        only for the reads over its candidate columns."""
+        st = TcReads()
+        C.memmove(C.byref(st), C.byref(self.struct), C.sizeof(TcReads))
+        if not st.qual and self.host.qual is not None:
+            st.qual = self.host.qual.ctypes.data
+        return DeviceReads(st, self.host, self.ctx, self.generation)
 
 
 class Context:
@@ -157,6 +168,7 @@ class Context:
         if rc != 0:
             raise TcError(rc, self._lib.tc_last_error(None).decode())
         self._h = h
+        self._generation = 0        # bumped whenever host arrays are staged through the context's device buffers
 
     def close(self):
         if getattr(self, "_h", None):
@@ -191,21 +203,28 @@ class Context:
         return float(self._lib.tc_last_pileup_kernel_ms(self._h))
 
     # ------------------------------------------------------------------ reads
-    @staticmethod
-    def _reads_struct(reads) -> TcReads:
+    def _reads_struct(self, reads) -> TcReads:
         if isinstance(reads, DeviceReads):
+            if reads.ctx is self and reads.generation != self._generation:
+                raise RuntimeError("these device reads are stale: the context has staged another batch since they were uploaded")
             return reads.struct
         if isinstance(reads, ReadBatch):
+            self._generation += 1           # host arrays are staged through the same device buffers
             return reads.c_struct()
         if isinstance(reads, TcReads):
             return reads
         raise TypeError(type(reads))
 
-    def upload(self, batch: ReadBatch, stream: int = 0) -> DeviceReads:
+    def upload(self, batch: ReadBatch, stream: int = 0, with_qual: bool = True) -> DeviceReads:
+        """Copy a host batch into the context's device buffers.  They are reused by the next upload — and by any
+        later call that is handed host arrays — so a DeviceReads is only valid until then (checked)."""
         dev = TcReads()
         host = batch.c_struct()
+        if not with_qual:
+            host.qual = None
+        self._generation += 1
         self._check(self._lib.tc_reads_upload(self._h, C.byref(host), C.byref(dev), stream))
-        return DeviceReads(dev, batch)
+        return DeviceReads(dev, batch, self, self._generation)
 
     # ------------------------------------------------------------------ (1) pileup
     def pileup_counts(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):
@@ -266,46 +285,18 @@ class Context:
         self._check(self._lib.tc_list_insert_candidates(self._h, _ptr(flags), int(ref_len), _ptr(out), cap, C.byref(n), 0))
         return out[: n.value].copy()
 
-    SLICE_THRESHOLD = 100_000
-
     def extract_inserts(self, reads, ref_len: int, positions, params: PileupParams | None = None):
         """ExtractInserts for the given 1-based positions.  Returns a list of dicts with the modal
         upper-cased string of each column (``None`` when pysam would have returned ``""``).
 
-        For large HOST batches only the reads that can reach a candidate column travel to the device
-        (this pass is the only one that needs QUAL, 8x the size of the packed bases): reads are
-        start-sorted, so the reads overlapping column c lie in pos (c - max_span, c]; candidates whose
-        read ranges overlap share one upload."""
+        Host-resident SEQ / QUAL / CIGAR arrays travel to the device only for the reads that can reach a
+        candidate column (tc_extract_inserts stages them range by range; this pass is the only one that
+        needs QUAL, 8x the size of the packed bases)."""
         params = params or extractinserts_params()
         pos = np.ascontiguousarray(positions, dtype=np.int32)
         if pos.shape[0] == 0:
             return []
-        if not isinstance(reads, ReadBatch) or reads.n_reads <= self.SLICE_THRESHOLD:
-            return self._extract_inserts_raw(reads, ref_len, pos, params)
-        batch = reads
-        if batch.max_ref_span < 0:
-            batch.max_ref_span = int(batch.ref_spans().max()) if batch.n_reads else 0
-        ms = max(int(batch.max_ref_span), 1)
-        cols = pos.astype(np.int64) - 1
-        lo = np.searchsorted(batch.pos, cols - ms + 1, side="left")
-        hi = np.searchsorted(batch.pos, cols + 1, side="left")
-        out: list = [None] * len(pos)
-        groups: list[tuple[int, int, list[int]]] = []      # (first read, end read, candidate indices)
-        for i in np.argsort(lo, kind="stable"):
-            i = int(i)
-            if groups and lo[i] <= groups[-1][1]:
-                r0, r1, members = groups[-1]
-                groups[-1] = (r0, max(r1, int(hi[i])), members + [i])
-            else:
-                groups.append((int(lo[i]), int(hi[i]), [i]))
-        for r0, r1, members in groups:
-            members.sort(key=lambda i: int(pos[i]))
-            res = self._extract_inserts_raw(batch.slice(r0, r1), ref_len, np.ascontiguousarray(pos[members]), params)
-            for i, item in zip(members, res):
-                if item["first_read"] >= 0:
-                    item["first_read"] += r0
-                out[i] = item
-        return out
+        return self._extract_inserts_raw(reads, ref_len, pos, params)
 
     def _extract_inserts_raw(self, reads, ref_len: int, pos: np.ndarray, params: PileupParams):
         n = int(pos.shape[0])

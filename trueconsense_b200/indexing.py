@@ -58,13 +58,16 @@ class BamHandle:
                              "(its DataFrame index would hold duplicate positions)")
         return b
 
-    def device_reads(self):
-        """Upload once per handle; later passes (ExtractInserts) reuse the device copy."""
+    def device_reads(self, with_host_qual: bool = False):
+        """The reads of the first reference in device memory: uploaded (without QUAL) once per handle and
+        reused by later passes while the context has not staged anything else; ExtractInserts adds the
+        host QUAL array, of which only the stretches over candidate columns are ever copied."""
         ctx = gpu.default_context()
         with self._lock:
-            if self._dev is None or self._dev[0] is not ctx:
-                self._dev = (ctx, ctx.upload(self.contig0_nolock()))
-            return self._dev[1]
+            d = self._dev
+            if d is None or d.ctx is not ctx or d.generation != ctx._generation:
+                d = self._dev = ctx.upload(self.contig0_nolock(), with_qual=False)
+            return d.with_host_qual() if with_host_qual else d
 
     def contig0_nolock(self) -> ReadBatch:
         if self._reads is None:
@@ -157,5 +160,5 @@ def BuildIndex(bamfile, ref):
     reads = handle.contig0()
     if not reads.sorted:
         raise ValueError("Unsorted input. Pileup aborts")
-    counts = gpu.default_context().pileup_counts(reads, ref_length)
+    counts = gpu.default_context().pileup_counts(handle.device_reads(), ref_length)
     return frame_from_counts(counts)
