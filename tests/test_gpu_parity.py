@@ -575,3 +575,32 @@ def test_extract_inserts_long_insertions_both_forms(ctx, orc):
             exp, n = _oracle_modal(pileup, b, g["pos"])
             assert (g["string"], g["n_entries"]) == (exp, n), (kernel, g)
     assert got[5]["string"] == "C+12" + ins_a
+
+
+# ---------------------------------------------------------------------------- multi-GPU pieces on one device
+def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
+    """tc_allreduce_counts through a real NCCL communicator (one rank: identity), and the per-rank slices of
+    sharding.read_range summed on one device equal the full table."""
+    import torch
+
+    from trueconsense_b200 import sharding
+
+    pileup, _ = orc
+    ref, _, b = _synth("amplicon_deep")
+    L = len(ref)
+    exp = pileup.pileup_counts(b, L, threads=4)
+    comm = sharding.NcclComm(0, 1, 0)
+    try:
+        out = sharding.pileup_counts_read_range(ctx, b, L, 0, 1, comm)
+        ctx.allreduce_counts(out, comm)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), exp)
+    finally:
+        comm.close()
+    total = torch.zeros((8, L), dtype=torch.int32, device="cuda")
+    for rank in range(3):
+        lo, hi = sharding.read_range(b.n_reads, rank, 3)
+        part = torch.empty_like(total)
+        ctx.pileup_counts(b.slice(lo, hi), L, out=part)
+        total += part
+    assert np.array_equal(total.cpu().numpy(), exp)

@@ -237,6 +237,10 @@ class Context:
         self._check(self._lib.tc_pileup_counts(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), stream))
         return out
 
+    def allreduce_counts(self, counts_dev, comm, stream: int = 0) -> None:
+        """Sum a device count table over the ranks of ``comm`` (sharding.NcclComm) in place."""
+        self._check(self._lib.tc_allreduce_counts(self._h, _ptr(counts_dev), int(counts_dev.numel()), comm.handle, stream))
+
     # ------------------------------------------------------------------ (3) depth
     def depth(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):
         params = params or buildindex_params()
