@@ -82,6 +82,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds4(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
 }
@@ -142,65 +143,118 @@ __device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nop
     return o;
 }
 
-// Walk, common form (no pads, no zero-length ops anywhere in the sub-tile).  Lanes are kept in step on
-// their M/=/X ops: every outer iteration first lets each lane consume the ops in front of its next match op
-// (typically one I or D), then all lanes emit one match op together — so the match body runs once per
-// match op of the longest read instead of once per op.  Without pads an insertion counts iff the op before
-// it consumes the reference, and after a deletion that column reads "*+n..", no longer an X (one add does both).
-template <int ROWW>
-__device__ __forceinline__ walk_out walk_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi, int* err) {
-    const bool has_seq = lq != 0;
-    int y = 0, nd = 0, b_first = INT_MAX, last_end = 0, k = 0;
-    bool prev_ref = false, prev_d = false;
-    while (__any_sync(FULL, k < nops)) {
-        uint32_t c = 0;
-        bool at_m = false;
-        while (k < nops) {
-            c = lds(cs + 4 * k);
-            const uint32_t op = c & 15u;
-            const uint32_t fl = op_flags(op);
-            if (fl & 1u) { at_m = true; break; }
-            const int l = (int)(c >> 4);
-            const int e = x + l;
-            // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
-            // column x-1 (+1 I, and -1 X when that column belongs to a deletion)
-            const bool is_d = (op == OP_D), is_i = (op == OP_I);
-            const bool ev = (is_d && e <= ROWW) || (is_i && prev_ref && x >= 1 && x <= ROWW);
-            if (ev) reds(xi + 4 * (is_d ? x : x - 1), is_d ? 1u : (prev_d ? 0xffffu : 0x10000u));
-            if (is_d && l > 1 && e <= ROWW) for (int col = x + 1; col < e; ++col) reds(xi + 4 * col, 1u);
-            prev_ref = (fl & 2u) != 0;
-            prev_d = is_d;
-            x = (fl & 2u) ? e : x;
-            y += (fl & 4u) ? l : 0;
-            ++k;
+// Expansion passes of the general form (after walk_read_general).  A: one row word per iteration; a non-zero word
+// is the (end column, shift) of a new regime; the word becomes funnelshift(source words under D) cut at the end.
+// B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row.
+template <int WC>
+__device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t row, const uint32_t sq, const uint32_t cs) {
+    // ---- expand A: one row word per iteration; a non-zero word starts a new regime (end column, shift)
+    {
+        const bool any_m = wo.b_first != INT_MAX;
+        const int o0 = any_m ? wo.b_first >> 3 : 0;
+        const int words = any_m ? ((wo.last_end - 1) >> 3) - o0 + 1 : 0;
+        const int itmax = __reduce_max_sync(FULL, words);
+        // Every lane runs all itmax iterations, no branches: past its own last word a lane points at its
+        // row's pad word (always zero: no new regime, and the regime in force has ended, so it stores zero).
+        // Source addresses under a regime that has ended stay inside the warp's shared-memory slice.
+        uint32_t rp = row + 4u * o0;            // the row word of this iteration
+        const uint32_t rpad = row + 4u * WC;
+        uint32_t sp = sq + 4u * o0;             // the SEQ word under it (+ 4 * (D >> 3) of the regime in force)
+        int sh4 = 0, rem4 = 0, left = words;    // rem4: 4 * (columns the regime still covers from this word's first column)
+#pragma unroll 4
+        for (int it = 0; it < itmax; ++it) {
+            const uint32_t rq = left > 0 ? rp : rpad;
+            const uint32_t t = lds(rq);
+            if (t) {
+                const int D = (int)t >> 11;
+                rem4 = 4 * ((int)(t & 0x7ffu) - 8 * (o0 + it));
+                sp = sq + 4u * (o0 + it) + (uint32_t)((D >> 3) << 2);
+                sh4 = (D & 7) << 2;
+            }
+            const uint32_t v = __funnelshift_l(lds(sp + 4), lds(sp), sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4, 0));
+            sts(rq, v);
+            rem4 -= 32; rp += 4; sp += 4; --left;
         }
-        if (at_m) {
-            const int l = (int)(c >> 4);
-            const int e = x + l;
-            // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-            if (e > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
-            else {
-                if (has_seq) {
-                    const int D = y - x;
-                    const int fw8 = (x + 7) & ~7;
-                    if (fw8 < e) sts(row + (fw8 >> 1), (uint32_t)e | ((uint32_t)D << 11));
-                    if (x & 7) {
-                        const int fe = min(e, (x | 7) + 1);
-                        sts(cs + 4 * nd, (uint32_t)x | ((uint32_t)(fe - x) << 11) | ((uint32_t)D << 14));
-                    ++nd;
-                    }
-                    b_first = min(b_first, x);
-                    last_end = e;
-                }
-                x = e; y += l;
-                prev_ref = true; prev_d = false;
-                ++k;
+    }
+    // ---- expand B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row
+    {
+        const int itmax = __reduce_max_sync(FULL, wo.nd);
+        for (int it = 0; it < itmax; ++it) {
+            if (it < wo.nd) {
+                const uint32_t d = lds(cs + 4 * it);
+                const int b = (int)(d & 0x7ffu), flen = (int)((d >> 11) & 7u), D = (int)d >> 14;
+                const int o = b >> 3, kb = b & 7;
+                const int q0 = 8 * o + D;
+                const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
+                const uint32_t v = __funnelshift_l(lds(s + 4), lds(s), (q0 & 7) << 2);
+                const uint32_t m = (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, 4 * (kb + flen));
+                sts(row + 4 * o, lds(row + 4 * o) | (v & m));
             }
         }
-        if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
     }
-    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end; o.x_end = x;
-    return o;
+}
+
+// Common form, fused: walk and expansion in one pass (no descriptors).  One lane = one read; lanes are kept in
+// step on CHUNKS of match ops: a chunk is the part of an M/=/X op that falls into four consecutive row words
+// (at most 32 - (x & 7) columns).  Per outer iteration a lane first consumes the ops in front of its next match
+// op (typically one I or D: the sparse X / I events), then emits one chunk: five source words, four funnel
+// shifts under the op's shift D (query index = column + D), head / tail masks, four red.shared.or into its own
+// row.  Straight-line, ~45 instructions per chunk, nothing is written to be re-read by a later pass.
+// sq: shared address of the read's first staged SEQ word.  Returns the read's end column (x after the last op).
+template <int ROWW>
+__device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi,
+                                                const uint32_t sq, int* err) {
+    const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
+    int y = 0, k = 0, rem = 0;
+    bool prev_ref = false, prev_d = false;
+    while (__any_sync(FULL, k < nops || rem > 0)) {
+        if (rem == 0) {
+            while (k < nops) {
+                const uint32_t c = lds(cs + 4 * k);
+                const uint32_t op = c & 15u;
+                const uint32_t fl = op_flags(op);
+                const int l = (int)(c >> 4);
+                ++k;
+                if (fl & 1u) {
+                    // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
+                    if (x + l > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+                    else rem = l;
+                    break;
+                }
+                const int e = x + l;
+                // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
+                // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*")
+                const bool is_d = (op == OP_D), is_i = (op == OP_I);
+                const bool ev = (is_d && e <= ROWW) || (is_i && prev_ref && x >= 1 && x <= ROWW);
+                if (ev) reds(xi + 4 * (is_d ? x : x - 1), is_d ? 1u : (prev_d ? 0xffffu : 0x10000u));
+                if (is_d && l > 1 && e <= ROWW) for (int col = x + 1; col < e; ++col) reds(xi + 4 * col, 1u);
+                prev_ref = (fl & 2u) != 0;
+                prev_d = is_d;
+                x = (fl & 2u) ? e : x;
+                y += (fl & 4u) ? l : 0;
+                if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+            }
+        }
+        if (rem > 0) {
+            const int kb = x & 7;
+            const int cl = min(rem, 32 - kb);
+            if (has_seq) {
+                const int q0 = (x - kb) + (y - x);                  // query index under the first column of row word x >> 3
+                const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
+                const int sh4 = (q0 & 7) << 2;
+                const uint32_t w0 = lds(s), w1 = lds(s + 4), w2 = lds(s + 8), w3 = lds(s + 12), w4 = lds(s + 16);
+                const int rem4 = 4 * (kb + cl);                     // 4 * columns from the first row word's start to the chunk's end
+                const uint32_t ro = row + (uint32_t)((x >> 3) << 2);
+                reds_or(ro, __funnelshift_l(w1, w0, sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
+                reds_or(ro + 4, __funnelshift_l(w2, w1, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32, 0)));
+                reds_or(ro + 8, __funnelshift_l(w3, w2, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 64, 0)));
+                reds_or(ro + 12, __funnelshift_l(w4, w3, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 96, 0)));
+            }
+            x += cl; y += cl; rem -= cl;
+            prev_ref = true; prev_d = false;
+        }
+    }
+    return x;
 }
 
 template <int WC>
@@ -433,9 +487,16 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         const uint32_t cs = cig_s + 4u * (co - cbase_al);
         const int nops = act ? (int)(co_next - co) : 0;
         const int x0 = p - w0;
-        walk_out wo;
-        if (cig_exotic) wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
-        else wo = walk_read_common<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
+        const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
+        int x_end;
+        if (!cig_exotic) {
+            x_end = emit_read_common<ROWW>(cs, nops, x0, lq, row, xi, sq, &a.status->err);
+        } else {
+            // pads or zero-length ops somewhere in the sub-tile (rare): the general three-pass form
+            const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
+            x_end = wo.x_end;
+            expand_rows<WC>(wo, row, sq, cs);
+        }
 
         // ---- without a span pass: sort order, range, span statistics and the two ends of every read's span in the
         // coverage difference array (adds to the same column are combined inside the warp first)
@@ -444,7 +505,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             if (lane == 0) pprev = prev_pos;
             if (lane < n && p < pprev) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
             prev_pos = __shfl_sync(FULL, p, n - 1);
-            const int span = act ? wo.x_end - x0 : 0;
+            const int span = act ? x_end - x0 : 0;
             const bool bad = act && (p >= L || p + span > L);
             if (bad) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
             const bool has = act && span > 0 && !bad;
@@ -456,51 +517,6 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             if (has && (__ffs(g1) - 1) == lane) atomicAdd(&a.diff[p + span], -__popc(g1));
         }
 
-        // ---- expand A: one row word per iteration; a non-zero word starts a new regime (end column, shift)
-        const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
-        {
-            const bool any_m = wo.b_first != INT_MAX;
-            const int o0 = any_m ? wo.b_first >> 3 : 0;
-            const int words = any_m ? ((wo.last_end - 1) >> 3) - o0 + 1 : 0;
-            const int itmax = __reduce_max_sync(FULL, words);
-            // Every lane runs all itmax iterations, no branches: past its own last word a lane points at its
-            // row's pad word (always zero: no new regime, and the regime in force has ended, so it stores zero).
-            // Source addresses under a regime that has ended stay inside the warp's shared-memory slice.
-            uint32_t rp = row + 4u * o0;            // the row word of this iteration
-            const uint32_t rpad = row + 4u * WC;
-            uint32_t sp = sq + 4u * o0;             // the SEQ word under it (+ 4 * (D >> 3) of the regime in force)
-            int sh4 = 0, rem4 = 0, left = words;    // rem4: 4 * (columns the regime still covers from this word's first column)
-#pragma unroll 4
-            for (int it = 0; it < itmax; ++it) {
-                const uint32_t rq = left > 0 ? rp : rpad;
-                const uint32_t t = lds(rq);
-                if (t) {
-                    const int D = (int)t >> 11;
-                    rem4 = 4 * ((int)(t & 0x7ffu) - 8 * (o0 + it));
-                    sp = sq + 4u * (o0 + it) + (uint32_t)((D >> 3) << 2);
-                    sh4 = (D & 7) << 2;
-                }
-                const uint32_t v = __funnelshift_l(lds(sp + 4), lds(sp), sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4, 0));
-                sts(rq, v);
-                rem4 -= 32; rp += 4; sp += 4; --left;
-            }
-        }
-        // ---- expand B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row
-        {
-            const int itmax = __reduce_max_sync(FULL, wo.nd);
-            for (int it = 0; it < itmax; ++it) {
-                if (it < wo.nd) {
-                    const uint32_t d = lds(cs + 4 * it);
-                    const int b = (int)(d & 0x7ffu), flen = (int)((d >> 11) & 7u), D = (int)d >> 14;
-                    const int o = b >> 3, kb = b & 7;
-                    const int q0 = 8 * o + D;
-                    const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
-                    const uint32_t v = __funnelshift_l(lds(s + 4), lds(s), (q0 & 7) << 2);
-                    const uint32_t m = (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, 4 * (kb + flen));
-                    sts(row + 4 * o, lds(row + 4 * o) | (v & m));
-                }
-            }
-        }
         __syncwarp();
 
         // ---- column sum: lane owns row words lane + 32 j, all 32 rows
