@@ -604,3 +604,44 @@ def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
         ctx.pileup_counts(b.slice(lo, hi), L, out=part)
         total += part
     assert np.array_equal(total.cpu().numpy(), exp)
+
+
+# ---------------------------------------------------------------------------- BASELINE.json's five configs
+FIVE = [(0, 1.0), (1, 0.1), (2, 0.2), (3, 0.005), (4, 0.1)]
+
+
+@pytest.mark.parametrize("idx,scale", FIVE)
+def test_five_configs_hot_path_vs_oracle(ctx, orc, idx, scale):
+    """Each of BASELINE.json's configs at a size the oracle finishes in seconds: count table, call table,
+    insertion candidates and insertion calls bit for bit; then the host walk runs over the GPU's table."""
+    from trueconsense_b200 import Sequences, synth
+
+    pileup, call = orc
+    w = synth.config(idx, scale=scale)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    exp = pileup.pileup_counts(b, L, threads=8)
+    got = ctx.pileup_counts(b, L)
+    assert np.array_equal(got, exp)
+    assert got[0].sum() == b.count_aligned_bases(0x4)
+    table = ctx.call(got, L, w.mincov, True)
+    ref = call.call_table(exp.astype(np.int64), w.mincov, True)
+    for k in ("call_char", "flags", "xrun", "ambig_char"):
+        assert np.array_equal(getattr(table, k), ref[k]), k
+    cands = [int(c) for c in ctx.list_insert_candidates(table.flags, L)]
+    assert cands == call.insert_candidates(exp.astype(np.int64), w.mincov)
+    positions = sorted(set(cands) | {1, L // 3, L // 2, L})
+    calls = ctx.extract_inserts(b, L, positions)
+    inserts = {}
+    for g in calls:
+        s_exp, n = _oracle_modal(pileup, b, g["pos"])
+        assert (g["string"], g["n_entries"]) == (s_exp, n), g
+        bases, size = call.extract_insert([s_exp] if s_exp else "")
+        if g["pos"] in cands and bases is not None:
+            inserts[g["pos"]] = {size: bases}
+    gff = synth.gff_dict(w.feats)
+    if idx == 4:
+        return      # the walk over 197 kb x 114 features is the host's business (tests/test_host_cpu.py covers its logic)
+    cons, newgff = Sequences.consensus_from_inserts(w.mincov, got, gff, True, (True, inserts) if inserts else (False, None), True)
+    assert len(cons) >= L - 64 and set(cons) <= set("ACGTNacgtn-MRWSYKVHDB")
+    assert set(newgff) == set(gff)
