@@ -222,7 +222,6 @@ def run_ours(args):
         kernel_ms.append(ctx.last_pileup_kernel_ms())
     ev1.record()
     barrier()
-    clocks = sampler.stop()
     launches = ctx.launches - launches0
     ms_total = ev0.elapsed_time(ev1)
     # ---------------- end to end through the C-ABI with host buffers: `e2e`
@@ -249,6 +248,7 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()          # sampled over both timed regions (device-resident steps, then end-to-end steps)
     h2d, d2h_lib = (b - a_ for a_, b in zip(xfer0, ctx.transfer_bytes()))
     h2d //= args.steps
     d2h = d2h_lib // args.steps + int(h.nbytes)

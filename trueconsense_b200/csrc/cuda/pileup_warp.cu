@@ -16,19 +16,22 @@
 //               and the window moves.  Deep data flushes once per thousands of reads.
 //   stage       the packed SEQ words and CIGAR ops of the <= 32 reads are contiguous in HBM: the warp
 //               copies them to its shared-memory slice as 16-byte vectors, byte-swapping SEQ words to
-//               "first base in the top nibble".  Codes that are not one-hot (N, IUPAC) are detected on
-//               the way (3 ops per word) and cleared in a second pass only when a sub-tile has any.
-//   walk        one lane per read, warp-uniform loop over CIGAR ops, straight-line body: every M/=/X op
-//               [b, e) with shift D (query index = column + D) leaves (e, D) in the read's row at the
-//               first 8-column word it covers the start of, and — when b is not a multiple of 8 — a
-//               head-fragment descriptor in place of the consumed ops.  Deletion columns and insertion
-//               anchors (sparse) go to packed 16+16-bit shared counters.
-//   expand A    one lane per read, one row word per iteration: a non-zero word is the (e, D) of a new
-//               regime; the word becomes funnelshift(source words under D) cut at e.  No searching, no
-//               inner loop.
-//   expand B    one head fragment per iteration, OR-ed into the lane's own row word.
+//               "first base in the top nibble"; the next sub-tile's lines are prefetched to L2.  Codes that
+//               are not one-hot (N, IUPAC) are detected on the way (3 ops per word) and cleared afterwards,
+//               one dirty vector per lane and iteration.
+//   emit        one lane per read, walk and expansion fused (emit_read_common): lanes stay in step on
+//               chunks of match ops — the part of an M/=/X op inside four consecutive 8-column row words —
+//               consuming the I / D / S ops in front of it first (deletion columns and insertion anchors,
+//               sparse, go to packed 16+16-bit shared counters with one red.shared.add), then five source
+//               words, four funnel shifts under the op's shift D (query index = column + D), head / tail
+//               masks, four red.shared.or into the lane's own row.  Nothing is written to be re-read.
+//               Sub-tiles containing pads or zero-length ops (rare) take the general three-pass form instead
+//               (walk_read_general + expand_rows: htslib's full look-ahead state).
 //   column sum  lane j owns row words j, j+32, ...: 32 rows go through two 16-input carry-save trees
 //               into the bit-sliced counters (4 + HI planes per word, in registers across sub-tiles).
+//   span pass   when the caller bounds the longest reference span (tc_reads_t.max_ref_span) the kernel also
+//               checks sort order and range and adds the two ends of every read's span to the coverage
+//               difference array (combined inside the warp with match.any) — no separate pass over the CIGARs.
 #include <limits.h>
 
 #include "pileup.cuh"
