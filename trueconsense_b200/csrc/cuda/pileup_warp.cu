@@ -238,6 +238,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
             }
         }
+        __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
         if (rem > 0) {
             const int kb = x & 7;
             const int cl = min(rem, 32 - kb);
