@@ -208,34 +208,37 @@ template <int ROWW>
 __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi,
                                                 const uint32_t sq, int* err) {
     const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
-    int y = 0, k = 0, rem = 0;
-    bool prev_ref = false, prev_d = false;
-    while (__any_sync(FULL, k < nops || rem > 0)) {
+    int y = 0, rem = 0;
+    uint32_t cp = cs;                       // next op
+    const uint32_t cend = cs + 4u * (uint32_t)nops;
+    // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
+    uint32_t prev = 0;
+    while (__any_sync(FULL, cp < cend || rem > 0)) {
         if (rem == 0) {
-            while (k < nops) {
-                const uint32_t c = lds(cs + 4 * k);
+            while (cp < cend) {
+                const uint32_t c = lds(cp);
                 const uint32_t op = c & 15u;
                 const uint32_t fl = op_flags(op);
                 const int l = (int)(c >> 4);
-                ++k;
+                cp += 4;
                 if (fl & 1u) {
                     // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-                    if (x + l > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+                    if (x + l > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
                     else rem = l;
                     break;
                 }
-                const int e = x + l;
                 // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
-                // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*")
-                const bool is_d = (op == OP_D), is_i = (op == OP_I);
-                const bool ev = (is_d && e <= ROWW) || (is_i && prev_ref && x >= 1 && x <= ROWW);
-                if (ev) reds(xi + 4 * (is_d ? x : x - 1), is_d ? 1u : (prev_d ? 0xffffu : 0x10000u));
-                if (is_d && l > 1 && e <= ROWW) for (int col = x + 1; col < e; ++col) reds(xi + 4 * col, 1u);
-                prev_ref = (fl & 2u) != 0;
-                prev_d = is_d;
-                x = (fl & 2u) ? e : x;
+                // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*").
+                // Without zero-length ops the anchor exists whenever the previous op consumed the reference; a
+                // column past the window is clamped (the read is rejected right below, its counts are void).
+                const bool is_d = (op == OP_D);
+                if (is_d || (op == OP_I && (prev & 2u)))
+                    reds(xi + 4u * (uint32_t)min(is_d ? x : x - 1, ROWW - 1), is_d ? 1u : ((prev & 1u) ? 0xffffu : 0x10000u));
+                if (is_d && l > 1) for (int col = x + 1; col < min(x + l, ROWW); ++col) reds(xi + 4 * col, 1u);
+                prev = (fl & 2u) | (is_d ? 1u : 0u);
+                x += (fl & 2u) ? l : 0;
                 y += (fl & 4u) ? l : 0;
-                if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); k = nops; }
+                if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
             }
         }
         __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
@@ -255,7 +258,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 reds_or(ro + 12, __funnelshift_l(w4, w3, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 96, 0)));
             }
             x += cl; y += cl; rem -= cl;
-            prev_ref = true; prev_d = false;
+            prev = 2u;
         }
     }
     return x;
