@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                     if (lane == 4) prefetch_l2(a.r.flag + rm);
                 }
             }
-            uint32_t dirty = 0, exacc = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
+            uint32_t dirty = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
             const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
             if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
@@ -452,16 +452,18 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                     for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
                 }
             }
+            // pads and zero-length ops: min over the words of min((op ^ P), len) is 0 exactly when one is present
+            uint32_t exmin = 1u;
             if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
                 const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
                 for (int i = lane; i < ncv; i += 64) {
                     uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
                     const bool b1 = i + 32 < ncv;
                     if (b1) v1 = __ldg(csrc + i + 32);
-                    exacc |= (uint32_t)((v0.x & 15u) == OP_P) | (uint32_t)(v0.x < 16u) | (uint32_t)((v0.y & 15u) == OP_P) | (uint32_t)(v0.y < 16u) |
-                             (uint32_t)((v0.z & 15u) == OP_P) | (uint32_t)(v0.z < 16u) | (uint32_t)((v0.w & 15u) == OP_P) | (uint32_t)(v0.w < 16u) |
-                             (uint32_t)((v1.x & 15u) == OP_P) | (uint32_t)(v1.x < 16u) | (uint32_t)((v1.y & 15u) == OP_P) | (uint32_t)(v1.y < 16u) |
-                             (uint32_t)((v1.z & 15u) == OP_P) | (uint32_t)(v1.z < 16u) | (uint32_t)((v1.w & 15u) == OP_P) | (uint32_t)(v1.w < 16u);
+                    exmin = min(exmin, min(min(min((v0.x & 15u) ^ 6u, v0.x >> 4), min((v0.y & 15u) ^ 6u, v0.y >> 4)),
+                                           min(min((v0.z & 15u) ^ 6u, v0.z >> 4), min((v0.w & 15u) ^ 6u, v0.w >> 4))));
+                    exmin = min(exmin, min(min(min((v1.x & 15u) ^ 6u, v1.x >> 4), min((v1.y & 15u) ^ 6u, v1.y >> 4)),
+                                           min(min((v1.z & 15u) ^ 6u, v1.z >> 4), min((v1.w & 15u) ^ 6u, v1.w >> 4))));
                     sts4(cig_s + 16 * i, v0);
                     if (b1) sts4(cig_s + 16 * (i + 32), v1);
                 }
@@ -469,11 +471,11 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 for (int i = lane; i < 4 * ncv; i += 32) {
                     const int64_t oi = (int64_t)cbase_al + i;
                     const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
-                    exacc |= (uint32_t)((c & 15u) == OP_P) | (uint32_t)(c < 16u);
+                    exmin = min(exmin, min((c & 15u) ^ 6u, c >> 4));
                     sts(cig_s + 4 * i, c);
                 }
             }
-            cig_exotic = __any_sync(FULL, exacc != 0);
+            cig_exotic = __any_sync(FULL, exmin == 0u);
             // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
             // Only the vectors that hold one are revisited, one per lane and iteration.
             while (__any_sync(FULL, dirty != 0)) {
