@@ -52,8 +52,8 @@ template <int WC> struct geom {
     static constexpr int RS = WC + 1;               // padded row stride (words)
     static constexpr int NW = WC / 32;              // row words owned by one lane in the column sum
     static constexpr int SEQ_PAD = 4;               // zero words in front of the staged SEQ stream
-    static constexpr int SEQ_CAP = WC * 28;         // staged SEQ words per sub-tile (WC=64: 32 reads of 448 bases)
-    static constexpr int CIG_CAP = WC * 16;         // staged CIGAR ops per sub-tile
+    static constexpr int SEQ_CAP = WC * 27;         // staged SEQ words per sub-tile (WC=64: 32 reads of 432 bases)
+    static constexpr int CIG_CAP = WC * 14;         // staged CIGAR ops per sub-tile
     static constexpr int SEQ_WORDS = SEQ_PAD + SEQ_CAP + 8;
     static constexpr int CIG_WORDS = CIG_CAP + 8;
     static constexpr int WARP_WORDS = 32 * RS + SEQ_WORDS + CIG_WORDS + ROWW;
@@ -238,7 +238,6 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 prev = (fl & 2u) | (is_d ? 1u : 0u);
                 x += (fl & 2u) ? l : 0;
                 y += (fl & 4u) ? l : 0;
-                if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
             }
         }
         __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
@@ -261,6 +260,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
             prev = 2u;
         }
     }
+    if (x > ROWW) atomicCAS(err, 0, TC_ERR_CAPACITY);       // deletions / skips ran past the window (their event columns were clamped)
     return x;
 }
 
