@@ -197,7 +197,8 @@ __device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t ro
     }
 }
 
-// Common form, fused: walk and expansion in one pass (no descriptors).  One lane = one read; lanes are kept in
+// Common form (no pads, no zero-length ops, every read has SEQ), fused: walk and expansion in one pass, no
+// descriptors.  One lane = one read; lanes are kept in
 // step on CHUNKS of match ops: a chunk is the part of an M/=/X op that falls into four consecutive row words
 // (at most 32 - (x & 7) columns).  Per outer iteration a lane first consumes the ops in front of its next match
 // op (typically one I or D: the sparse X / I events), then emits one chunk: five source words, four funnel
@@ -207,7 +208,6 @@ __device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t ro
 template <int ROWW>
 __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi,
                                                 const uint32_t sq, int* err) {
-    const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
     int y = 0, rem = 0;
     uint32_t cp = cs;                       // next op
     const uint32_t cend = cs + 4u * (uint32_t)nops;
@@ -223,7 +223,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 cp += 4;
                 if (fl & 1u) {
                     // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-                    if (x + l > ROWW || (has_seq && y + l > lq)) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
+                    if (x + l > ROWW || y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
                     else rem = l;
                     break;
                 }
@@ -244,7 +244,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
         if (rem > 0) {
             const int kb = x & 7;
             const int cl = min(rem, 32 - kb);
-            if (has_seq) {
+            {
                 const int q0 = (x - kb) + (y - x);                  // query index under the first column of row word x >> 3
                 const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
                 const int sh4 = (q0 & 7) << 2;
@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                     sts(cig_s + 4 * i, c);
                 }
             }
-            cig_exotic = __any_sync(FULL, exmin == 0u);
+            // ... and reads without SEQ ('*': every base reads 'N'): the general form below handles all of these
+            cig_exotic = __any_sync(FULL, exmin == 0u || (lane < n && lq == 0));
             // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
             // Only the vectors that hold one are revisited, one per lane and iteration.
             while (__any_sync(FULL, dirty != 0)) {
