@@ -68,6 +68,8 @@ def build_cuda(force: bool = False) -> str:
         cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
                "-Xcompiler", "-fvisibility=hidden", "-cudart", "static", "--fmad=false",
                "-I", INCLUDE, "-I", os.path.join(CSRC, "cuda")] + CUDA_ARCH_FLAGS
+        if os.environ.get("TC_NVCC_DEFS"):           # e.g. "-DTC_CHUNK_WORDS=6" (tuning experiments)
+            cmd += os.environ["TC_NVCC_DEFS"].split()
         if os.environ.get("TC_PTXAS_V"):
             cmd += ["-Xptxas", "-v"]
         cmd += ["-o", CUDA_LIB] + cu + ["-ldl"]

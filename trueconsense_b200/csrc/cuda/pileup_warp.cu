@@ -42,6 +42,10 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int MIN_SLACK = 64;
 constexpr int HI_PLANES = 7;            // bit-sliced planes above "eights": 15 + 16*127 = 2047 reads per run
 constexpr int RUN_CAP = 2047;
+#ifndef TC_CHUNK_WORDS
+#define TC_CHUNK_WORDS 6
+#endif
+constexpr int CHUNK_WORDS = TC_CHUNK_WORDS;     // row words per emitted chunk of a match op
 // per op: bit0 = M/=/X, bit1 = consumes reference, bit2 = consumes query (MIDNSHP=X -> 0..8)
 constexpr uint32_t OPFLAGS = 7u | (4u << 3) | (2u << 6) | (2u << 9) | (4u << 12) | (7u << 21) | (7u << 24);
 // clamped shift: ops 11..15 (not defined by BAM) index past the table and read 0
@@ -199,13 +203,13 @@ __device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t ro
 
 // Common form (no pads, no zero-length ops, every read has SEQ), fused: walk and expansion in one pass, no
 // descriptors.  One lane = one read; lanes are kept in
-// step on CHUNKS of match ops: a chunk is the part of an M/=/X op that falls into four consecutive row words
-// (at most 32 - (x & 7) columns).  Per outer iteration a lane first consumes the ops in front of its next match
-// op (typically one I or D: the sparse X / I events), then emits one chunk: five source words, four funnel
-// shifts under the op's shift D (query index = column + D), head / tail masks, four red.shared.or into its own
-// row.  Straight-line, ~45 instructions per chunk, nothing is written to be re-read by a later pass.
+// step on CHUNKS of match ops: a chunk is the part of an M/=/X op that falls into CW consecutive row words
+// (at most 8 * CW - (x & 7) columns; CW = 6 measured best on ONT-like reads, 4 and 8 within 3 %).  Per outer iteration a lane first consumes the ops in front of its next match
+// op (typically one I or D: the sparse X / I events), then emits one chunk: CW + 1 source words, CW funnel
+// shifts under the op's shift D (query index = column + D), head / tail masks, CW red.shared.or into its own
+// row.  Straight-line, nothing is written to be re-read by a later pass.
 // sq: shared address of the read's first staged SEQ word.  Returns the read's end column (x after the last op).
-template <int ROWW>
+template <int ROWW, int CW>
 __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi,
                                                 const uint32_t sq, int* err) {
     int y = 0, rem = 0;
@@ -243,18 +247,20 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
         __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
         if (rem > 0) {
             const int kb = x & 7;
-            const int cl = min(rem, 32 - kb);
+            const int cl = min(rem, 8 * CW - kb);
             {
                 const int q0 = (x - kb) + (y - x);                  // query index under the first column of row word x >> 3
                 const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
                 const int sh4 = (q0 & 7) << 2;
-                const uint32_t w0 = lds(s), w1 = lds(s + 4), w2 = lds(s + 8), w3 = lds(s + 12), w4 = lds(s + 16);
+                uint32_t w[CW + 1];
+#pragma unroll
+                for (int j = 0; j <= CW; ++j) w[j] = lds(s + 4 * j);
                 const int rem4 = 4 * (kb + cl);                     // 4 * columns from the first row word's start to the chunk's end
                 const uint32_t ro = row + (uint32_t)((x >> 3) << 2);
-                reds_or(ro, __funnelshift_l(w1, w0, sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
-                reds_or(ro + 4, __funnelshift_l(w2, w1, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32, 0)));
-                reds_or(ro + 8, __funnelshift_l(w3, w2, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 64, 0)));
-                reds_or(ro + 12, __funnelshift_l(w4, w3, sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 96, 0)));
+                reds_or(ro, __funnelshift_l(w[1], w[0], sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
+#pragma unroll
+                for (int j = 1; j < CW; ++j)
+                    reds_or(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32 * j, 0)));
             }
             x += cl; y += cl; rem -= cl;
             prev = 2u;
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
         int x_end;
         if (!cig_exotic) {
-            x_end = emit_read_common<ROWW>(cs, nops, x0, lq, row, xi, sq, &a.status->err);
+            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, lq, row, xi, sq, &a.status->err);
         } else {
             // pads or zero-length ops somewhere in the sub-tile (rare): the general three-pass form
             const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
