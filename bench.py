@@ -134,6 +134,28 @@ def cpu_port(batch, L, mincov, threads, max_reads):
     return bases, t2 - t0, f"first {sub.n_reads} start-sorted reads of the sample ({bases} aligned bases); pileup {t1 - t0:.2f}s + call/inserts {t2 - t1:.2f}s"
 
 
+def host_decode_rate(batch, L, max_reads=200_000):
+    """Host BAM decode, reported separately from the kernels (north_star): a bounded slice of the sample is
+    written as a BGZF-compressed BAM and decoded back into the flat arrays with all host threads
+    (trueconsense_b200/csrc/host/bamio.c).  Returns a dict for the JSON line."""
+    import tempfile
+
+    from trueconsense_b200 import bamio
+
+    sub = batch.slice(0, min(batch.n_reads, max_reads))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "decode.bam")
+        bamio.write_bam(path, sub, "ref", L, level=1)
+        size = os.path.getsize(path)
+        t0 = time.perf_counter()
+        back = bamio.read_bam(path)
+        dt = time.perf_counter() - t0
+    bases = sub.count_aligned_bases(0)
+    return {"reads": int(back.n_reads), "bam_bytes": int(size), "seconds": dt, "aligned_bases_per_s": bases / dt,
+            "threads": os.cpu_count() or 1, "t_inflate_s": float(back.info.get("t_inflate_s", 0.0)),
+            "t_parse_s": float(back.info.get("t_parse_s", 0.0))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -275,6 +297,10 @@ def run_ours(args):
             opile.build()
             cb, ct, desc = cpu_port(batch, L, w.mincov, 1, int(args.cpu_reads))
             cpu = {"value": cb / ct, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+        try:
+            decode = host_decode_rate(batch, L)
+        except Exception as e:      # reporting aid only
+            decode = {"error": str(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,6 +317,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
+            "host_decode": decode,
         }
         print(json.dumps(line))
     if world > 1:
