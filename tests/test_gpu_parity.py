@@ -15,7 +15,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 pytestmark = pytest.mark.gpu
 
 MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
-KERNELS = [1, 2, 3]   # pileup kernel variants: 1 scatter (smem atomics), 2 SWAR CTA tiles, 3 SWAR warp streams
+KERNELS = [1, 2, 3, 4]   # pileup kernel variants: 1 scatter (smem atomics), 2 SWAR CTA tiles, 3 SWAR warp streams, 4 pieces of long reads + 3
 
 
 @pytest.fixture(scope="module")
@@ -45,7 +45,7 @@ def _pileup(ctx, b, L, kernel):
     try:
         return ctx.pileup_counts(b, L, gpu.buildindex_params(kernel))
     except gpu.TcError as e:
-        if kernel in (2, 3) and e.code == -8:
+        if kernel in (2, 3, 4) and e.code == -8:
             return ctx.pileup_counts(b, L, gpu.buildindex_params(0))
         raise
 
@@ -645,3 +645,26 @@ def test_five_configs_hot_path_vs_oracle(ctx, orc, idx, scale):
     cons, newgff = Sequences.consensus_from_inserts(w.mincov, got, gff, True, (True, inserts) if inserts else (False, None), True)
     assert len(cons) >= L - 64 and set(cons) <= set("ACGTNacgtn-MRWSYKVHDB")
     assert set(newgff) == set(gff)
+
+
+def test_long_reads_take_the_pieces_path(ctx, orc):
+    """Reads spanning thousands of columns are cut into pieces and go through the SWAR kernel (variant 4) — no
+    fallback to the scatter kernel — with and without a span bound; BASELINE config 5 shape."""
+    import copy
+
+    from trueconsense_b200 import gpu, synth
+
+    pileup, _ = orc
+    w = synth.config(4, scale=0.05)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    assert b.max_ref_span > 5000
+    exp = pileup.pileup_counts(b, L, threads=8)
+    assert np.array_equal(ctx.pileup_counts(b, L, gpu.buildindex_params(4)), exp)      # explicit: raises instead of falling back
+    nb = copy.copy(b)
+    nb.max_ref_span = -1
+    l0 = ctx.launches
+    assert np.array_equal(ctx.pileup_counts(nb, L), exp)                                # no bound: 3 declines, 4 takes over
+    assert ctx.launches - l0 < 40
+    ref, _, s = _synth("long_reads")
+    assert np.array_equal(ctx.pileup_counts(s, len(ref), gpu.buildindex_params(4)), pileup.pileup_counts(s, len(ref), threads=4))

@@ -219,8 +219,10 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
     const bool per_entry = p->min_base_quality > 0;
     int variant = p->kernel;
-    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? 3 : 1;
-    if (variant < 1 || variant > 3) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
+    // reads longer than variant 3's widest window are cut into pieces first (variant 4, pileup_long.cu)
+    const int LONG_SPAN = 1024 - 8 - 64;
+    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? (a.span_hint > LONG_SPAN ? 4 : 3) : 1;
+    if (variant < 1 || variant > 4) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
     if (variant != 1 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels have no base-quality filter; use kernel=1");
     if (variant != 1 && !tc_pileup_swar_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
     if (a.r.n > 0) {
@@ -228,12 +230,13 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         if (variant != 1) {
             // coverage ends, span statistics and the sortedness / range checks: one thread per read — unless the
             // caller bounded the longest span, then variant 3 does all of that while it walks the CIGARs anyway
-            if (variant != 3 || a.span_hint == 0) {
+            if (variant != 3 || a.span_hint == 0 || a.span_hint > LONG_SPAN) {
                 a.span_hint = 0;
                 depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
                 TC_LAUNCH_CHECK();
             }
-            rc = variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_swar_launch(ctx, a, s);
+            a.pieces = nullptr; a.piece_order = nullptr; a.n_pieces = 0;
+            rc = variant == 4 ? tc_pileup_long_launch(ctx, a, s) : variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_swar_launch(ctx, a, s);
             if (rc) return rc;
         } else {
             int n_chunks = (int)((a.r.n + SC_CHUNK - 1) / SC_CHUNK);
@@ -259,9 +262,15 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     rc = fetch_status(ctx, d_status, &st, s);
     if (rc) return rc;
     if (st.err == TC_ERR_CAPACITY && variant != 1 && p->kernel == 0) {
-        // a read larger than the SWAR kernels' windows / staging buffers: the scatter kernel has no such limit
+        // reads spanning more than variant 3's window: cut them into pieces (variant 4); anything else the SWAR
+        // kernels decline (pads in long reads, a single read beyond the staging buffers): the scatter kernel
         tc_pileup_params_t q = *p;
-        q.kernel = 1;
+        q.kernel = (variant == 3 && a.span_hint == 0 && st.max_span > LONG_SPAN) ? 4 : 1;
+        if (q.kernel == 4) {
+            const int rc4 = tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
+            if (rc4 != TC_ERR_CAPACITY) return rc4;
+            q.kernel = 1;
+        }
         return tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
     }
     if (st.err == TC_ERR_CAPACITY)

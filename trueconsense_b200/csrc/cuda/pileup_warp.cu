@@ -210,9 +210,9 @@ __device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t ro
 // row.  Straight-line, nothing is written to be re-read by a later pass.
 // sq: shared address of the read's first staged SEQ word.  Returns the read's end column (x after the last op).
 template <int ROWW, int CW>
-__device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int lq, const uint32_t row, const uint32_t xi,
-                                                const uint32_t sq, int* err) {
-    int y = 0, rem = 0;
+__device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int y0, const int lq, const uint32_t row,
+                                                const uint32_t xi, const uint32_t sq, int* err) {
+    int y = y0, rem = 0;       // y0: query index of the first base relative to sq's first nibble (pieces of long reads: 0..7)
     uint32_t cp = cs;                       // next op
     const uint32_t cend = cs + 4u * (uint32_t)nops;
     // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
@@ -270,7 +270,7 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
     return x;
 }
 
-template <int WC>
+template <int WC, bool PIECES>
 __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pileup_args a) {
     using G = geom<WC>;
     constexpr int ROWW = G::ROWW, RS = G::RS, NW = G::NW;
@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
 
     // which geometry handles this batch: the narrowest whose slack is usable
     // the longest reference span: the caller's bound (tc_reads_t.max_ref_span) or what the span pass found
-    const bool fold = a.span_hint > 0;      // no span pass ran: this kernel also does its checks and the coverage ends
-    const int ms = (max(fold ? a.span_hint : a.status->max_span, 1) + 7) & ~7;
+    // (PIECES: the "reads" are pieces of at most PIECE_COLS columns; the span pass ran over the real reads)
+    const bool fold = !PIECES && a.span_hint > 0;   // no span pass ran: this kernel also does its checks and the coverage ends
+    const int ms = PIECES ? PIECE_COLS : ((max(fold ? a.span_hint : a.status->max_span, 1) + 7) & ~7);
     const int slack64 = (512 - ms - 8) & ~7, slack128 = (1024 - ms - 8) & ~7;
     const bool mine = (WC == 64) ? (slack64 >= MIN_SLACK) : (slack64 < MIN_SLACK);
     if (!mine) return;
@@ -300,9 +301,9 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     if (lane < G::SEQ_PAD) sts(seq_s + 4 * lane, 0u);
     __syncwarp();
 
-    const int64_t n_reads = a.r.n;
-    const int64_t n_seq_words = (int64_t)a.r.seq_off[n_reads];
-    const int64_t n_ops_total = (int64_t)a.r.cigar_off[n_reads];
+    const int64_t n_reads = PIECES ? a.n_pieces : a.r.n;
+    const int64_t n_seq_words = (int64_t)a.r.seq_off[a.r.n];
+    const int64_t n_ops_total = PIECES ? 0 : (int64_t)a.r.cigar_off[a.r.n];
     const int64_t gw = (int64_t)blockIdx.x * G::WARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * G::WARPS;
     int64_t r = gw * n_reads / n_warps;
@@ -363,150 +364,216 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     };
 
     while (r < r_end) {
-        // ---- metadata of the next (up to) 32 reads, one per lane
         const int nmax = (int)min((int64_t)32, r_end - r);
         const bool valid = lane < nmax;
         const int64_t ri = r + (valid ? lane : 0);
-        const int p = a.r.pos[ri];
-        const uint32_t so = a.r.seq_off[ri], so_next = a.r.seq_off[ri + 1];
-        const uint32_t co = a.r.cigar_off[ri], co_next = a.r.cigar_off[ri + 1];
-        const uint32_t flg = a.r.flag[ri];
-        const int lq = a.r.l_seq[ri];
-        bool passes = !(flg & (a.flag_filter | 4u)) && !(a.ignore_orphans && (flg & 1u) && !(flg & 2u));
-        if (a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[ri] < a.min_mapq) passes = false;
-        const int p0 = __shfl_sync(FULL, p, 0);
-        const bool fresh = (w0 == INT_MIN);
-        if (fresh) w0 = max(p0, 0) & ~7;
-        const uint32_t sbase_al = __shfl_sync(FULL, so, 0) & ~3u;
-        const uint32_t cbase_al = __shfl_sync(FULL, co, 0) & ~3u;
-        const bool inwin = p >= w0 && p - w0 < slack;
-        const bool fits = valid && inwin && (so_next - sbase_al + 1 <= (uint32_t)G::SEQ_CAP) && (co_next - cbase_al <= (uint32_t)G::CIG_CAP);
-        const unsigned fm = __ballot_sync(FULL, fits);
-        int n = (fm == FULL) ? 32 : __ffs(~fm) - 1;
-        n = min(n, RUN_CAP - run_reads);
-        if (n == 0) {
-            const bool inwin0 = __shfl_sync(FULL, (int)inwin, 0) != 0;
-            if ((!inwin0 && !fresh) || run_reads >= RUN_CAP) {      // the window (or the counters' range) is used up
-                flush();
-                w0 = INT_MIN; run_reads = 0;
+        int p, lq, n, nops_lane, y0 = 0;
+        bool passes = true, cig_exotic = false;
+        uint32_t cs, sq_lane;
+        if constexpr (PIECES) {
+            // ---- pieces of long reads: one record per lane, gathered through the start-sorted order
+            const tc_piece* pc = a.pieces + a.piece_order[ri];
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(pc)), m1 = __ldg(reinterpret_cast<const uint4*>(pc) + 1);
+            p = (int)m0.x; lq = (int)m1.y; y0 = (int)m1.z;
+            const uint32_t so = m0.y, co = m0.z;
+            nops_lane = (int)m0.w;
+            const int p0 = __shfl_sync(FULL, p, 0);
+            const bool fresh = (w0 == INT_MIN);
+            if (fresh) w0 = max(p0, 0) & ~7;
+            // every piece is staged on its own, as 16-byte vectors from the aligned-down start of its words / ops
+            const int sv = (int)(((so & 3u) + m1.x + 3u) >> 2), cv = (int)(((co & 3u) + m0.w + 3u) >> 2);
+            int s_inc = valid ? sv : 0, c_inc = valid ? cv : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ts = __shfl_up_sync(FULL, s_inc, o), tc = __shfl_up_sync(FULL, c_inc, o);
+                if (lane >= o) { s_inc += ts; c_inc += tc; }
+            }
+            const bool inwin = p >= w0 && p - w0 < slack;
+            const bool fits = valid && inwin && 4 * s_inc <= G::SEQ_CAP && 4 * c_inc <= G::CIG_CAP;
+            const unsigned fm = __ballot_sync(FULL, fits);
+            n = (fm == FULL) ? 32 : __ffs(~fm) - 1;
+            n = min(n, RUN_CAP - run_reads);
+            if (n == 0) {
+                const bool inwin0 = __shfl_sync(FULL, (int)inwin, 0) != 0;
+                if ((!inwin0 && !fresh) || run_reads >= RUN_CAP) {
+                    flush();
+                    w0 = INT_MIN; run_reads = 0;
+                    continue;
+                }
+                if (lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);     // one piece larger than the staging buffers
+                r += 1;
                 continue;
             }
-            // a negative position (TC_ERR_RANGE), or one read larger than the staging buffers
-            if (inwin0 && lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
-            if (fold && lane == 0) {
-                if (p0 < prev_pos) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
-                if (p0 < 0 && passes) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
-            }
-            prev_pos = p0;
-            r += 1;
-            continue;
-        }
-
-        // ---- stage SEQ words [sbase_al, send) and CIGAR ops [cbase_al, cend)
-        bool cig_exotic;
-        {
-            const uint32_t send = __shfl_sync(FULL, so_next, n - 1) + 1;        // one word of look-ahead for the funnel shift
-            const int nv = (int)((send - sbase_al + 3) >> 2);
-            const uint32_t cend = __shfl_sync(FULL, co_next, n - 1);
-            const int ncv = (int)((cend - cbase_al + 3) >> 2);
-            // the next sub-tile starts where this one ends and is about as large: pull its lines (and the
-            // metadata lines two sub-tiles ahead) towards L2 while this one is being processed
-            {
-                const int64_t s_lo = (int64_t)send - 1, s_len = (int64_t)send - sbase_al;
-                for (int64_t o = 32 * lane; o < s_len && s_lo + o < n_seq_words; o += 1024) prefetch_l2(a.r.seq4 + s_lo + o);
-                const int64_t c_len = (int64_t)cend - cbase_al;
-                for (int64_t o = 32 * lane; o < c_len && (int64_t)cend + o < n_ops_total; o += 1024) prefetch_l2(a.r.cigar + cend + o);
-                const int64_t rm = r + n + 64;
-                if (rm < n_reads) {
-                    if (lane == 0) prefetch_l2(a.r.pos + rm);
-                    if (lane == 1) prefetch_l2(a.r.seq_off + rm);
-                    if (lane == 2) prefetch_l2(a.r.cigar_off + rm);
-                    if (lane == 3) prefetch_l2(a.r.l_seq + rm);
-                    if (lane == 4) prefetch_l2(a.r.flag + rm);
-                }
-            }
-            uint32_t dirty = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
-            const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
-            if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
-                const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
-                int t = 0;
-                for (int i = lane; i < nv; i += 128, t += 4) {
-                    uint4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) {
-                        const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
-                        dirty |= (z != 0 ? 1u : 0u) << (t + u);
-                        v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
-                        v[u].z = __byte_perm(v[u].z, 0, 0x0123); v[u].w = __byte_perm(v[u].w, 0, 0x0123);
-                        sts4(sdst + 16 * (i + 32 * u), v[u]);
+            const uint32_t sdst = seq_s + 4u * G::SEQ_PAD + 16u * (uint32_t)(s_inc - sv);
+            const uint32_t cdst = cig_s + 16u * (uint32_t)(c_inc - cv);
+            if (lane < n) {
+                const int64_t sb = (int64_t)(so & ~3u);
+                for (int v = 0; v < sv; ++v) {
+                    uint4 q;
+                    if (sb + 4 * v + 4 <= n_seq_words) q = __ldg(reinterpret_cast<const uint4*>(a.r.seq4 + sb) + v);
+                    else {              // the last words of the batch: do not read past the array
+                        q.x = sb + 4 * v + 0 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 0) : 0u;
+                        q.y = sb + 4 * v + 1 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 1) : 0u;
+                        q.z = sb + 4 * v + 2 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 2) : 0u;
+                        q.w = sb + 4 * v + 3 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 3) : 0u;
                     }
-                }
-            } else {            // the last sub-tile of the batch: do not read past the array
-                int t = 0;
-                for (int i = lane; i < nv; i += 32, ++t) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int64_t wi = (int64_t)sbase_al + 4 * i + u;
-                        w[u] = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
+                    if (multibit(q.x) | multibit(q.y) | multibit(q.z) | multibit(q.w)) {
+                        q.x = clear_multibit(q.x); q.y = clear_multibit(q.y); q.z = clear_multibit(q.z); q.w = clear_multibit(q.w);
                     }
-                    const uint32_t z = multibit(w[0]) | multibit(w[1]) | multibit(w[2]) | multibit(w[3]);
-                    dirty |= (z != 0 ? 1u : 0u) << t;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
+                    q.x = __byte_perm(q.x, 0, 0x0123); q.y = __byte_perm(q.y, 0, 0x0123);
+                    q.z = __byte_perm(q.z, 0, 0x0123); q.w = __byte_perm(q.w, 0, 0x0123);
+                    sts4(sdst + 16 * v, q);
                 }
-            }
-            // pads and zero-length ops: min over the words of min((op ^ P), len) is 0 exactly when one is present
-            uint32_t exmin = 1u;
-            if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
-                const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
-                for (int i = lane; i < ncv; i += 64) {
-                    uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
-                    const bool b1 = i + 32 < ncv;
-                    if (b1) v1 = __ldg(csrc + i + 32);
-                    exmin = min(exmin, min(min(min((v0.x & 15u) ^ 6u, v0.x >> 4), min((v0.y & 15u) ^ 6u, v0.y >> 4)),
-                                           min(min((v0.z & 15u) ^ 6u, v0.z >> 4), min((v0.w & 15u) ^ 6u, v0.w >> 4))));
-                    exmin = min(exmin, min(min(min((v1.x & 15u) ^ 6u, v1.x >> 4), min((v1.y & 15u) ^ 6u, v1.y >> 4)),
-                                           min(min((v1.z & 15u) ^ 6u, v1.z >> 4), min((v1.w & 15u) ^ 6u, v1.w >> 4))));
-                    sts4(cig_s + 16 * i, v0);
-                    if (b1) sts4(cig_s + 16 * (i + 32), v1);
-                }
-            } else {
-                for (int i = lane; i < 4 * ncv; i += 32) {
-                    const int64_t oi = (int64_t)cbase_al + i;
-                    const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
-                    exmin = min(exmin, min((c & 15u) ^ 6u, c >> 4));
-                    sts(cig_s + 4 * i, c);
-                }
-            }
-            // ... and reads without SEQ ('*': every base reads 'N'): the general form below handles all of these
-            cig_exotic = __any_sync(FULL, exmin == 0u || (lane < n && lq == 0));
-            // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
-            // Only the vectors that hold one are revisited, one per lane and iteration.
-            while (__any_sync(FULL, dirty != 0)) {
-                if (dirty) {
-                    const int t = __ffs(dirty) - 1;
-                    dirty &= dirty - 1;
-                    const uint32_t q = sdst + 16 * (lane + 32 * t);
-                    uint4 v = lds4(q);
-                    v.x = clear_multibit(v.x); v.y = clear_multibit(v.y); v.z = clear_multibit(v.z); v.w = clear_multibit(v.w);
-                    sts4(q, v);
-                }
+                // the piece-CIGAR buffer is padded to whole vectors behind its last op
+                const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + (co & ~3u));
+                for (int v = 0; v < cv; ++v) sts4(cdst + 16 * v, __ldg(csrc + v));
             }
             __syncwarp();
-        }
+            cs = cdst + 4u * (co & 3u);
+            sq_lane = sdst + 4u * (so & 3u);
+        } else {
+            // ---- metadata of the next (up to) 32 reads, one per lane
+            p = a.r.pos[ri];
+            const uint32_t so = a.r.seq_off[ri], so_next = a.r.seq_off[ri + 1];
+            const uint32_t co = a.r.cigar_off[ri], co_next = a.r.cigar_off[ri + 1];
+            const uint32_t flg = a.r.flag[ri];
+            lq = a.r.l_seq[ri];
+            passes = !(flg & (a.flag_filter | 4u)) && !(a.ignore_orphans && (flg & 1u) && !(flg & 2u));
+            if (a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[ri] < a.min_mapq) passes = false;
+            const int p0 = __shfl_sync(FULL, p, 0);
+            const bool fresh = (w0 == INT_MIN);
+            if (fresh) w0 = max(p0, 0) & ~7;
+            const uint32_t sbase_al = __shfl_sync(FULL, so, 0) & ~3u;
+            const uint32_t cbase_al = __shfl_sync(FULL, co, 0) & ~3u;
+            const bool inwin = p >= w0 && p - w0 < slack;
+            const bool fits = valid && inwin && (so_next - sbase_al + 1 <= (uint32_t)G::SEQ_CAP) && (co_next - cbase_al <= (uint32_t)G::CIG_CAP);
+            const unsigned fm = __ballot_sync(FULL, fits);
+            n = (fm == FULL) ? 32 : __ffs(~fm) - 1;
+            n = min(n, RUN_CAP - run_reads);
+            if (n == 0) {
+                const bool inwin0 = __shfl_sync(FULL, (int)inwin, 0) != 0;
+                if ((!inwin0 && !fresh) || run_reads >= RUN_CAP) {      // the window (or the counters' range) is used up
+                    flush();
+                    w0 = INT_MIN; run_reads = 0;
+                    continue;
+                }
+                // a negative position (TC_ERR_RANGE), or one read larger than the staging buffers
+                if (inwin0 && lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
+                if (fold && lane == 0) {
+                    if (p0 < prev_pos) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
+                    if (p0 < 0 && passes) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+                }
+                prev_pos = p0;
+                r += 1;
+                continue;
+            }
 
+            // ---- stage SEQ words [sbase_al, send) and CIGAR ops [cbase_al, cend)
+            {
+                const uint32_t send = __shfl_sync(FULL, so_next, n - 1) + 1;        // one word of look-ahead for the funnel shift
+                const int nv = (int)((send - sbase_al + 3) >> 2);
+                const uint32_t cend = __shfl_sync(FULL, co_next, n - 1);
+                const int ncv = (int)((cend - cbase_al + 3) >> 2);
+                // the next sub-tile starts where this one ends and is about as large: pull its lines (and the
+                // metadata lines two sub-tiles ahead) towards L2 while this one is being processed
+                {
+                    const int64_t s_lo = (int64_t)send - 1, s_len = (int64_t)send - sbase_al;
+                    for (int64_t o = 32 * lane; o < s_len && s_lo + o < n_seq_words; o += 1024) prefetch_l2(a.r.seq4 + s_lo + o);
+                    const int64_t c_len = (int64_t)cend - cbase_al;
+                    for (int64_t o = 32 * lane; o < c_len && (int64_t)cend + o < n_ops_total; o += 1024) prefetch_l2(a.r.cigar + cend + o);
+                    const int64_t rm = r + n + 64;
+                    if (rm < n_reads) {
+                        if (lane == 0) prefetch_l2(a.r.pos + rm);
+                        if (lane == 1) prefetch_l2(a.r.seq_off + rm);
+                        if (lane == 2) prefetch_l2(a.r.cigar_off + rm);
+                        if (lane == 3) prefetch_l2(a.r.l_seq + rm);
+                        if (lane == 4) prefetch_l2(a.r.flag + rm);
+                    }
+                }
+                uint32_t dirty = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
+                const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
+                if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
+                    int t = 0;
+                    for (int i = lane; i < nv; i += 128, t += 4) {
+                        uint4 v[4];
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) {
+                            const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
+                            dirty |= (z != 0 ? 1u : 0u) << (t + u);
+                            v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
+                            v[u].z = __byte_perm(v[u].z, 0, 0x0123); v[u].w = __byte_perm(v[u].w, 0, 0x0123);
+                            sts4(sdst + 16 * (i + 32 * u), v[u]);
+                        }
+                    }
+                } else {            // the last sub-tile of the batch: do not read past the array
+                    int t = 0;
+                    for (int i = lane; i < nv; i += 32, ++t) {
+                        uint32_t w[4];
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int64_t wi = (int64_t)sbase_al + 4 * i + u;
+                            w[u] = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
+                        }
+                        const uint32_t z = multibit(w[0]) | multibit(w[1]) | multibit(w[2]) | multibit(w[3]);
+                        dirty |= (z != 0 ? 1u : 0u) << t;
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
+                    }
+                }
+                // pads and zero-length ops: min over the words of min((op ^ P), len) is 0 exactly when one is present
+                uint32_t exmin = 1u;
+                if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
+                    const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
+                    for (int i = lane; i < ncv; i += 64) {
+                        uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
+                        const bool b1 = i + 32 < ncv;
+                        if (b1) v1 = __ldg(csrc + i + 32);
+                        exmin = min(exmin, min(min(min((v0.x & 15u) ^ 6u, v0.x >> 4), min((v0.y & 15u) ^ 6u, v0.y >> 4)),
+                                               min(min((v0.z & 15u) ^ 6u, v0.z >> 4), min((v0.w & 15u) ^ 6u, v0.w >> 4))));
+                        exmin = min(exmin, min(min(min((v1.x & 15u) ^ 6u, v1.x >> 4), min((v1.y & 15u) ^ 6u, v1.y >> 4)),
+                                               min(min((v1.z & 15u) ^ 6u, v1.z >> 4), min((v1.w & 15u) ^ 6u, v1.w >> 4))));
+                        sts4(cig_s + 16 * i, v0);
+                        if (b1) sts4(cig_s + 16 * (i + 32), v1);
+                    }
+                } else {
+                    for (int i = lane; i < 4 * ncv; i += 32) {
+                        const int64_t oi = (int64_t)cbase_al + i;
+                        const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
+                        exmin = min(exmin, min((c & 15u) ^ 6u, c >> 4));
+                        sts(cig_s + 4 * i, c);
+                    }
+                }
+                // ... and reads without SEQ ('*': every base reads 'N'): the general form below handles all of these
+                cig_exotic = __any_sync(FULL, exmin == 0u || (lane < n && lq == 0));
+                // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
+                // Only the vectors that hold one are revisited, one per lane and iteration.
+                while (__any_sync(FULL, dirty != 0)) {
+                    if (dirty) {
+                        const int t = __ffs(dirty) - 1;
+                        dirty &= dirty - 1;
+                        const uint32_t q = sdst + 16 * (lane + 32 * t);
+                        uint4 v = lds4(q);
+                        v.x = clear_multibit(v.x); v.y = clear_multibit(v.y); v.z = clear_multibit(v.z); v.w = clear_multibit(v.w);
+                        sts4(q, v);
+                    }
+                }
+                __syncwarp();
+            }
+            cs = cig_s + 4u * (co - cbase_al);
+            nops_lane = (int)(co_next - co);
+            sq_lane = seq_s + 4u * G::SEQ_PAD + 4u * (so - sbase_al);
+        }
         // ---- walk
         const bool act = lane < n && passes;
-        const uint32_t cs = cig_s + 4u * (co - cbase_al);
-        const int nops = act ? (int)(co_next - co) : 0;
+        const int nops = act ? nops_lane : 0;
         const int x0 = p - w0;
-        const uint32_t sq = seq_s + 4u * G::SEQ_PAD + (act ? 4u * (so - sbase_al) : 0u);
+        const uint32_t sq = act ? sq_lane : seq_s + 4u * G::SEQ_PAD;
         int x_end;
         if (!cig_exotic) {
-            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, lq, row, xi, sq, &a.status->err);
+            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, y0, lq, row, xi, sq, &a.status->err);
         } else {
             // pads or zero-length ops somewhere in the sub-tile (rare): the general three-pass form
             const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
@@ -588,12 +655,12 @@ bool tc_pileup_warp_supported(const pileup_args& a) {
     return (((uintptr_t)a.r.seq4 | (uintptr_t)a.r.cigar) & 15u) == 0;
 }
 
-template <int WC>
+template <int WC, bool PIECES>
 static int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
     using G = geom<WC>;
     const size_t smem = sizeof(uint32_t) * (size_t)G::WARP_WORDS * G::WARPS;
-    TC_CUDA(cudaFuncSetAttribute(warp_pileup_kernel<WC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    warp_pileup_kernel<WC><<<ctx->sm_count, G::WARPS * 32, smem, s>>>(a);
+    TC_CUDA(cudaFuncSetAttribute(warp_pileup_kernel<WC, PIECES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    warp_pileup_kernel<WC, PIECES><<<ctx->sm_count, G::WARPS * 32, smem, s>>>(a);
     TC_LAUNCH_CHECK();
     return TC_OK;
 }
@@ -601,7 +668,10 @@ static int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
 // Both geometries are enqueued; each reads the longest reference span the span pass left in
 // a.status and returns at once unless it is the one that fits (no host round trip in between).
 int tc_pileup_warp_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
-    int rc = launch_geom<64>(ctx, a, s);
+    int rc = launch_geom<64, false>(ctx, a, s);
     if (rc) return rc;
-    return launch_geom<128>(ctx, a, s);
+    return launch_geom<128, false>(ctx, a, s);
 }
+
+// pieces of long reads (pileup_long.cu): always the 512-column geometry
+int tc_pileup_warp_launch_pieces(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) { return launch_geom<64, true>(ctx, a, s); }
