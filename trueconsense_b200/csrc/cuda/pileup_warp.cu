@@ -215,16 +215,18 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
     int y = y0, rem = 0;       // y0: query index of the first base relative to sq's first nibble (pieces of long reads: 0..7)
     uint32_t cp = cs;                       // next op
     const uint32_t cend = cs + 4u * (uint32_t)nops;
+    uint32_t cnext = lds(cs);               // ops are fetched one ahead of their use (the address stays inside the slice)
     // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
     uint32_t prev = 0;
     while (__any_sync(FULL, cp < cend || rem > 0)) {
         if (rem == 0) {
             while (cp < cend) {
-                const uint32_t c = lds(cp);
+                const uint32_t c = cnext;
+                cp += 4;
+                cnext = lds(cp);
                 const uint32_t op = c & 15u;
                 const uint32_t fl = op_flags(op);
                 const int l = (int)(c >> 4);
-                cp += 4;
                 if (fl & 1u) {
                     // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
                     if (x + l > ROWW || y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
