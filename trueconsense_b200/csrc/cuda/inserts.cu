@@ -49,6 +49,7 @@ struct ins_args {
     uint8_t* ent_sel;               // bit 0: selected (fetched and passed by the stepper), bit 1: yields an entry
     int32_t* seg_count;             // [n_cand] admitted entries
     int32_t* overflow;              // [1] some column had more distinct keys than INS_TBL holds
+    const int32_t* layout;          // device-built layout (ins_layout_kernel): [0] tiles, [1] slots, [2] 1 = did not fit; NULL: host-built
     uint8_t* bases_fixed;           // [n_cand][INS_BASES_FIXED] inserted characters of each winner (longer ones: ins_bases_kernel)
     tc_status* status;
 };
@@ -139,10 +140,39 @@ __device__ __forceinline__ read_syms read_syms_of(const ins_args& a, uint32_t re
     return rs;
 }
 
+// The slot / tile layout built on the device, so that the ranges need not travel to the host first: slot offsets
+// and first tiles per candidate (serial, a handful of candidates), then the candidate of every tile.  When the
+// layout does not fit the buffers the host sized speculatively, layout[2] says so and no tile runs.
+__global__ void __launch_bounds__(256) ins_layout_kernel(ins_args a, int64_t* __restrict__ seg_off, int32_t* __restrict__ tile_first,
+                                                         int32_t* __restrict__ tile_cand, int32_t* __restrict__ layout, int64_t slot_cap, int tile_cap) {
+    __shared__ int n_tiles_s;
+    if (threadIdx.x == 0) {
+        int64_t off = 0; int64_t tiles = 0;
+        for (int i = 0; i < a.n_cand; ++i) {
+            seg_off[i] = off; tile_first[i] = (int32_t)min(tiles, (int64_t)0x7fffffff);
+            const int64_t len = a.range[2 * i + 1] - a.range[2 * i];
+            off += len; tiles += (len + INS_TILE - 1) / INS_TILE;
+        }
+        seg_off[a.n_cand] = off; tile_first[a.n_cand] = (int32_t)min(tiles, (int64_t)0x7fffffff);
+        const bool fits = off <= slot_cap && tiles <= tile_cap;
+        layout[0] = fits ? (int32_t)tiles : 0;
+        layout[1] = (int32_t)min(off, (int64_t)0x7fffffff);
+        layout[2] = fits ? 0 : 1;
+        n_tiles_s = fits ? (int)tiles : 0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles_s; t += blockDim.x) {
+        int lo = 0, hi = a.n_cand - 1;          // last candidate whose first tile is <= t
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_first[mid] <= t) lo = mid; else hi = mid - 1; }
+        tile_cand[t] = lo;
+    }
+}
+
 // select: one thread per read of the candidate's range
 __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
     __shared__ int wlast[INS_TILE / 32];
     const int tile = blockIdx.x;
+    if (a.layout && tile >= a.layout[0]) return;
     const int ci = a.tile_cand[tile];
     const int c = a.cand[ci] - 1;
     const int lo = a.range[2 * ci], hi = a.range[2 * ci + 1];
@@ -237,6 +267,7 @@ __global__ void __launch_bounds__(INS_TILE) ins_admit_kernel(ins_args a) {
     __shared__ long long base_s;
     __shared__ int prev_s;
     const int tile = blockIdx.x;
+    if (a.layout && tile >= a.layout[0]) return;
     const int ci = a.tile_cand[tile];
     const int lo = a.range[2 * ci], hi = a.range[2 * ci + 1];
     const int t0 = a.tile_first[ci];
@@ -322,6 +353,7 @@ __global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_c
     __shared__ unsigned long long best_s;
     __shared__ int over_s;
     const int ci = blockIdx.x;
+    if (a.layout && a.layout[2]) return;        // the speculative layout did not fit: the host sizes it and runs again
     const int64_t off = a.seg_off[ci];
     const int lo = a.range[2 * ci];
     const int n = a.range[2 * ci + 1] - lo;
@@ -455,7 +487,12 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
     cand_range_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(a);
     TC_LAUNCH_CHECK();
-    // host side of the layout: slot offsets and the tile table (a few integers per candidate)
+    // Layout of the entry slots.  With everything resident on the device and the hash count, the layout is built
+    // on the device into buffers sized from the last calls (no read-back of the ranges, one synchronisation per
+    // call); otherwise — host arrays to stage range by range, the sorted form, or a layout that did not fit — on
+    // the host from the ranges.
+    const bool spec = !(host_seq || host_qual || host_cig) && p->kernel != 2 && !(p->reserved & 1);
+    if (ctx->ins_slot_cap <= 0) ctx->ins_slot_cap = 1 << 16;     // grows to twice the largest layout seen
     int32_t* h_range = (int32_t*)malloc(24 * (size_t)n_cand);
     int64_t* h_off = (int64_t*)malloc(8 * ((size_t)n_cand + 1));
     int32_t* h_tfirst = (int32_t*)malloc(4 * ((size_t)n_cand + 1));
@@ -465,6 +502,9 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     if (!h_range || !h_off || !h_tfirst || !h_fixed) { free(h_range); free(h_off); free(h_tfirst); free(h_fixed); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
 #define INS_FREE() do { free(h_range); free(h_off); free(h_tfirst); free(h_tcand); free(h_entry); free(h_fixed); } while (0)
 #define INS_CUDA(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { INS_FREE(); return tc_cuda_fail(ctx, e__, what); } } while (0)
+    int64_t total = 0;
+    int n_tiles = 0;
+    if (!spec) {
     INS_CUDA(cudaMemcpyAsync(h_range, d_range, 24 * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "range readback");
     INS_CUDA(cudaStreamSynchronize(s), "range readback");
     ctx->d2h_bytes += 24 * (int64_t)n_cand;
@@ -494,15 +534,19 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
         h_off[i + 1] = h_off[i] + len;
         h_tfirst[i + 1] = h_tfirst[i] + (int32_t)((len + INS_TILE - 1) / INS_TILE);
     }
-    const int64_t total = h_off[n_cand];
-    const int n_tiles = h_tfirst[n_cand];
+    total = h_off[n_cand];
+    n_tiles = h_tfirst[n_cand];
     if (total >= 0x7fffffffll) { INS_FREE(); return tc_fail(ctx, TC_ERR_CAPACITY, "too many candidate column entries (%lld)", (long long)total); }
     h_tcand = (int32_t*)malloc(4 * (size_t)(n_tiles > 0 ? n_tiles : 1));
     if (!h_tcand) { INS_FREE(); return tc_fail(ctx, TC_ERR_NOMEM, "out of host memory"); }
     for (int i = 0; i < n_cand; ++i) for (int t = h_tfirst[i]; t < h_tfirst[i + 1]; ++t) h_tcand[t] = i;
+    } else {
+        total = ctx->ins_slot_cap;
+        n_tiles = (int)(total / INS_TILE) + n_cand + 1;
+    }
     const size_t T = (size_t)(total > 0 ? total : 1), NT = (size_t)(n_tiles > 0 ? n_tiles : 1);
     // one slab: keys, indel, qpos, head, sel per slot; tile tables; per-candidate offsets, counts
-    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + (size_t)n_cand * INS_BASES_FIXED + 256;
+    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + (size_t)n_cand * INS_BASES_FIXED + 256 + 16;
     uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
     tc_insert_call_t* d_calls = (tc_insert_call_t*)tc_dev_buf(ctx, SLOT_INS_E, sizeof(tc_insert_call_t) * (size_t)n_cand);
     if (!slab || !d_calls) { INS_FREE(); return TC_ERR_NOMEM; }
@@ -512,13 +556,21 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + n_cand + 1; a.tile_last = a.tile_sel + NT;
     a.seg_count = a.tile_last + NT; a.overflow = a.seg_count + n_cand;
-    a.ent_head = (uint8_t*)(a.overflow + 1); a.ent_sel = a.ent_head + T; a.bases_fixed = a.ent_sel + T;
+    int32_t* d_layout = a.overflow + 1;         // [3], speculative layout only
+    a.ent_head = (uint8_t*)(d_layout + 3); a.ent_sel = a.ent_head + T; a.bases_fixed = a.ent_sel + T;
     a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst;
-    INS_CUDA(cudaMemcpyAsync(d_off, h_off, 8 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "offset upload");
-    INS_CUDA(cudaMemcpyAsync(d_tfirst, h_tfirst, 4 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "tile table upload");
-    if (n_tiles) INS_CUDA(cudaMemcpyAsync(d_tcand, h_tcand, 4 * (size_t)n_tiles, cudaMemcpyHostToDevice, s), "tile table upload");
     INS_CUDA(cudaMemsetAsync(a.seg_count, 0, 4 * ((size_t)n_cand + 1), s), "memset");
-    ctx->h2d_bytes += 12 * ((int64_t)n_cand + 1) + 4 * (int64_t)n_tiles;
+    if (spec) {
+        a.layout = d_layout;
+        ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT);
+        ctx->launches++;
+    } else {
+        a.layout = nullptr;
+        INS_CUDA(cudaMemcpyAsync(d_off, h_off, 8 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "offset upload");
+        INS_CUDA(cudaMemcpyAsync(d_tfirst, h_tfirst, 4 * ((size_t)n_cand + 1), cudaMemcpyHostToDevice, s), "tile table upload");
+        if (n_tiles) INS_CUDA(cudaMemcpyAsync(d_tcand, h_tcand, 4 * (size_t)n_tiles, cudaMemcpyHostToDevice, s), "tile table upload");
+        ctx->h2d_bytes += 12 * ((int64_t)n_cand + 1) + 4 * (int64_t)n_tiles;
+    }
     if (n_tiles) {
         ins_select_kernel<<<n_tiles, INS_TILE, 0, s>>>(a);
         ctx->launches++;
@@ -528,17 +580,31 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     bool sorted_form = p->kernel == 2;
     const size_t tbl_smem = (size_t)INS_TBL * 16;
     int32_t h_over = 0;
+    int32_t h_layout[3] = {0, 0, 0};
     if (!sorted_form) {
         INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
         ins_count_kernel<<<n_cand, 1024, tbl_smem, s>>>(a, d_calls);
         ctx->launches++;
         INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
+        if (spec) INS_CUDA(cudaMemcpyAsync(h_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
     }
     INS_CUDA(cudaMemcpyAsync(calls, d_calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "insert calls readback");
     INS_CUDA(cudaMemcpyAsync(h_fixed, a.bases_fixed, (size_t)n_cand * INS_BASES_FIXED, cudaMemcpyDeviceToHost, s), "inserted bases readback");
     INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
     INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
     ctx->d2h_bytes += (int64_t)(sizeof(tc_insert_call_t) + INS_BASES_FIXED) * n_cand + (int64_t)sizeof(tc_status) + 4;
+    if (spec) {
+        if (h_layout[2] || h_over) {
+            // the layout did not fit the speculative buffers (size them for next time), or a column needs the sorted
+            // form: run again with the layout built on the host
+            if (h_layout[2]) ctx->ins_slot_cap = 2 * (int64_t)h_layout[1] + 4096;
+            INS_FREE();
+            tc_pileup_params_t q = *p;
+            q.reserved |= 1;
+            return tc_extract_inserts(ctx, reads, ref_len, cand_pos, n_cand, &q, calls, bases, bases_cap, stream);
+        }
+        total = h_layout[1];
+    }
     if (sorted_form || h_over) {
         // radix sort + run-length encoding over the same slots
         uint8_t* slab2 = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_C, T * (8 + 4 + 4) + 64);

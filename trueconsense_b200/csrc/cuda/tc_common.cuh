@@ -33,6 +33,7 @@ struct tc_ctx {
     int timing;             // bracket the pileup kernel with events
     cudaEvent_t ev0, ev1;
     int ev_valid;
+    int64_t ins_slot_cap;   // tc_extract_inserts: entry slots its speculative (no read-back) layout may use; grows on demand
 };
 
 // device-side status block written by kernels, read back once per call
