@@ -284,10 +284,12 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     // (PIECES: the "reads" are pieces of at most PIECE_COLS columns; the span pass ran over the real reads)
     const bool fold = !PIECES && a.span_hint > 0;   // no span pass ran: this kernel also does its checks and the coverage ends
     const int ms = PIECES ? PIECE_COLS : ((max(fold ? a.span_hint : a.status->max_span, 1) + 7) & ~7);
-    const int slack64 = (512 - ms - 8) & ~7, slack128 = (1024 - ms - 8) & ~7;
-    const bool mine = (WC == 64) ? (slack64 >= MIN_SLACK) : (slack64 < MIN_SLACK);
+    // 256-column windows (short reads: half the shared memory per warp, more warps per SM), 512 or 1024
+    const int slack32 = (256 - ms - 8) & ~7, slack64 = (512 - ms - 8) & ~7, slack128 = (1024 - ms - 8) & ~7;
+    const bool mine = (WC == 32) ? (slack32 >= MIN_SLACK)
+                    : (WC == 64) ? (slack32 < MIN_SLACK && slack64 >= MIN_SLACK) : (slack64 < MIN_SLACK);
     if (!mine) return;
-    const int slack = (WC == 64) ? slack64 : slack128;
+    const int slack = (WC == 32) ? slack32 : (WC == 64) ? slack64 : slack128;
     if (slack < MIN_SLACK) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
         return;
@@ -667,10 +669,12 @@ static int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
     return TC_OK;
 }
 
-// Both geometries are enqueued; each reads the longest reference span the span pass left in
+// All geometries are enqueued; each reads the longest reference span the span pass left in
 // a.status and returns at once unless it is the one that fits (no host round trip in between).
 int tc_pileup_warp_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
-    int rc = launch_geom<64, false>(ctx, a, s);
+    int rc = launch_geom<32, false>(ctx, a, s);
+    if (rc) return rc;
+    rc = launch_geom<64, false>(ctx, a, s);
     if (rc) return rc;
     return launch_geom<128, false>(ctx, a, s);
 }
