@@ -107,46 +107,83 @@ __global__ void __launch_bounds__(SC_THREADS) pileup_scatter_kernel(pileup_args 
     }
 }
 
-// Single-CTA inclusive scan of the difference array into the coverage row, plus its maximum.
-// L is at most a few hundred thousand: one SM streams it in microseconds, and a single CTA needs
-// no inter-block carry protocol.
-__global__ void __launch_bounds__(1024) coverage_scan_kernel(const int32_t* __restrict__ diff, int32_t* __restrict__ cov,
-                                                             int L, tc_status* status) {
+// Inclusive scan of the difference array into the coverage row, plus its maximum, as two small multi-CTA kernels
+// (a single CTA streaming L elements was the largest fixed cost of a small sample):
+//   cov_block_kernel   every CTA scans its 4096 columns locally and leaves its total
+//   cov_apply_kernel   every CTA adds the totals of the CTAs before it (a handful: L / 4096), tracks the maximum and —
+//                      when `xi` is given (variant 3 / 4: packed X | I event counters per column) — unpacks those
+//                      into rows X and I of the count table that `cov` is row 0 of.
+constexpr int COV_BLOCK = 4096;
+
+__global__ void __launch_bounds__(1024) cov_block_kernel(const int32_t* __restrict__ diff, int32_t* __restrict__ cov, int L,
+                                                         int32_t* __restrict__ block_total) {
     __shared__ int warp_sums[32];
-    __shared__ int carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const int i0 = blockIdx.x * COV_BLOCK + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = (i0 + t < L) ? diff[i0 + t] : 0;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    int s = v[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) warp_sums[warp] = s;
     __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int prefix = (warp > 0 ? warp_sums[warp - 1] : 0) + (s - v[3]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) if (i0 + t < L) cov[i0 + t] = prefix + v[t];
+    if (threadIdx.x == 1023) block_total[blockIdx.x] = prefix + v[3];
+}
+
+__global__ void __launch_bounds__(1024) cov_apply_kernel(int32_t* __restrict__ cov, int L, const int32_t* __restrict__ block_total,
+                                                         tc_status* status, const unsigned long long* __restrict__ xi) {
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        int c = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) c += block_total[b];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) carry_s = c;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int i0 = blockIdx.x * COV_BLOCK + threadIdx.x * 4;
     int vmax = 0;
-    for (int base = 0; base < L; base += 1024 * 4) {
-        int i0 = base + threadIdx.x * 4;
-        int v[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[t] = (i0 + t < L) ? diff[i0 + t] : 0;
-        v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
-        int s = v[3];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-        if (lane == 31) warp_sums[warp] = s;
-        __syncthreads();
-        if (warp == 0) {
-            int w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-            warp_sums[lane] = w;
+    for (int t = 0; t < 4; ++t) {
+        if (i0 + t < L) {
+            const int c = cov[i0 + t] + carry;
+            cov[i0 + t] = c;
+            vmax = max(vmax, c);
+            if (xi) {
+                const unsigned long long e = xi[i0 + t];
+                cov[(size_t)TC_ROW_X * L + i0 + t] = (int32_t)(uint32_t)e;
+                cov[(size_t)TC_ROW_I * L + i0 + t] = (int32_t)(uint32_t)(e >> 32);
+            }
         }
-        __syncthreads();
-        int prefix = carry_s + (warp > 0 ? warp_sums[warp - 1] : 0) + (s - v[3]);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (i0 + t < L) { int c = prefix + v[t]; cov[i0 + t] = c; vmax = max(vmax, c); }
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = prefix + v[3];
-        __syncthreads();
     }
     for (int o = 16; o; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) atomicMax(&status->max_cov, vmax);
+    if (lane == 0 && vmax > 0) atomicMax(&status->max_cov, vmax);
+}
+
+static int coverage_scan(tc_ctx* ctx, const int32_t* d_diff, int32_t* d_cov, int L, tc_status* d_status, const unsigned long long* xi,
+                         cudaStream_t s) {
+    const int nb = (L + COV_BLOCK - 1) / COV_BLOCK;
+    int32_t* totals = (int32_t*)tc_dev_buf(ctx, SLOT_COV_TOTALS, 4 * (size_t)nb + 16);
+    if (!totals) return TC_ERR_NOMEM;
+    cov_block_kernel<<<nb, 1024, 0, s>>>(d_diff, d_cov, L, totals);
+    TC_LAUNCH_CHECK();
+    cov_apply_kernel<<<nb, 1024, 0, s>>>(d_cov, L, totals, d_status, xi);
+    TC_LAUNCH_CHECK();
+    return TC_OK;
 }
 
 // kernel (3) on its own: one thread per read adds its span ends to the difference array
@@ -208,11 +245,14 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     if (rc) return rc;
     const bool out_dev = tc_is_device_ptr(counts);
     int32_t* d_counts = out_dev ? counts : (int32_t*)tc_dev_buf(ctx, SLOT_COUNTS, sizeof(int32_t) * TC_NROWS * (size_t)L);
-    int32_t* d_diff = (int32_t*)tc_dev_buf(ctx, SLOT_DIFF, sizeof(int32_t) * ((size_t)L + 1));
+    // the coverage difference array and, behind it, variant 3's packed X | I event counters: one buffer, one memset
+    const size_t diff_words = ((size_t)L + 2) & ~(size_t)1;
+    int32_t* d_diff = (int32_t*)tc_dev_buf(ctx, SLOT_DIFF, sizeof(int32_t) * diff_words + 8 * ((size_t)L + 1));
     tc_status* d_status = (tc_status*)tc_dev_buf(ctx, SLOT_STATUS, sizeof(tc_status));
     if (!d_counts || !d_diff || !d_status) return TC_ERR_NOMEM;
     TC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * TC_NROWS * (size_t)L, s));
-    TC_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(int32_t) * ((size_t)L + 1), s));
+    TC_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(int32_t) * diff_words + 8 * ((size_t)L + 1), s));
+    a.xi = (unsigned long long*)(d_diff + diff_words);
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality;
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
@@ -254,8 +294,8 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         if (ctx->timing) { TC_CUDA(cudaEventRecord(ctx->ev1, s)); ctx->ev_valid = 1; }
     }
     if (!per_entry) {
-        coverage_scan_kernel<<<1, 1024, 0, s>>>(d_diff, d_counts, L, d_status);
-        TC_LAUNCH_CHECK();
+        rc = coverage_scan(ctx, d_diff, d_counts, L, d_status, (variant == 3 || variant == 4) ? a.xi : nullptr, s);
+        if (rc) return rc;
     }
     tc_status st;
     if (!out_dev) TC_D2H(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, s);
@@ -323,8 +363,8 @@ TC_API int tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, con
         depth_diff_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, s>>>(a);
         TC_LAUNCH_CHECK();
     }
-    coverage_scan_kernel<<<1, 1024, 0, s>>>(d_diff, d_depth, L, d_status);
-    TC_LAUNCH_CHECK();
+    rc = coverage_scan(ctx, d_diff, d_depth, L, d_status, nullptr, s);
+    if (rc) return rc;
     if (!out_dev) TC_D2H(depth, d_depth, sizeof(int32_t) * (size_t)L, s);
     tc_status st;
     rc = fetch_status(ctx, d_status, &st, s);

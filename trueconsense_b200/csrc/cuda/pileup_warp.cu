@@ -60,7 +60,7 @@ template <int WC> struct geom {
     static constexpr int CIG_CAP = WC * 14;         // staged CIGAR ops per sub-tile
     static constexpr int SEQ_WORDS = SEQ_PAD + SEQ_CAP + 8;
     static constexpr int CIG_WORDS = CIG_CAP + 8;
-    static constexpr int WARP_WORDS = 32 * RS + SEQ_WORDS + CIG_WORDS + ROWW;
+    static constexpr int WARP_WORDS = 32 * RS + SEQ_WORDS + CIG_WORDS;
     static constexpr int WARPS = (227 * 1024 / 4) / WARP_WORDS > 16 ? 16 : (227 * 1024 / 4) / WARP_WORDS;
 };
 
@@ -89,6 +89,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// X and I events go straight to a packed global counter per column (X count in the low, I count in the high 32
+// bits): they are sparse (a few per read), and keeping them out of shared memory buys another resident warp.
+// One add serves both kinds: +1 (a deletion column), +2^32 (an insertion anchor), +2^32 - 1 (an anchor on a
+// deletion's last column: that column reads "*+n..", no longer "*").
+__device__ __forceinline__ void red_xi(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+constexpr unsigned long long XI_X = 1ull, XI_I = 1ull << 32, XI_I_MINUS_X = (1ull << 32) - 1ull;
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds4(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
@@ -100,9 +106,9 @@ __device__ __forceinline__ void sts4(uint32_t a, uint4 v) {
 // Walk, general form (pads / zero-length ops present in the sub-tile): one op per iteration with the full
 // look-ahead state of htslib's resolve_cigar2.  One lane = one read.  cs: word offset of the read's staged
 // CIGAR ops (overwritten by head-fragment descriptors), x: start column inside the window, lq: l_seq,
-// row: word offset of the lane's row, xi: word offset of the warp's packed X|I counters.
+// row: shared address of the lane's row, xi: the packed X|I counters of the window's first column, xi_n: columns left.
 template <int ROWW>
-__device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nops, int x, const int lq, const uint32_t row, const uint32_t xi, int* err) {
+__device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nops, int x, const int lq, const uint32_t row, unsigned long long* xi, const int xi_n, int* err) {
     const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
     int y = 0, nd = 0, b_first = INT_MAX, last_end = 0;
     int pend = 0, lastcol = 0;
@@ -129,10 +135,10 @@ __device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nop
                 last_end = e;
             }
             if (op == OP_D && e <= ROWW)
-                for (int col = x; col < e; ++col) reds(xi + 4 * col, 1u);
+                for (int col = x; col < e; ++col) red_xi(xi + min(col, xi_n - 1), XI_X);
             if (op == OP_I) {
                 if (pend && l > 0) {
-                    if (lastcol >= 0 && lastcol < ROWW) reds(xi + 4 * lastcol, last_was_d ? 0xffffu : 0x10000u);
+                    if (lastcol >= 0 && lastcol < ROWW) red_xi(xi + min(lastcol, xi_n - 1), last_was_d ? XI_I_MINUS_X : XI_I);
                     pend = 0;
                 }
             } else if (op == OP_P) {
@@ -211,7 +217,7 @@ __device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t ro
 // sq: shared address of the read's first staged SEQ word.  Returns the read's end column (x after the last op).
 template <int ROWW, int CW>
 __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int y0, const int lq, const uint32_t row,
-                                                const uint32_t xi, const uint32_t sq, int* err) {
+                                                unsigned long long* xi, const int xi_n, const uint32_t sq, int* err) {
     int y = y0, rem = 0;       // y0: query index of the first base relative to sq's first nibble (pieces of long reads: 0..7)
     uint32_t cp = cs;                       // next op
     const uint32_t cend = cs + 4u * (uint32_t)nops;
@@ -236,11 +242,11 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
                 // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*").
                 // Without zero-length ops the anchor exists whenever the previous op consumed the reference; a
-                // column past the window is clamped (the read is rejected right below, its counts are void).
+                // column past the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
                 const bool is_d = (op == OP_D);
                 if (is_d || (op == OP_I && (prev & 2u)))
-                    reds(xi + 4u * (uint32_t)min(is_d ? x : x - 1, ROWW - 1), is_d ? 1u : ((prev & 1u) ? 0xffffu : 0x10000u));
-                if (is_d && l > 1) for (int col = x + 1; col < min(x + l, ROWW); ++col) reds(xi + 4 * col, 1u);
+                    red_xi(xi + min(is_d ? x : x - 1, xi_n - 1), is_d ? XI_X : ((prev & 1u) ? XI_I_MINUS_X : XI_I));
+                if (is_d && l > 1) for (int col = x + 1; col < min(x + l, xi_n); ++col) red_xi(xi + col, XI_X);
                 prev = (fl & 2u) | (is_d ? 1u : 0u);
                 x += (fl & 2u) ? l : 0;
                 y += (fl & 4u) ? l : 0;
@@ -299,9 +305,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     const uint32_t rows = (uint32_t)__cvta_generic_to_shared(smem) + 4u * (threadIdx.x >> 5) * G::WARP_WORDS;   // [32][RS]
     const uint32_t seq_s = rows + 4u * 32 * RS;                 // seq_s + 4 * SEQ_PAD <-> SEQ word sbase_al
     const uint32_t cig_s = seq_s + 4u * G::SEQ_WORDS;
-    const uint32_t xi = cig_s + 4u * G::CIG_WORDS;              // [ROWW]  X count | I count << 16
     for (int i = lane; i < 32 * RS; i += 32) sts(rows + 4 * i, 0u);
-    for (int i = lane; i < ROWW; i += 32) sts(xi + 4 * i, 0u);
     if (lane < G::SEQ_PAD) sts(seq_s + 4 * lane, 0u);
     __syncwarp();
 
@@ -353,17 +357,6 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
 #pragma unroll
             for (int p = 0; p < HI_PLANES; ++p) hi[j][p] = 0;
         }
-        for (int i = lane; i < ROWW; i += 32) {
-            const uint32_t v = lds(xi + 4 * i);
-            if (v) {
-                const int xv = (int)(v & 0xffffu), iv = (int)(v >> 16);
-                if (w0 + i < L) {
-                    if (xv) atomicAdd(&a.counts[(size_t)TC_ROW_X * L + w0 + i], xv);
-                    if (iv) atomicAdd(&a.counts[(size_t)TC_ROW_I * L + w0 + i], iv);
-                }
-                sts(xi + 4 * i, 0u);
-            }
-        }
         __syncwarp();
     };
 
@@ -379,6 +372,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             const tc_piece* pc = a.pieces + a.piece_order[ri];
             const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(pc)), m1 = __ldg(reinterpret_cast<const uint4*>(pc) + 1);
             p = (int)m0.x; lq = (int)m1.y; y0 = (int)m1.z;
+            passes = p < L;
             const uint32_t so = m0.y, co = m0.z;
             nops_lane = (int)m0.w;
             const int p0 = __shfl_sync(FULL, p, 0);
@@ -444,6 +438,10 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             lq = a.r.l_seq[ri];
             passes = !(flg & (a.flag_filter | 4u)) && !(a.ignore_orphans && (flg & 1u) && !(flg & 2u));
             if (a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[ri] < a.min_mapq) passes = false;
+            if (p >= L) {       // starts past the reference: TC_ERR_RANGE (the span pass says so; without one, here) — never walked
+                if (fold && valid && passes) atomicCAS(&a.status->err, 0, TC_ERR_RANGE);
+                passes = false;
+            }
             const int p0 = __shfl_sync(FULL, p, 0);
             const bool fresh = (w0 == INT_MIN);
             if (fresh) w0 = max(p0, 0) & ~7;
@@ -575,12 +573,13 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         const int nops = act ? nops_lane : 0;
         const int x0 = p - w0;
         const uint32_t sq = act ? sq_lane : seq_s + 4u * G::SEQ_PAD;
+        if (!act) cs = cig_s;           // lanes without a read still run the loops' first fetch: keep it inside the slice
         int x_end;
         if (!cig_exotic) {
-            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, y0, lq, row, xi, sq, &a.status->err);
+            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, y0, lq, row, a.xi + w0, L - w0, sq, &a.status->err);
         } else {
             // pads or zero-length ops somewhere in the sub-tile (rare): the general three-pass form
-            const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, xi, &a.status->err);
+            const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, a.xi + w0, L - w0, &a.status->err);
             x_end = wo.x_end;
             expand_rows<WC>(wo, row, sq, cs);
         }
