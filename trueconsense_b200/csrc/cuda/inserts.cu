@@ -351,36 +351,48 @@ __global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_c
     unsigned int* tcnt = reinterpret_cast<unsigned int*>(tkey + INS_TBL);           // [INS_TBL]
     unsigned int* tfirst = tcnt + INS_TBL;                                          // [INS_TBL] first slot (file order) of the key
     __shared__ unsigned long long best_s;
-    __shared__ int over_s;
+    __shared__ int over_s, hashed_s;
     const int ci = blockIdx.x;
     if (a.layout && a.layout[2]) return;        // the speculative layout did not fit: the host sizes it and runs again
     const int64_t off = a.seg_off[ci];
     const int lo = a.range[2 * ci];
     const int n = a.range[2 * ci + 1] - lo;
     for (int i = threadIdx.x; i < INS_TBL; i += blockDim.x) { tkey[i] = KEY_NONE; tcnt[i] = 0; tfirst[i] = 0xffffffffu; }
-    if (threadIdx.x == 0) { best_s = 0ull; over_s = 0; }
+    if (threadIdx.x == 0) { best_s = 0ull; over_s = 0; hashed_s = 0; }
     __syncthreads();
-    const int n_round = (n + 31) & ~31;     // whole warps stay together for the match
-    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
-        const unsigned long long k = i < n ? a.ent_key[off + i] : KEY_NONE;
-        // lanes holding the same key insert once (most entries of a column print the same string)
-        const unsigned grp = __match_any_sync(0xffffffffu, k);
-        if (k == KEY_NONE || (__ffs(grp) - 1) != (int)(threadIdx.x & 31)) continue;
-        unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
-        int probes = 0;
-        for (;;) {
-            const unsigned long long old = atomicCAS(&tkey[h], KEY_NONE, k);
-            if (old == KEY_NONE || old == k) { atomicAdd(&tcnt[h], (unsigned)__popc(grp)); atomicMin(&tfirst[h], (unsigned)i); break; }
-            h = (h + 1) & (INS_TBL - 1);
-            if (++probes >= INS_TBL * 7 / 8) { over_s = 1; break; }
+    // four keys per thread are in flight at a time (the loop is bound by the latency of these loads)
+    for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
+        unsigned long long kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+            kk[u] = i < n ? a.ent_key[off + i] : KEY_NONE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+            const unsigned long long k = kk[u];
+            // lanes holding the same key insert once (most entries of a column print the same string)
+            const unsigned grp = __match_any_sync(0xffffffffu, k);
+            if (k == KEY_NONE || (__ffs(grp) - 1) != (int)(threadIdx.x & 31)) continue;
+            if (!(k >> 62)) hashed_s = 1;       // a hashed key (an insertion longer than 12): entries get verified below
+            unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
+            int probes = 0;
+            for (;;) {
+                const unsigned long long old = atomicCAS(&tkey[h], KEY_NONE, k);
+                if (old == KEY_NONE || old == k) { atomicAdd(&tcnt[h], (unsigned)__popc(grp)); atomicMin(&tfirst[h], (unsigned)i); break; }
+                h = (h + 1) & (INS_TBL - 1);
+                if (++probes >= INS_TBL * 7 / 8) { over_s = 1; break; }
+            }
         }
     }
     __syncthreads();
     if (over_s) { if (threadIdx.x == 0) atomicExch(a.overflow, 1); return; }
-    // hashed keys (insertions longer than 8): every entry against the first entry of its key
+    // hashed keys (insertions longer than 12): every entry against the first entry of its key
+    if (hashed_s)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned long long k = a.ent_key[off + i];
-        if (k == KEY_NONE || (k >> 62)) continue;
+        if (k == KEY_NONE || (k >> 62)) continue;      // exact keys need no check
         unsigned h = (unsigned)(k ^ (k >> 29)) & (INS_TBL - 1);
         while (tkey[h] != k) h = (h + 1) & (INS_TBL - 1);
         const unsigned f = tfirst[h];
