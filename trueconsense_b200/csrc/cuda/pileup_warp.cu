@@ -221,25 +221,22 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
     int y = y0, rem = 0;       // y0: query index of the first base relative to sq's first nibble (pieces of long reads: 0..7)
     uint32_t cp = cs;                       // next op
     const uint32_t cend = cs + 4u * (uint32_t)nops;
-    uint32_t cnext = lds(cs);               // ops are fetched one ahead of their use (the address stays inside the slice)
+    // the next two ops are fetched ahead of their use (the addresses stay inside the slice: the staged CIGARs are
+    // followed by padding words)
+    uint32_t c0 = lds(cs), c1 = lds(cs + 4);
     // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
     uint32_t prev = 0;
     while (__any_sync(FULL, cp < cend || rem > 0)) {
-        if (rem == 0) {
-            while (cp < cend) {
-                const uint32_t c = cnext;
-                cp += 4;
-                cnext = lds(cp);
+        // Between two chunks a lane consumes at most one op that is not a match (typically the I or D between two
+        // match ops) and then starts the match op behind it: straight-line code for the common "M I M D M" shape;
+        // a second op in a row that is not a match (S I, D I, ...) simply waits for the next iteration.
+        if (rem == 0 && cp < cend) {
+            uint32_t c = c0;
+            uint32_t fl = op_flags(c & 15u);
+            if (!(fl & 1u)) {
                 const uint32_t op = c & 15u;
-                const uint32_t fl = op_flags(op);
                 const int l = (int)(c >> 4);
-                if (fl & 1u) {
-                    // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-                    if (x + l > ROWW || y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
-                    else rem = l;
-                    break;
-                }
-                // one shared add serves both events: a deletion's first column (+1 X), or an insertion's anchor
+                // one add serves both events: a deletion's first column (+1 X), or an insertion's anchor
                 // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*").
                 // Without zero-length ops the anchor exists whenever the previous op consumed the reference; a
                 // column past the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
@@ -250,7 +247,17 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 prev = (fl & 2u) | (is_d ? 1u : 0u);
                 x += (fl & 2u) ? l : 0;
                 y += (fl & 4u) ? l : 0;
+                cp += 4;
+                c = c1;
+                fl = op_flags(c & 15u);
             }
+            if ((fl & 1u) && cp < cend) {
+                const int l = (int)(c >> 4);
+                // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
+                if (x + l > ROWW || y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
+                else { rem = l; cp += 4; }
+            }
+            c0 = lds(cp); c1 = lds(cp + 4);
         }
         __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
         if (rem > 0) {
