@@ -16,22 +16,31 @@
 //               and the window moves.  Deep data flushes once per thousands of reads.
 //   stage       the packed SEQ words and CIGAR ops of the <= 32 reads are contiguous in HBM: the warp
 //               copies them to its shared-memory slice as 16-byte vectors, byte-swapping SEQ words to
-//               "first base in the top nibble"; the next sub-tile's lines are prefetched to L2.  Codes that
-//               are not one-hot (N, IUPAC) are detected on the way (3 ops per word) and cleared afterwards,
-//               one dirty vector per lane and iteration.
-//   emit        one lane per read, walk and expansion fused (emit_read_common): lanes stay in step on
-//               chunks of match ops — the part of an M/=/X op inside four consecutive 8-column row words —
-//               consuming the I / D / S ops in front of it first (deletion columns and insertion anchors,
-//               sparse, go to packed 16+16-bit shared counters with one red.shared.add), then five source
-//               words, four funnel shifts under the op's shift D (query index = column + D), head / tail
-//               masks, four red.shared.or into the lane's own row.  Nothing is written to be re-read.
-//               Sub-tiles containing pads or zero-length ops (rare) take the general three-pass form instead
-//               (walk_read_general + expand_rows: htslib's full look-ahead state).
-//   column sum  lane j owns row words j, j+32, ...: 32 rows go through two 16-input carry-save trees
+//               "first base in the top nibble" and packing CIGAR ops to 16 bits (length < 4096 inside a
+//               window); the next sub-tile's lines are prefetched to L2.  Codes that are not one-hot (N,
+//               IUPAC) are detected on the way (3 ops per word) and cleared afterwards, one dirty vector
+//               per lane and iteration.
+//   emit        one lane per read, walk and expansion fused (emit_phase): lanes stay in step on
+//               chunks of match ops — the part of an M/=/X op inside CW consecutive 8-column row words —
+//               consuming the I / D / S op in front of it first (deletion columns and insertion anchors,
+//               sparse, go to packed 64-bit global counters with one red.global.add), then CW + 1 source
+//               words, CW funnel shifts under the op's shift D (query index = column + D), head / tail
+//               masks, CW red.shared.or into the lane's own row.  Nothing is written to be re-read.
+//   phases      the lanes' rows cover 256 columns only (32 x 33 words per warp whatever the window width):
+//               a window of 512 / 1024 columns is walked in 2 / 4 PHASES — every lane runs until its read
+//               reaches the phase's last column (chunks are cut there), the rows are summed into that
+//               phase's counters and cleared, and the walk resumes from the registers it stopped in.  The
+//               kernel's speed is proportional to the warps resident per SM (measured: 6 / 8 / 10 / 12
+//               warps -> 1.06 / 0.80 / 0.70 / 0.60 ms), shared memory is what limits them, and rows of
+//               the full window width were 44 % of a warp's slice.
+//   column sum  lane j owns row word j of the phase: 32 rows go through two 16-input carry-save trees
 //               into the bit-sliced counters (4 + HI planes per word, in registers across sub-tiles).
 //   span pass   when the caller bounds the longest reference span (tc_reads_t.max_ref_span) the kernel also
 //               checks sort order and range and adds the two ends of every read's span to the coverage
 //               difference array (combined inside the warp with match.any) — no separate pass over the CIGARs.
+//   declined    sub-tiles with pads, zero-length ops, or an op of 4096+ bases that matters raise
+//               TC_ERR_CAPACITY: tc_pileup_counts then runs the batch through the scatter kernel, which
+//               carries htslib's full look-ahead state (such CIGARs are legal and essentially never seen).
 #include <limits.h>
 
 #include "pileup.cuh"
@@ -46,22 +55,33 @@ constexpr int RUN_CAP = 2047;
 #define TC_CHUNK_WORDS 6
 #endif
 constexpr int CHUNK_WORDS = TC_CHUNK_WORDS;     // row words per emitted chunk of a match op
+#ifndef TC_MAX_WARPS
+#define TC_MAX_WARPS 24                         // 80 registers per thread (short reads: 24 warps fit the 256-column geometry)
+#endif
+#ifndef TC_CIG_PER_WC
+#define TC_CIG_PER_WC 16
+#endif
+#ifndef TC_PHASE_WORDS
+#define TC_PHASE_WORDS 32                       // 32: 256-column phases; 0: one phase (rows as wide as the window)
+#endif
 // per op: bit0 = M/=/X, bit1 = consumes reference, bit2 = consumes query (MIDNSHP=X -> 0..8)
 constexpr uint32_t OPFLAGS = 7u | (4u << 3) | (2u << 6) | (2u << 9) | (4u << 12) | (7u << 21) | (7u << 24);
 // clamped shift: ops 11..15 (not defined by BAM) index past the table and read 0
 __device__ __forceinline__ uint32_t op_flags(uint32_t op) { return __funnelshift_rc(OPFLAGS, 0u, 3u * op) & 7u; }
 
 template <int WC> struct geom {
-    static constexpr int ROWW = WC * 8;             // window / row width in reference columns
-    static constexpr int RS = WC + 1;               // padded row stride (words)
-    static constexpr int NW = WC / 32;              // row words owned by one lane in the column sum
+    static constexpr int ROWW = WC * 8;             // window width in reference columns
+    static constexpr int PW = (TC_PHASE_WORDS > 0 && TC_PHASE_WORDS < WC) ? TC_PHASE_WORDS : WC;   // row words (8 columns each) per phase
+    static constexpr int NPH = WC / PW;             // phases
+    static constexpr int NW = WC / 32;              // window words owned by one lane in the column sum
+    static constexpr int RS = PW + 1;               // padded row stride (words)
     static constexpr int SEQ_PAD = 4;               // zero words in front of the staged SEQ stream
     static constexpr int SEQ_CAP = WC * 27;         // staged SEQ words per sub-tile (WC=64: 32 reads of 432 bases)
-    static constexpr int CIG_CAP = WC * 14;         // staged CIGAR ops per sub-tile
+    static constexpr int CIG_CAP = WC * TC_CIG_PER_WC;   // staged CIGAR ops per sub-tile (16 bits each)
     static constexpr int SEQ_WORDS = SEQ_PAD + SEQ_CAP + 8;
-    static constexpr int CIG_WORDS = CIG_CAP + 8;
+    static constexpr int CIG_WORDS = CIG_CAP / 2 + 4;
     static constexpr int WARP_WORDS = 32 * RS + SEQ_WORDS + CIG_WORDS;
-    static constexpr int WARPS = (227 * 1024 / 4) / WARP_WORDS > 16 ? 16 : (227 * 1024 / 4) / WARP_WORDS;
+    static constexpr int WARPS = (227 * 1024 / 4) / WARP_WORDS > TC_MAX_WARPS ? TC_MAX_WARPS : (227 * 1024 / 4) / WARP_WORDS;
 };
 
 __device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
@@ -78,8 +98,6 @@ __device__ __forceinline__ uint32_t clear_multibit(uint32_t w) {
     return w & ~(m * 15u);
 }
 
-struct walk_out { int nd, b_first, last_end, x_end; };
-
 extern __shared__ __align__(16) uint32_t smem[];
 
 // Shared memory is addressed through 32-bit shared-window byte addresses and explicit ld/st/red.shared:
@@ -88,7 +106,6 @@ extern __shared__ __align__(16) uint32_t smem[];
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void reds(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // X and I events go straight to a packed global counter per column (X count in the low, I count in the high 32
 // bits): they are sparse (a few per read), and keeping them out of shared memory buys another resident warp.
 // One add serves both kinds: +1 (a deletion column), +2^32 (an insertion anchor), +2^32 - 1 (an anchor on a
@@ -103,135 +120,44 @@ __device__ __forceinline__ void sts4(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Walk, general form (pads / zero-length ops present in the sub-tile): one op per iteration with the full
-// look-ahead state of htslib's resolve_cigar2.  One lane = one read.  cs: word offset of the read's staged
-// CIGAR ops (overwritten by head-fragment descriptors), x: start column inside the window, lq: l_seq,
-// row: shared address of the lane's row, xi: the packed X|I counters of the window's first column, xi_n: columns left.
-template <int ROWW>
-__device__ __forceinline__ walk_out walk_read_general(const uint32_t cs, int nops, int x, const int lq, const uint32_t row, unsigned long long* xi, const int xi_n, int* err) {
-    const bool has_seq = lq != 0;           // SEQ '*': every base reads 'N' — events and coverage only
-    int y = 0, nd = 0, b_first = INT_MAX, last_end = 0;
-    int pend = 0, lastcol = 0;
-    bool last_was_d = false;
-    const int kmax = __reduce_max_sync(FULL, nops);
-    for (int k = 0; k < kmax; ++k) {
-        if (k < nops) {
-            const uint32_t c = lds(cs + 4 * k);
-            const uint32_t op = c & 15u;
-            const int l = (int)(c >> 4);
-            const uint32_t fl = op_flags(op);
-            const int e = x + l;
-            if ((fl & 1u) && has_seq && l > 0 && (y + l > lq || e > ROWW)) { atomicCAS(err, 0, TC_ERR_CAPACITY); nops = 0; }   // CIGAR longer than SEQ
-            else if ((fl & 1u) && has_seq && l > 0) {
-                const int D = y - x;
-                const int fw8 = (x + 7) & ~7;
-                if (fw8 < e) sts(row + (fw8 >> 1), (uint32_t)e | ((uint32_t)D << 11));
-                if (x & 7) {
-                    const int fe = min(e, (x | 7) + 1);
-                    sts(cs + 4 * nd, (uint32_t)x | ((uint32_t)(fe - x) << 11) | ((uint32_t)D << 14));
-                    ++nd;
-                }
-                b_first = min(b_first, x);
-                last_end = e;
-            }
-            if (op == OP_D && e <= ROWW)
-                for (int col = x; col < e; ++col) red_xi(xi + min(col, xi_n - 1), XI_X);
-            if (op == OP_I) {
-                if (pend && l > 0) {
-                    if (lastcol >= 0 && lastcol < ROWW) red_xi(xi + min(lastcol, xi_n - 1), last_was_d ? XI_I_MINUS_X : XI_I);
-                    pend = 0;
-                }
-            } else if (op == OP_P) {
-                if (pend == 1) pend = 2;
-            } else if (!(fl & 2u)) {
-                if (pend == 1) pend = 0;
-            }
-            if (fl & 2u) { pend = 1; last_was_d = (op == OP_D); lastcol = e - 1; }
-            x = (fl & 2u) ? e : x;
-            y += (fl & 4u) ? l : 0;
-            if (x > ROWW) { atomicCAS(err, 0, TC_ERR_CAPACITY); nops = 0; nd = 0; b_first = INT_MAX; }
-        }
-    }
-    walk_out o; o.nd = nd; o.b_first = b_first; o.last_end = last_end; o.x_end = x;
-    return o;
-}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts2(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+// two BAM CIGAR words -> two 16-bit ops (len << 4 | op, len < 4096) in one word
+__device__ __forceinline__ uint32_t pack_ops(uint32_t c0, uint32_t c1) { return __byte_perm(c0, c1, 0x5410); }
+// pads and zero-length ops: min((op ^ P), len) is 0 exactly for those
+__device__ __forceinline__ uint32_t op_exotic_min(uint32_t c) { return min((c & 15u) ^ 6u, c >> 4); }
+constexpr uint32_t OP_BIG = 1u << 16;           // an op of 4096+ bases does not fit 16 bits
+constexpr uint32_t S_SATURATED = (4095u << 4) | OP_S;
 
-// Expansion passes of the general form (after walk_read_general).  A: one row word per iteration; a non-zero word
-// is the (end column, shift) of a new regime; the word becomes funnelshift(source words under D) cut at the end.
-// B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row.
-template <int WC>
-__device__ __forceinline__ void expand_rows(const walk_out wo, const uint32_t row, const uint32_t sq, const uint32_t cs) {
-    // ---- expand A: one row word per iteration; a non-zero word starts a new regime (end column, shift)
-    {
-        const bool any_m = wo.b_first != INT_MAX;
-        const int o0 = any_m ? wo.b_first >> 3 : 0;
-        const int words = any_m ? ((wo.last_end - 1) >> 3) - o0 + 1 : 0;
-        const int itmax = __reduce_max_sync(FULL, words);
-        // Every lane runs all itmax iterations, no branches: past its own last word a lane points at its
-        // row's pad word (always zero: no new regime, and the regime in force has ended, so it stores zero).
-        // Source addresses under a regime that has ended stay inside the warp's shared-memory slice.
-        uint32_t rp = row + 4u * o0;            // the row word of this iteration
-        const uint32_t rpad = row + 4u * WC;
-        uint32_t sp = sq + 4u * o0;             // the SEQ word under it (+ 4 * (D >> 3) of the regime in force)
-        int sh4 = 0, rem4 = 0, left = words;    // rem4: 4 * (columns the regime still covers from this word's first column)
-#pragma unroll 4
-        for (int it = 0; it < itmax; ++it) {
-            const uint32_t rq = left > 0 ? rp : rpad;
-            const uint32_t t = lds(rq);
-            if (t) {
-                const int D = (int)t >> 11;
-                rem4 = 4 * ((int)(t & 0x7ffu) - 8 * (o0 + it));
-                sp = sq + 4u * (o0 + it) + (uint32_t)((D >> 3) << 2);
-                sh4 = (D & 7) << 2;
-            }
-            const uint32_t v = __funnelshift_l(lds(sp + 4), lds(sp), sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4, 0));
-            sts(rq, v);
-            rem4 -= 32; rp += 4; sp += 4; --left;
-        }
-    }
-    // ---- expand B: head fragments (an M op starting inside a row word), OR-ed into the lane's own row
-    {
-        const int itmax = __reduce_max_sync(FULL, wo.nd);
-        for (int it = 0; it < itmax; ++it) {
-            if (it < wo.nd) {
-                const uint32_t d = lds(cs + 4 * it);
-                const int b = (int)(d & 0x7ffu), flen = (int)((d >> 11) & 7u), D = (int)d >> 14;
-                const int o = b >> 3, kb = b & 7;
-                const int q0 = 8 * o + D;
-                const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
-                const uint32_t v = __funnelshift_l(lds(s + 4), lds(s), (q0 & 7) << 2);
-                const uint32_t m = (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, 4 * (kb + flen));
-                sts(row + 4 * o, lds(row + 4 * o) | (v & m));
-            }
-        }
-    }
-}
+// A lane's walk over its read, resumable between phases.
+struct lane_walk {
+    uint32_t cp, cend;      // shared addresses of the next op and of the end of the read's ops (16 bits each)
+    uint32_t c0, c1;        // the next two ops, fetched ahead of their use
+    uint32_t prev;          // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
+    int x, y, rem;          // window column, query index, columns left of the match op being emitted
+};
 
-// Common form (no pads, no zero-length ops, every read has SEQ), fused: walk and expansion in one pass, no
-// descriptors.  One lane = one read; lanes are kept in
-// step on CHUNKS of match ops: a chunk is the part of an M/=/X op that falls into CW consecutive row words
-// (at most 8 * CW - (x & 7) columns; CW = 6 measured best on ONT-like reads, 4 and 8 within 3 %).  Per outer iteration a lane first consumes the ops in front of its next match
-// op (typically one I or D: the sparse X / I events), then emits one chunk: CW + 1 source words, CW funnel
-// shifts under the op's shift D (query index = column + D), head / tail masks, CW red.shared.or into its own
-// row.  Straight-line, nothing is written to be re-read by a later pass.
-// sq: shared address of the read's first staged SEQ word.  Returns the read's end column (x after the last op).
-template <int ROWW, int CW>
-__device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nops, int x, const int y0, const int lq, const uint32_t row,
-                                                unsigned long long* xi, const int xi_n, const uint32_t sq, int* err) {
-    int y = y0, rem = 0;       // y0: query index of the first base relative to sq's first nibble (pieces of long reads: 0..7)
-    uint32_t cp = cs;                       // next op
-    const uint32_t cend = cs + 4u * (uint32_t)nops;
-    // the next two ops are fetched ahead of their use (the addresses stay inside the slice: the staged CIGARs are
-    // followed by padding words)
-    uint32_t c0 = lds(cs), c1 = lds(cs + 4);
-    // what the op before the current one was: bit 1 = it consumed the reference, bit 0 = it was a deletion
-    uint32_t prev = 0;
-    while (__any_sync(FULL, cp < cend || rem > 0)) {
-        // Between two chunks a lane consumes at most one op that is not a match (typically the I or D between two
-        // match ops) and then starts the match op behind it: straight-line code for the common "M I M D M" shape;
-        // a second op in a row that is not a match (S I, D I, ...) simply waits for the next iteration.
-        if (rem == 0 && cp < cend) {
-            uint32_t c = c0;
+// One phase of the walk (no pads, no zero-length ops: those sub-tiles are declined), walk and expansion fused, no
+// descriptors.  One lane = one read; lanes are kept in step on CHUNKS of match ops: a chunk is the part of an M/=/X
+// op that falls into CW consecutive row words (at most 8 * CW - (x & 7) columns; CW = 6 measured best on ONT-like
+// reads, 4 and 8 within 3 %) and in front of the phase's last column xlim.  Per iteration a lane first consumes at
+// most one op that is not a match (typically the I or D between two match ops: the sparse X / I events) and starts
+// the match op behind it — straight-line code for the common "M I M D M" shape; a second op in a row that is not a
+// match (S I, D I, ...) simply waits for the next iteration — then emits one chunk: CW + 1 source words, CW funnel
+// shifts under the op's shift D (query index = column + D), head / tail masks, CW red.shared.or into its own row.
+// rowp: shared address of the lane's row minus the phase's first word; sq: shared address of the read's first staged
+// SEQ word; lq: l_seq (reads without SEQ have had their match ops turned into reference skips).  Returns whether any
+// lane did anything (the rows are then summed).
+template <int ROWW, int CW, bool LIMIT>
+__device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uint32_t rowp, const int xlim,
+                                           unsigned long long* xi, const int xi_n, const uint32_t sq, int* err) {
+    bool any_iter = false;
+    // LIMIT: the phase ends at column xlim (otherwise it runs to the end of the reads and xlim plays no part)
+    while (__any_sync(FULL, (s.cp < s.cend || s.rem > 0) && (!LIMIT || s.x < xlim))) {
+        any_iter = true;
+        if (s.rem == 0 && s.cp < s.cend && (!LIMIT || s.x < xlim)) {
+            uint32_t c = s.c0;
             uint32_t fl = op_flags(c & 15u);
             if (!(fl & 1u)) {
                 const uint32_t op = c & 15u;
@@ -241,54 +167,56 @@ __device__ __forceinline__ int emit_read_common(const uint32_t cs, const int nop
                 // Without zero-length ops the anchor exists whenever the previous op consumed the reference; a
                 // column past the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
                 const bool is_d = (op == OP_D);
-                if (is_d || (op == OP_I && (prev & 2u)))
-                    red_xi(xi + min(is_d ? x : x - 1, xi_n - 1), is_d ? XI_X : ((prev & 1u) ? XI_I_MINUS_X : XI_I));
-                if (is_d && l > 1) for (int col = x + 1; col < min(x + l, xi_n); ++col) red_xi(xi + col, XI_X);
-                prev = (fl & 2u) | (is_d ? 1u : 0u);
-                x += (fl & 2u) ? l : 0;
-                y += (fl & 4u) ? l : 0;
-                cp += 4;
-                c = c1;
+                if (is_d || (op == OP_I && (s.prev & 2u)))
+                    red_xi(xi + min(is_d ? s.x : s.x - 1, xi_n - 1), is_d ? XI_X : ((s.prev & 1u) ? XI_I_MINUS_X : XI_I));
+                if (is_d && l > 1) for (int col = s.x + 1; col < min(s.x + l, xi_n); ++col) red_xi(xi + col, XI_X);
+                s.prev = (fl & 2u) | (is_d ? 1u : 0u);
+                s.x += (fl & 2u) ? l : 0;
+                s.y += (fl & 4u) ? l : 0;
+                s.cp += 2;
+                c = s.c1;
                 fl = op_flags(c & 15u);
             }
-            if ((fl & 1u) && cp < cend) {
+            if ((fl & 1u) && s.cp < s.cend) {
                 const int l = (int)(c >> 4);
                 // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-                if (x + l > ROWW || y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); cp = cend; }
-                else { rem = l; cp += 4; }
+                if (s.x + l > ROWW || s.y + l > lq) { atomicCAS(err, 0, TC_ERR_CAPACITY); s.cp = s.cend; }
+                else { s.rem = l; s.cp += 2; }
             }
-            c0 = lds(cp); c1 = lds(cp + 4);
+            s.c0 = lds16(s.cp); s.c1 = lds16(s.cp + 2);
         }
-        __syncwarp();           // lanes leave the loop above at different points: emit the chunks together
-        if (rem > 0) {
+        __syncwarp();           // lanes leave the part above at different points: emit the chunks together
+        if (s.rem > 0 && (!LIMIT || s.x < xlim)) {
+            const int x = s.x;
             const int kb = x & 7;
-            const int cl = min(rem, 8 * CW - kb);
+            const int cl = LIMIT ? min(min(s.rem, 8 * CW - kb), xlim - x) : min(s.rem, 8 * CW - kb);
             {
-                const int q0 = (x - kb) + (y - x);                  // query index under the first column of row word x >> 3
-                const uint32_t s = sq + (uint32_t)((q0 >> 3) << 2);
+                const int q0 = (x - kb) + (s.y - x);                // query index under the first column of row word x >> 3
+                const uint32_t src = sq + (uint32_t)((q0 >> 3) << 2);
                 const int sh4 = (q0 & 7) << 2;
                 uint32_t w[CW + 1];
 #pragma unroll
-                for (int j = 0; j <= CW; ++j) w[j] = lds(s + 4 * j);
+                for (int j = 0; j <= CW; ++j) w[j] = lds(src + 4 * j);
                 const int rem4 = 4 * (kb + cl);                     // 4 * columns from the first row word's start to the chunk's end
-                const uint32_t ro = row + (uint32_t)((x >> 3) << 2);
+                const uint32_t ro = rowp + (uint32_t)((x >> 3) << 2);
                 reds_or(ro, __funnelshift_l(w[1], w[0], sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
+                // words behind the chunk's end get an empty mask (a cut at xlim may leave them past the row: they
+                // land, as zeros, in the pad / the next row / the SEQ pad — inside the warp's slice)
 #pragma unroll
                 for (int j = 1; j < CW; ++j)
                     reds_or(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32 * j, 0)));
             }
-            x += cl; y += cl; rem -= cl;
-            prev = 2u;
+            s.x += cl; s.y += cl; s.rem -= cl;
+            s.prev = 2u;
         }
     }
-    if (x > ROWW) atomicCAS(err, 0, TC_ERR_CAPACITY);       // deletions / skips ran past the window (their event columns were clamped)
-    return x;
+    return any_iter;
 }
 
 template <int WC, bool PIECES>
 __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pileup_args a) {
     using G = geom<WC>;
-    constexpr int ROWW = G::ROWW, RS = G::RS, NW = G::NW;
+    constexpr int ROWW = G::ROWW, RS = G::RS, NW = G::NW, NPH = G::NPH, PW = G::PW, KW = G::PW / 32;
     const int lane = threadIdx.x & 31;
     const int L = a.L;
 
@@ -372,7 +300,8 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         const bool valid = lane < nmax;
         const int64_t ri = r + (valid ? lane : 0);
         int p, lq, n, nops_lane, y0 = 0;
-        bool passes = true, cig_exotic = false;
+        bool passes = true, declined = false;
+        uint32_t big = 0;               // OR of the staged CIGAR words: >= OP_BIG <=> some op does not fit 16 bits
         uint32_t cs, sq_lane;
         if constexpr (PIECES) {
             // ---- pieces of long reads: one record per lane, gathered through the start-sorted order
@@ -410,7 +339,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 continue;
             }
             const uint32_t sdst = seq_s + 4u * G::SEQ_PAD + 16u * (uint32_t)(s_inc - sv);
-            const uint32_t cdst = cig_s + 16u * (uint32_t)(c_inc - cv);
+            const uint32_t cdst = cig_s + 8u * (uint32_t)(c_inc - cv);
             if (lane < n) {
                 const int64_t sb = (int64_t)(so & ~3u);
                 for (int v = 0; v < sv; ++v) {
@@ -431,10 +360,29 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 }
                 // the piece-CIGAR buffer is padded to whole vectors behind its last op
                 const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + (co & ~3u));
-                for (int v = 0; v < cv; ++v) sts4(cdst + 16 * v, __ldg(csrc + v));
+                for (int v = 0; v < cv; ++v) {
+                    const uint4 q = __ldg(csrc + v);
+                    big |= q.x | q.y | q.z | q.w;
+                    sts2(cdst + 8 * v, pack_ops(q.x, q.y), pack_ops(q.z, q.w));
+                }
             }
             __syncwarp();
-            cs = cdst + 4u * (co & 3u);
+            cs = cdst + 2u * (co & 3u);
+            // an op of 4096+ bases (pileup_long.cu drops leading clips; a trailing one is harmless): set right below
+            if (__any_sync(FULL, big >= OP_BIG)) {
+                if (lane < n) {
+                    bool after_sat = false;
+                    for (uint32_t k = 0; k < m0.w; ++k) {
+                        const uint32_t c = __ldg(a.r.cigar + co + k), op = c & 15u;
+                        if (c >= OP_BIG) {
+                            if (op == OP_H) sts16(cs + 2 * k, (1u << 4) | OP_H);
+                            else if (op == OP_S) { sts16(cs + 2 * k, S_SATURATED); after_sat = true; }
+                            else declined = true;
+                        } else if (after_sat && op_flags(op) != 0u) declined = true;       // the query index behind the clip is unknown
+                    }
+                }
+                __syncwarp();
+            }
             sq_lane = sdst + 4u * (so & 3u);
         } else {
             // ---- metadata of the next (up to) 32 reads, one per lane
@@ -532,7 +480,8 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                         for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
                     }
                 }
-                // pads and zero-length ops: min over the words of min((op ^ P), len) is 0 exactly when one is present
+                // CIGAR ops, packed to 16 bits.  Pads and zero-length ops: min over the ops of min((op ^ P), len) is 0
+                // exactly when one is present
                 uint32_t exmin = 1u;
                 if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
                     const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
@@ -540,23 +489,39 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                         uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
                         const bool b1 = i + 32 < ncv;
                         if (b1) v1 = __ldg(csrc + i + 32);
-                        exmin = min(exmin, min(min(min((v0.x & 15u) ^ 6u, v0.x >> 4), min((v0.y & 15u) ^ 6u, v0.y >> 4)),
-                                               min(min((v0.z & 15u) ^ 6u, v0.z >> 4), min((v0.w & 15u) ^ 6u, v0.w >> 4))));
-                        exmin = min(exmin, min(min(min((v1.x & 15u) ^ 6u, v1.x >> 4), min((v1.y & 15u) ^ 6u, v1.y >> 4)),
-                                               min(min((v1.z & 15u) ^ 6u, v1.z >> 4), min((v1.w & 15u) ^ 6u, v1.w >> 4))));
-                        sts4(cig_s + 16 * i, v0);
-                        if (b1) sts4(cig_s + 16 * (i + 32), v1);
+                        exmin = min(exmin, min(min(op_exotic_min(v0.x), op_exotic_min(v0.y)), min(op_exotic_min(v0.z), op_exotic_min(v0.w))));
+                        exmin = min(exmin, min(min(op_exotic_min(v1.x), op_exotic_min(v1.y)), min(op_exotic_min(v1.z), op_exotic_min(v1.w))));
+                        big |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                        sts2(cig_s + 8 * i, pack_ops(v0.x, v0.y), pack_ops(v0.z, v0.w));
+                        if (b1) sts2(cig_s + 8 * (i + 32), pack_ops(v1.x, v1.y), pack_ops(v1.z, v1.w));
                     }
                 } else {
                     for (int i = lane; i < 4 * ncv; i += 32) {
                         const int64_t oi = (int64_t)cbase_al + i;
                         const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
-                        exmin = min(exmin, min((c & 15u) ^ 6u, c >> 4));
-                        sts(cig_s + 4 * i, c);
+                        exmin = min(exmin, op_exotic_min(c));
+                        big |= c;
+                        sts16(cig_s + 2 * i, c);
                     }
                 }
-                // ... and reads without SEQ ('*': every base reads 'N'): the general form below handles all of these
-                cig_exotic = __any_sync(FULL, exmin == 0u || (lane < n && lq == 0));
+                declined = exmin == 0u;
+                __syncwarp();
+                // an op of 4096+ bases (rare: a long clip): hard clips count for nothing, a soft clip saturates (fine when
+                // nothing that consumes the query or the reference follows), anything else is declined
+                if (__any_sync(FULL, big >= OP_BIG)) {
+                    if (lane < n) {
+                        bool after_sat = false;
+                        for (uint32_t k = co; k < co_next; ++k) {
+                            const uint32_t c = __ldg(a.r.cigar + k), op = c & 15u;
+                            if (c >= OP_BIG) {
+                                if (op == OP_H) sts16(cig_s + 2 * (k - cbase_al), (1u << 4) | OP_H);
+                                else if (op == OP_S) { sts16(cig_s + 2 * (k - cbase_al), S_SATURATED); after_sat = true; }
+                                else declined = true;
+                            } else if (after_sat && op_flags(op) != 0u) declined = true;       // the query index behind the clip is unknown
+                        }
+                    }
+                    __syncwarp();
+                }
                 // some base is N / IUPAC (rare in real reads): clear those codes — they only count towards coverage.
                 // Only the vectors that hold one are revisited, one per lane and iteration.
                 while (__any_sync(FULL, dirty != 0)) {
@@ -571,7 +536,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 }
                 __syncwarp();
             }
-            cs = cig_s + 4u * (co - cbase_al);
+            cs = cig_s + 2u * (co - cbase_al);
             nops_lane = (int)(co_next - co);
             sq_lane = seq_s + 4u * G::SEQ_PAD + 4u * (so - sbase_al);
         }
@@ -581,15 +546,66 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
         const int x0 = p - w0;
         const uint32_t sq = act ? sq_lane : seq_s + 4u * G::SEQ_PAD;
         if (!act) cs = cig_s;           // lanes without a read still run the loops' first fetch: keep it inside the slice
-        int x_end;
-        if (!cig_exotic) {
-            x_end = emit_read_common<ROWW, CHUNK_WORDS>(cs, nops, x0, y0, lq, row, a.xi + w0, L - w0, sq, &a.status->err);
-        } else {
-            // pads or zero-length ops somewhere in the sub-tile (rare): the general three-pass form
-            const walk_out wo = walk_read_general<ROWW>(cs, nops, x0, lq, row, a.xi + w0, L - w0, &a.status->err);
-            x_end = wo.x_end;
-            expand_rows<WC>(wo, row, sq, cs);
+        // reads without SEQ ('*': every base reads 'N' — coverage and events only; rare): their match ops become
+        // reference skips of the same length, and the walk below needs no special case
+        if (__any_sync(FULL, act && lq == 0)) {
+            if (act && lq == 0)
+                for (int k = 0; k < nops; ++k) {
+                    const uint32_t c = lds16(cs + 2 * k);
+                    if (op_flags(c & 15u) & 1u) sts16(cs + 2 * k, (c & ~15u) | OP_N);
+                }
+            __syncwarp();
         }
+        // pads, zero-length ops or an over-long op somewhere in the sub-tile: declined (the batch goes to the scatter kernel)
+        const bool skip = __any_sync(FULL, declined);
+        if (skip && lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
+        lane_walk st;
+        st.cp = cs; st.cend = cs + 2u * (uint32_t)(skip ? 0 : nops);
+        st.c0 = lds16(cs); st.c1 = lds16(cs + 2);
+        st.prev = 0; st.x = x0; st.y = y0; st.rem = 0;
+        // ---- phases: walk up to the phase's last column, then sum the rows into the phase's counters
+#pragma unroll
+        for (int ph = 0; ph < NPH; ++ph) {
+            const int xlim = (ph == NPH - 1) ? INT_MAX : 8 * PW * (ph + 1);      // the last phase runs to the end of the reads
+            const bool did = emit_phase<ROWW, CHUNK_WORDS, (NPH > 1)>(st, lq, row - 4u * PW * ph, xlim, a.xi + w0, L - w0, sq, &a.status->err);
+            __syncwarp();
+            if (!did) continue;
+            // column sum: lane owns row words lane + 32 k of the phase, all 32 rows
+#pragma unroll
+            for (int k = 0; k < KW; ++k) {
+                const int j = ph * KW + k;
+                const uint32_t col = rows + 4u * (lane + 32 * k);
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    if (blk * 16 < n) {
+                        uint32_t xw[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) { xw[q] = lds(col + 4u * (blk * 16 + q) * RS); sts(col + 4u * (blk * 16 + q) * RS, 0u); }
+                        uint32_t twosA, twosB, foursA, foursB, eightsA, eightsB, sixteens;
+                        csa(twosA, ones[j], ones[j], xw[0], xw[1]);
+                        csa(twosB, ones[j], ones[j], xw[2], xw[3]);
+                        csa(foursA, twos[j], twos[j], twosA, twosB);
+                        csa(twosA, ones[j], ones[j], xw[4], xw[5]);
+                        csa(twosB, ones[j], ones[j], xw[6], xw[7]);
+                        csa(foursB, twos[j], twos[j], twosA, twosB);
+                        csa(eightsA, fours[j], fours[j], foursA, foursB);
+                        csa(twosA, ones[j], ones[j], xw[8], xw[9]);
+                        csa(twosB, ones[j], ones[j], xw[10], xw[11]);
+                        csa(foursA, twos[j], twos[j], twosA, twosB);
+                        csa(twosA, ones[j], ones[j], xw[12], xw[13]);
+                        csa(twosB, ones[j], ones[j], xw[14], xw[15]);
+                        csa(foursB, twos[j], twos[j], twosA, twosB);
+                        csa(eightsB, fours[j], fours[j], foursA, foursB);
+                        csa(sixteens, eights[j], eights[j], eightsA, eightsB);
+                        uint32_t carry = sixteens;
+#pragma unroll
+                        for (int pl = 0; pl < HI_PLANES; ++pl) { const uint32_t t = hi[j][pl] & carry; hi[j][pl] ^= carry; carry = t; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const int x_end = st.x;
 
         // ---- without a span pass: sort order, range, span statistics and the two ends of every read's span in the
         // coverage difference array (adds to the same column are combined inside the warp first)
@@ -610,41 +626,6 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             if (has && (__ffs(g1) - 1) == lane) atomicAdd(&a.diff[p + span], -__popc(g1));
         }
 
-        __syncwarp();
-
-        // ---- column sum: lane owns row words lane + 32 j, all 32 rows
-#pragma unroll
-        for (int j = 0; j < NW; ++j) {
-            const uint32_t col = rows + 4u * (lane + 32 * j);
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk) {
-                if (blk * 16 < n) {
-                    uint32_t xw[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) { xw[q] = lds(col + 4u * (blk * 16 + q) * RS); sts(col + 4u * (blk * 16 + q) * RS, 0u); }
-                    uint32_t twosA, twosB, foursA, foursB, eightsA, eightsB, sixteens;
-                    csa(twosA, ones[j], ones[j], xw[0], xw[1]);
-                    csa(twosB, ones[j], ones[j], xw[2], xw[3]);
-                    csa(foursA, twos[j], twos[j], twosA, twosB);
-                    csa(twosA, ones[j], ones[j], xw[4], xw[5]);
-                    csa(twosB, ones[j], ones[j], xw[6], xw[7]);
-                    csa(foursB, twos[j], twos[j], twosA, twosB);
-                    csa(eightsA, fours[j], fours[j], foursA, foursB);
-                    csa(twosA, ones[j], ones[j], xw[8], xw[9]);
-                    csa(twosB, ones[j], ones[j], xw[10], xw[11]);
-                    csa(foursA, twos[j], twos[j], twosA, twosB);
-                    csa(twosA, ones[j], ones[j], xw[12], xw[13]);
-                    csa(twosB, ones[j], ones[j], xw[14], xw[15]);
-                    csa(foursB, twos[j], twos[j], twosA, twosB);
-                    csa(eightsB, fours[j], fours[j], foursA, foursB);
-                    csa(sixteens, eights[j], eights[j], eightsA, eightsB);
-                    uint32_t carry = sixteens;
-#pragma unroll
-                    for (int pl = 0; pl < HI_PLANES; ++pl) { const uint32_t t = hi[j][pl] & carry; hi[j][pl] ^= carry; carry = t; }
-                }
-            }
-        }
-        __syncwarp();
         r += n;
         run_reads += n;
     }
