@@ -83,6 +83,53 @@ def test_pileup_quirk_batch_direct(ctx, orc, kernel):
     assert np.array_equal(got, pileup.pileup_counts(b, fixtures.QUIRK_REF_LEN))
 
 
+def test_pileup_warp_kernel_takes_plain_quirks_itself(ctx, orc):
+    """Variant 3 declines only pads and zero-length ops (TC_ERR_CAPACITY -> scatter kernel).  Everything else of
+    the quirk set — SEQ '*', IUPAC codes, leading deletions, D/N/I adjacencies, clips, flags — it must take itself
+    (explicit kernel=3, no fallback), bit-exact with the oracle."""
+    from oracle import fixtures
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    recs = [r for r in fixtures.quirk_records() if "P" not in r["cigar"]]
+    assert any(r["seq"] == "*" for r in recs)
+    b = ReadBatch.from_records(recs)
+    got = ctx.pileup_counts(b, fixtures.QUIRK_REF_LEN, gpu.buildindex_params(3))
+    assert np.array_equal(got, pileup.pileup_counts(b, fixtures.QUIRK_REF_LEN))
+    # ... and with pads present it declines, while the library's own choice falls back transparently
+    with pytest.raises(gpu.TcError) as e:
+        ctx.pileup_counts(fixtures.quirk_batch(), fixtures.QUIRK_REF_LEN, gpu.buildindex_params(3))
+    assert e.value.code == -8
+
+
+def test_pileup_ops_longer_than_16_bits(ctx, orc):
+    """Variant 3 stages CIGAR ops as 16 bits (length < 4096).  Longer hard clips count for nothing, a longer soft
+    clip is fine at the end of a read; in front of aligned bases it is declined (explicit kernel=3) and the
+    library's own choice (kernel=0) still answers bit-exactly."""
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    rng = np.random.default_rng(5)
+    L = 400
+    seq = lambda n: "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    ok = [dict(pos=5, cigar="5000H20M2I10M", seq=seq(32)), dict(pos=6, cigar="20M1D10M70000H", seq=seq(30)),
+          dict(pos=7, cigar="30M4500S", seq=seq(4530)), dict(pos=7, cigar="4096H10M2D5M3S4096H", seq=seq(18), flag=16),
+          dict(pos=9, cigar="40M", seq=seq(40))]
+    b = ReadBatch.from_records(ok)
+    exp = pileup.pileup_counts(b, L)
+    assert np.array_equal(ctx.pileup_counts(b, L, gpu.buildindex_params(3)), exp)
+    assert np.array_equal(ctx.pileup_counts(b, L, gpu.buildindex_params(0)), exp)
+    lead = ok + [dict(pos=12, cigar="4200S30M", seq=seq(4230))]
+    b2 = ReadBatch.from_records(lead)
+    exp2 = pileup.pileup_counts(b2, L)
+    with pytest.raises(gpu.TcError) as e:
+        ctx.pileup_counts(b2, L, gpu.buildindex_params(3))
+    assert e.value.code == -8
+    assert np.array_equal(ctx.pileup_counts(b2, L, gpu.buildindex_params(0)), exp2)
+
+
 SYNTH_CASES = {
     "shotgun_indels": dict(n_reads=6000, read_len=120, read_len_jitter=30, indel_rate=0.03, indel_maxlen=3, softclip_rate=0.2,
                            softclip_max=12, n_rate=0.01, iupac_rate=0.01, refskip_rate=0.05, special_flag_rate=0.05, sub_rate=0.02),

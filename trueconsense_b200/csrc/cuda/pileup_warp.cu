@@ -59,7 +59,10 @@ constexpr int CHUNK_WORDS = TC_CHUNK_WORDS;     // row words per emitted chunk o
 #define TC_MAX_WARPS 24                         // 80 registers per thread (short reads: 24 warps fit the 256-column geometry)
 #endif
 #ifndef TC_CIG_PER_WC
-#define TC_CIG_PER_WC 16
+#define TC_CIG_PER_WC 15
+#endif
+#ifndef TC_SEQ_PER_WC
+#define TC_SEQ_PER_WC 26
 #endif
 #ifndef TC_PHASE_WORDS
 #define TC_PHASE_WORDS 32                       // 32: 256-column phases; 0: one phase (rows as wide as the window)
@@ -76,7 +79,7 @@ template <int WC> struct geom {
     static constexpr int NW = WC / 32;              // window words owned by one lane in the column sum
     static constexpr int RS = PW + 1;               // padded row stride (words)
     static constexpr int SEQ_PAD = 4;               // zero words in front of the staged SEQ stream
-    static constexpr int SEQ_CAP = WC * 27;         // staged SEQ words per sub-tile (WC=64: 32 reads of 432 bases)
+    static constexpr int SEQ_CAP = WC * TC_SEQ_PER_WC;   // staged SEQ words per sub-tile (26: WC=64 holds 32 reads of 416 bases; longer reads make shorter sub-tiles)
     static constexpr int CIG_CAP = WC * TC_CIG_PER_WC;   // staged CIGAR ops per sub-tile (16 bits each)
     static constexpr int SEQ_WORDS = SEQ_PAD + SEQ_CAP + 8;
     static constexpr int CIG_WORDS = CIG_CAP / 2 + 4;
