@@ -78,8 +78,8 @@ typedef struct tc_reads {
     const uint32_t* seq4;       /* [n_seq_words] */
     const uint8_t*  qual;       /* [8*n_seq_words] phred bytes; may be NULL when no pass reads QUAL */
     const uint32_t* cigar;      /* [n_cigar_ops] */
-    /* mate information, only read by the samtools-stepper emulation (tc_extract_inserts);
-     * may be NULL for unpaired data */
+    /* mate information: reserved for htslib's mate-overlap quality rewriting, which no kernel emulates yet
+     *  — never read and never copied to the device today; may be NULL */
     const uint64_t* qname_hash; /* [n] any hash of QNAME that is equal for both mates */
     const int32_t*  mpos;       /* [n] PNEXT (0-based, -1 if unavailable) */
     const int32_t*  isize;      /* [n] TLEN */

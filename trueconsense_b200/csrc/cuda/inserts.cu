@@ -473,7 +473,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     // reads them only for the reads over the candidate columns, and QUAL alone is 8x the packed bases.  (Without a
     // span bound the CIGARs of all reads are needed first, so they are staged in full.)
     const bool bounded = reads->max_ref_span > 0;
-    const int stage = NEED_QUAL | NEED_MATE | DEFER_SEQ | DEFER_QUAL | (bounded ? DEFER_CIGAR : 0);
+    const int stage = NEED_QUAL | DEFER_SEQ | DEFER_QUAL | (bounded ? DEFER_CIGAR : 0);
     const bool host_seq = reads->seq4 && !tc_is_device_ptr(reads->seq4);
     const bool host_qual = reads->qual && !tc_is_device_ptr(reads->qual);
     const bool host_cig = bounded && reads->cigar && !tc_is_device_ptr(reads->cigar);

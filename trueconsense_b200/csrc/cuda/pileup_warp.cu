@@ -113,8 +113,7 @@ __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.s
 // bits): they are sparse (a few per read), and keeping them out of shared memory buys another resident warp.
 // One add serves both kinds: +1 (a deletion column), +2^32 (an insertion anchor), +2^32 - 1 (an anchor on a
 // deletion's last column: that column reads "*+n..", no longer "*").
-__device__ __forceinline__ void red_xi(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-constexpr unsigned long long XI_X = 1ull, XI_I = 1ull << 32, XI_I_MINUS_X = (1ull << 32) - 1ull;
+__device__ __forceinline__ void red_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds4(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
@@ -154,7 +153,7 @@ struct lane_walk {
 // lane did anything (the rows are then summed).
 template <int ROWW, int CW, bool LIMIT>
 __device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uint32_t rowp, const int xlim,
-                                           unsigned long long* xi, const int xi_n, const uint32_t sq, int* err) {
+                                           uint32_t* xi, const int xi_n, const uint32_t sq, int* err) {
     bool any_iter = false;
     // LIMIT: the phase ends at column xlim (otherwise it runs to the end of the reads and xlim plays no part)
     while (__any_sync(FULL, (s.cp < s.cend || s.rem > 0) && (!LIMIT || s.x < xlim))) {
@@ -165,17 +164,20 @@ __device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uin
             if (!(fl & 1u)) {
                 const uint32_t op = c & 15u;
                 const int l = (int)(c >> 4);
-                // one add serves both events: a deletion's first column (+1 X), or an insertion's anchor
-                // column x-1 (+1 I, and -1 X when that column belongs to a deletion: it reads "*+n..", not "*").
-                // Without zero-length ops the anchor exists whenever the previous op consumed the reference; a
-                // column past the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
+                // X / I events: a deletion's first column counts +1 X; an insertion counts +1 I on its anchor column
+                // x-1 — and -1 X there when that column belongs to a deletion (it reads "*+n..", not "*").  Without
+                // zero-length ops the anchor exists whenever the previous op consumed the reference; a column past
+                // the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
                 const bool is_d = (op == OP_D);
-                if (is_d || (op == OP_I && (s.prev & 2u)))
-                    red_xi(xi + min(is_d ? s.x : s.x - 1, xi_n - 1), is_d ? XI_X : ((s.prev & 1u) ? XI_I_MINUS_X : XI_I));
-                if (is_d && l > 1) for (int col = s.x + 1; col < min(s.x + l, xi_n); ++col) red_xi(xi + col, XI_X);
+                const bool ev = is_d || (op == OP_I && (s.prev & 2u));
+                const int col = min(is_d ? s.x : s.x - 1, xi_n - 1);
+                uint32_t* cell = xi + 2 * col;               // [0] X, [1] I
+                if (ev) red_u32(cell + (is_d ? 0 : 1), 1u);
+                if (ev && !is_d && (s.prev & 1u)) red_u32(cell, 0xffffffffu);
+                if (is_d && l > 1) for (int k = s.x + 1; k < min(s.x + l, xi_n); ++k) red_u32(xi + 2 * k, 1u);
                 s.prev = (fl & 2u) | (is_d ? 1u : 0u);
-                s.x += (fl & 2u) ? l : 0;
-                s.y += (fl & 4u) ? l : 0;
+                if (fl & 2u) s.x += l;
+                if (fl & 4u) s.y += l;
                 s.cp += 2;
                 c = s.c1;
                 fl = op_flags(c & 15u);
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
 #pragma unroll
         for (int ph = 0; ph < NPH; ++ph) {
             const int xlim = (ph == NPH - 1) ? INT_MAX : 8 * PW * (ph + 1);      // the last phase runs to the end of the reads
-            const bool did = emit_phase<ROWW, CHUNK_WORDS, (NPH > 1)>(st, lq, row - 4u * PW * ph, xlim, a.xi + w0, L - w0, sq, &a.status->err);
+            const bool did = emit_phase<ROWW, CHUNK_WORDS, (NPH > 1)>(st, lq, row - 4u * PW * ph, xlim, reinterpret_cast<uint32_t*>(a.xi + w0), L - w0, sq, &a.status->err);
             __syncwarp();
             if (!did) continue;
             // column sum: lane owns row words lane + 32 k of the phase, all 32 rows

@@ -187,7 +187,7 @@ TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* de
     if (!ctx || !host || !dev) return tc_fail(ctx, TC_ERR_ARG, "NULL argument");
     TC_CUDA(cudaSetDevice(ctx->device));
     dreads d;
-    int need = (host->qual ? NEED_QUAL : 0) | NEED_MATE;
+    int need = host->qual ? NEED_QUAL : 0;      // the mate arrays stay on the host: no kernel reads them
     int rc = tc_resolve_reads(ctx, host, &d, need, (cudaStream_t)stream);
     if (rc) return rc;
     *dev = *host;
