@@ -80,16 +80,19 @@ __global__ void lr_split_kernel(pileup_args a, const uint32_t* __restrict__ piec
         ++pi;
         while (w & 3u) pcig[w++] = 0x10u | OP_H;            // pad to a whole vector with no-op hard clips (never read: cig_n stops before)
     };
-    for (uint32_t k = a.r.cigar_off[r]; k < a.r.cigar_off[r + 1]; ++k) {
-        const uint32_t c = a.r.cigar[k];
+    bool ok = true;
+    tc_for_each_op(a.r.cigar, a.r.cigar_off[r], a.r.cigar_off[r + 1], [&](uint32_t c) {
         const uint32_t op = c & 15u;
         int l = (int)(c >> 4);
-        if (op == OP_P || l == 0 || op > OP_X) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); return; }      // general form only
+        if (op == OP_P || l == 0 || op > OP_X) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); ok = false; return false; }      // scatter kernel only
         if (!op_consumes_ref(op)) {
-            if (!open) { open = true; px = x; py = y; pw = w; }     // leading clips / insertions open the first piece
+            // clips in front of the first aligned base are dropped (a soft clip only moves the query index): pieces
+            // never carry an over-long leading clip into the kernel's 16-bit op staging
+            if (!open && (op == OP_H || op == OP_S)) { if (op == OP_S) y += l; return true; }
+            if (!open) { open = true; px = x; py = y; pw = w; }     // a leading insertion opens the first piece
             pcig[w++] = c;
             if (op == OP_I || op == OP_S) y += l;
-            continue;
+            return true;
         }
         const bool match = op_is_match(op);
         while (l > 0) {
@@ -104,7 +107,9 @@ __global__ void lr_split_kernel(pileup_args a, const uint32_t* __restrict__ piec
             x += take; l -= take;
             if (match) y += take;
         }
-    }
+        return true;
+    });
+    if (!ok) return;
     if (open && has_ref) close_piece();
 }
 
