@@ -130,6 +130,62 @@ def test_pileup_ops_longer_than_16_bits(ctx, orc):
     assert np.array_equal(ctx.pileup_counts(b2, L, gpu.buildindex_params(0)), exp2)
 
 
+@pytest.mark.parametrize("span,seed", [(390, 1), (390, 2), (200, 3), (880, 4), (880, 5)])
+def test_pileup_phase_boundaries_fuzz(ctx, orc, span, seed):
+    """Variant 3 walks a window in phases of 256 columns.  Reads that all start within a few columns of each other
+    (one window) with random CIGARs — match ops, deletions and reference skips that end on, start on or straddle
+    the phase borders, insertions and clips anywhere — must give the oracle's table, without falling back."""
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    rng = np.random.default_rng(1000 + seed)
+    L = 3000
+    base = 1000                      # the window starts here: phase borders at base + 256, + 512, + 768
+    recs = []
+    for i in range(1500):
+        pos = base + int(rng.integers(0, 24))
+        x, ops, qlen = pos, [], 0
+        if rng.random() < 0.2:
+            l = int(rng.integers(1, 12)); ops.append(("S", l)); qlen += l
+        target = pos + span + int(rng.integers(-20, 20))
+        while x < target:
+            # steer some ops to end exactly on (or one off) a phase border
+            border = base + 256 * (1 + (x - base) // 256)
+            l = int(rng.integers(1, 60))
+            if rng.random() < 0.35 and border - x < 80:
+                l = border - x + int(rng.integers(-1, 2))
+            l = max(1, min(l, target - x + 2))
+            ops.append(("M", l)); x += l; qlen += l
+            u = rng.random()
+            if u < 0.35:
+                l = int(rng.integers(1, 4)); ops.append(("I", l)); qlen += l
+            elif u < 0.7:
+                l = int(rng.integers(1, 30)) if rng.random() < 0.2 and x + 30 < target else int(rng.integers(1, 3)); ops.append(("D", l)); x += l
+            elif u < 0.75 and x + 40 < target:
+                l = int(rng.integers(1, 40)); ops.append(("N", l)); x += l
+            elif u < 0.8:
+                li, ld = int(rng.integers(1, 3)), int(rng.integers(1, 3))
+                ops += [("D", ld), ("I", li)] if rng.random() < 0.5 else [("I", li), ("D", ld)]
+                x += ld; qlen += li
+        if ops[-1][0] != "M":
+            ops.append(("M", 3)); qlen += 3
+        if rng.random() < 0.2:
+            l = int(rng.integers(1, 12)); ops.append(("S", l)); qlen += l
+        # merge equal neighbours (M M after a dropped op cannot happen here, but keep the CIGAR canonical)
+        cig = "".join(f"{l}{o}" for o, l in ops)
+        seq = "".join("ACGTN"[j] for j in rng.choice(5, qlen, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        recs.append(dict(pos=pos, cigar=cig, seq=seq, flag=16 if rng.random() < 0.5 else 0))
+    recs.sort(key=lambda r: r["pos"])
+    b = ReadBatch.from_records(recs)
+    exp = pileup.pileup_counts(b, L, threads=4)
+    got = ctx.pileup_counts(b, L, gpu.buildindex_params(3))
+    assert np.array_equal(got, exp)
+    b.max_ref_span = int(max(sum(int(l) for l, o in __import__("re").findall(r"(\d+)([MDN])", r["cigar"])) for r in recs))
+    got2 = ctx.pileup_counts(b, L, gpu.buildindex_params(3))
+    assert np.array_equal(got2, exp)
+
+
 SYNTH_CASES = {
     "shotgun_indels": dict(n_reads=6000, read_len=120, read_len_jitter=30, indel_rate=0.03, indel_maxlen=3, softclip_rate=0.2,
                            softclip_max=12, n_rate=0.01, iupac_rate=0.01, refskip_rate=0.05, special_flag_rate=0.05, sub_rate=0.02),
