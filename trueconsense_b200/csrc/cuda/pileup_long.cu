@@ -53,17 +53,22 @@ __global__ void lr_count_kernel(pileup_args a, uint32_t* __restrict__ n_pieces, 
     n_ops[r] = (no + 3u) & ~3u;
 }
 
-__global__ void lr_split_kernel(pileup_args a, const uint32_t* __restrict__ piece_base, const uint32_t* __restrict__ ops_base,
+// One thread per read walks its CIGAR, but the ops come through shared memory: per round the warp loads the next 32
+// ops of each of its 32 reads with one coalesced 128-byte request per read (all 32 in flight together), then every lane
+// consumes its own read's 32 ops.  (A thread streaming its own 2.4 KB of ops from HBM alone took 485 us on config 5.)
+constexpr int LR_SPLIT_THREADS = 128;
+__global__ void __launch_bounds__(LR_SPLIT_THREADS) lr_split_kernel(pileup_args a, const uint32_t* __restrict__ piece_base, const uint32_t* __restrict__ ops_base,
                                 tc_piece* __restrict__ pieces, uint32_t* __restrict__ pcig, int32_t* __restrict__ piece_pos) {
+    __shared__ uint32_t stage[LR_SPLIT_THREADS / 32][32][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.r.n) return;
-    if (piece_base[r + 1] == piece_base[r]) return;
-    const int lq = a.r.l_seq[r];
-    if (lq == 0) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); return; }        // SEQ '*': general form only
-    const uint32_t sbeg = a.r.seq_off[r];
-    uint32_t pi = piece_base[r];            // next piece record
-    uint32_t w = ops_base[r];               // next op slot (multiple of 4)
-    int x = a.r.pos[r], y = 0;
+    bool valid = r < a.r.n && piece_base[r + 1] != piece_base[r];
+    const int lq = valid ? a.r.l_seq[r] : 0;
+    if (valid && lq == 0) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); valid = false; }        // SEQ '*': scatter kernel only
+    const uint32_t sbeg = valid ? a.r.seq_off[r] : 0u;
+    uint32_t pi = valid ? piece_base[r] : 0u;            // next piece record
+    uint32_t w = valid ? ops_base[r] : 0u;               // next op slot (multiple of 4)
+    int x = valid ? a.r.pos[r] : 0, y = 0;
     int cell_end = (x / PIECE_COLS + 1) * PIECE_COLS;
     // the open piece
     int px = x, py = 0;
@@ -80,37 +85,48 @@ __global__ void lr_split_kernel(pileup_args a, const uint32_t* __restrict__ piec
         ++pi;
         while (w & 3u) pcig[w++] = 0x10u | OP_H;            // pad to a whole vector with no-op hard clips (never read: cig_n stops before)
     };
-    bool ok = true;
-    tc_for_each_op(a.r.cigar, a.r.cigar_off[r], a.r.cigar_off[r + 1], [&](uint32_t c) {
-        const uint32_t op = c & 15u;
-        int l = (int)(c >> 4);
-        if (op == OP_P || l == 0 || op > OP_X) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); ok = false; return false; }      // scatter kernel only
-        if (!op_consumes_ref(op)) {
-            // clips in front of the first aligned base are dropped (a soft clip only moves the query index): pieces
-            // never carry an over-long leading clip into the kernel's 16-bit op staging
-            if (!open && (op == OP_H || op == OP_S)) { if (op == OP_S) y += l; return true; }
-            if (!open) { open = true; px = x; py = y; pw = w; }     // a leading insertion opens the first piece
-            pcig[w++] = c;
-            if (op == OP_I || op == OP_S) y += l;
-            return true;
+    uint32_t k = valid ? a.r.cigar_off[r] : 0u;
+    uint32_t k1 = valid ? a.r.cigar_off[r + 1] : 0u;
+    while (__any_sync(0xffffffffu, k < k1)) {
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t ki = __shfl_sync(0xffffffffu, k, i), k1i = __shfl_sync(0xffffffffu, k1, i);
+            if (ki + lane < k1i) stage[wib][i][lane] = __ldg(a.r.cigar + ki + lane);
         }
-        const bool match = op_is_match(op);
-        while (l > 0) {
-            if (x == cell_end) {            // the next column belongs to the next cell: cut here
-                if (open && has_ref) { close_piece(); open = false; has_ref = false; }
-                cell_end += PIECE_COLS;
+        __syncwarp();
+        const int nb = (int)min(32u, k1 - k);
+        for (int t = 0; t < nb; ++t) {
+            const uint32_t c = stage[wib][lane][t];
+            const uint32_t op = c & 15u;
+            int l = (int)(c >> 4);
+            if (op == OP_P || l == 0 || op > OP_X) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); k1 = k; valid = false; break; }      // scatter kernel only
+            if (!op_consumes_ref(op)) {
+                // clips in front of the first aligned base are dropped (a soft clip only moves the query index): pieces
+                // never carry an over-long leading clip into the kernel's 16-bit op staging
+                if (!open && (op == OP_H || op == OP_S)) { if (op == OP_S) y += l; continue; }
+                if (!open) { open = true; px = x; py = y; pw = w; }     // a leading insertion opens the first piece
+                pcig[w++] = c;
+                if (op == OP_I || op == OP_S) y += l;
+                continue;
             }
-            if (!open) { open = true; px = x; py = y; pw = w; }
-            const int take = min(l, cell_end - x);
-            pcig[w++] = ((uint32_t)take << 4) | op;
-            has_ref = true;
-            x += take; l -= take;
-            if (match) y += take;
+            const bool match = op_is_match(op);
+            while (l > 0) {
+                if (x == cell_end) {            // the next column belongs to the next cell: cut here
+                    if (open && has_ref) { close_piece(); open = false; has_ref = false; }
+                    cell_end += PIECE_COLS;
+                }
+                if (!open) { open = true; px = x; py = y; pw = w; }
+                const int take = min(l, cell_end - x);
+                pcig[w++] = ((uint32_t)take << 4) | op;
+                has_ref = true;
+                x += take; l -= take;
+                if (match) y += take;
+            }
         }
-        return true;
-    });
-    if (!ok) return;
-    if (open && has_ref) close_piece();
+        if (valid) k += (uint32_t)nb;
+        __syncwarp();
+    }
+    if (valid && open && has_ref) close_piece();
 }
 
 __global__ void lr_iota_kernel(uint32_t* __restrict__ idx, int64_t n) {
@@ -153,7 +169,7 @@ int tc_pileup_long_launch(tc_ctx* ctx, const pileup_args& a0, cudaStream_t s) {
     uint32_t* idx_in = (uint32_t*)(key_out + NP); uint32_t* idx_out = idx_in + NP;
     uint32_t* pcig = idx_out + NP;
     pcig = (uint32_t*)(((uintptr_t)pcig + 15) & ~(uintptr_t)15);
-    lr_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, piece_base, ops_base, pieces, pcig, key_in);
+    lr_split_kernel<<<(unsigned)((n + LR_SPLIT_THREADS - 1) / LR_SPLIT_THREADS), LR_SPLIT_THREADS, 0, s>>>(a, piece_base, ops_base, pieces, pcig, key_in);
     TC_LAUNCH_CHECK();
     lr_iota_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(idx_in, (int64_t)NP);
     TC_LAUNCH_CHECK();

@@ -101,27 +101,6 @@ __device__ __forceinline__ bool op_consumes_ref(uint32_t op) {
 __device__ __forceinline__ bool op_is_match(uint32_t op) { return (0x181u >> op) & 1u; }          // M, =, X
 __device__ __forceinline__ bool op_consumes_query_skip(uint32_t op) { return op == OP_I || op == OP_S; }
 
-// The CIGAR ops [k0, k1) of one read, in order, for a thread that walks them alone and does real work per op (the
-// long-read split: 485 -> 407 us on config 5): 16-byte loads once k is aligned, the next vector requested before the
-// current one is consumed.  (The plain span sums got slower with it, 65 -> 90 us, and keep their scalar loops.)
-// f(op_word) returns false to stop.
-template <class F>
-__device__ __forceinline__ void tc_for_each_op(const uint32_t* __restrict__ cig, uint32_t k0, uint32_t k1, F f) {
-    uint32_t k = k0;
-    const bool vec = ((uintptr_t)cig & 15u) == 0;
-    while (k < k1 && (!vec || (k & 3u))) { if (!f(__ldg(cig + k))) return; ++k; }
-    if (k + 4 <= k1) {
-        uint4 nxt = __ldg(reinterpret_cast<const uint4*>(cig + k));
-        while (k + 4 <= k1) {
-            const uint4 cur = nxt;
-            if (k + 8 <= k1) nxt = __ldg(reinterpret_cast<const uint4*>(cig + k + 4));
-            if (!f(cur.x) || !f(cur.y) || !f(cur.z) || !f(cur.w)) return;
-            k += 4;
-        }
-    }
-    while (k < k1) { if (!f(__ldg(cig + k))) return; ++k; }
-}
-
 // 4-bit base code q of a read whose packed words start at w (BAM byte stream inside the words)
 __device__ __forceinline__ uint32_t seq_code(const uint32_t* __restrict__ w, int q) {
     uint32_t word = __ldg(w + (q >> 3));
