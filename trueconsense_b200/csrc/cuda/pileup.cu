@@ -190,6 +190,7 @@ static int coverage_scan(tc_ctx* ctx, const int32_t* d_diff, int32_t* d_cov, int
 __global__ void depth_diff_kernel(pileup_args a) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.r.n) return;
+    if (a.span_out) a.span_out[r] = -1;
     if (r > 0 && a.r.pos[r] < a.r.pos[r - 1]) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
     if (!read_passes(a, r)) return;
     int start = a.r.pos[r];
@@ -199,12 +200,44 @@ __global__ void depth_diff_kernel(pileup_args a) {
         uint32_t c = a.r.cigar[k];
         if (op_consumes_ref(c & 15u)) span += (int)(c >> 4);
     }
+    if (a.span_out) a.span_out[r] = span;
     if (start + span > a.L) { atomicCAS(&a.status->err, 0, TC_ERR_RANGE); return; }
     if (span > 0) { atomicAdd(&a.diff[start], 1); atomicAdd(&a.diff[start + span], -1); }
     else atomicAdd(&a.status->n_zero_span, 1);
     atomicMax(&a.status->max_span, span);
 }
 
+
+// the same for long CIGARs (hundreds of ops per read): one warp per read, coalesced loads, a warp sum
+__global__ void depth_diff_warp_kernel(pileup_args a) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.r.n) return;
+    const bool passes = read_passes(a, r);
+    const int start = a.r.pos[r];
+    const bool inside = start >= 0 && start < a.L;
+    int span = 0;
+    if (passes && inside)
+        for (uint32_t k = a.r.cigar_off[r] + lane; k < a.r.cigar_off[r + 1]; k += 32) {
+            const uint32_t c = __ldg(a.r.cigar + k);
+            if (op_consumes_ref(c & 15u)) span += (int)(c >> 4);
+        }
+    span = __reduce_add_sync(0xffffffffu, span);
+    if (lane != 0) return;
+    if (a.span_out) a.span_out[r] = (passes && inside) ? span : -1;
+    if (r > 0 && start < a.r.pos[r - 1]) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
+    if (!passes) return;
+    if (!inside) { atomicCAS(&a.status->err, 0, TC_ERR_RANGE); return; }
+    if (start + span > a.L) { atomicCAS(&a.status->err, 0, TC_ERR_RANGE); return; }
+    if (span > 0) { atomicAdd(&a.diff[start], 1); atomicAdd(&a.diff[start + span], -1); }
+    else atomicAdd(&a.status->n_zero_span, 1);
+    atomicMax(&a.status->max_span, span);
+}
+
+static void launch_depth_diff(const pileup_args& a, int64_t n_cigar_ops, cudaStream_t s) {
+    if (n_cigar_ops > 64 * a.r.n) depth_diff_warp_kernel<<<(unsigned)((a.r.n * 32 + 255) / 256), 256, 0, s>>>(a);
+    else depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
+}
 
 static int fetch_status(tc_ctx* ctx, tc_status* d_status, tc_status* out, cudaStream_t s) {
     TC_D2H(ctx->host_status, d_status, sizeof(tc_status), s);
@@ -257,6 +290,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality;
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
     a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
+    a.span_out = nullptr;
     const bool per_entry = p->min_base_quality > 0;
     int variant = p->kernel;
     // reads longer than variant 3's widest window are cut into pieces first (variant 4, pileup_long.cu)
@@ -272,7 +306,11 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
             // caller bounded the longest span, then variant 3 does all of that while it walks the CIGARs anyway
             if (variant != 3 || a.span_hint == 0 || a.span_hint > LONG_SPAN) {
                 a.span_hint = 0;
-                depth_diff_kernel<<<(unsigned)((a.r.n + 255) / 256), 256, 0, s>>>(a);
+                if (variant == 4) {         // the long-read split needs every read's span: one walk over the CIGARs serves both
+                    a.span_out = (int32_t*)tc_dev_buf(ctx, SLOT_SPAN_END, sizeof(int32_t) * (size_t)a.r.n);
+                    if (!a.span_out) return TC_ERR_NOMEM;
+                }
+                launch_depth_diff(a, reads->n_cigar_ops, s);
                 TC_LAUNCH_CHECK();
             }
             a.pieces = nullptr; a.piece_order = nullptr; a.n_pieces = 0;
@@ -358,9 +396,9 @@ TC_API int tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, con
     TC_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(int32_t) * ((size_t)L + 1), s));
     TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = 0; a.ignore_orphans = p->ignore_orphans;
-    a.counts = nullptr; a.diff = d_diff; a.status = d_status; a.span_hint = 0;
+    a.counts = nullptr; a.diff = d_diff; a.status = d_status; a.span_hint = 0; a.span_out = nullptr;
     if (d.n > 0) {
-        depth_diff_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, s>>>(a);
+        launch_depth_diff(a, reads->n_cigar_ops, s);
         TC_LAUNCH_CHECK();
     }
     rc = coverage_scan(ctx, d_diff, d_depth, L, d_status, nullptr, s);

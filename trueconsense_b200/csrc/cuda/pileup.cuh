@@ -25,6 +25,7 @@ struct pileup_args {
     int32_t* diff;          // [L+1]
     tc_status* status;
     int32_t span_hint;      // tc_reads_t.max_ref_span (0 = unknown: a span pass finds it)
+    int32_t* span_out;      // [n] optional: the span pass leaves every read's reference span here (-1: filtered / out of range)
     // PIECES mode of variant 3 (long reads): pieces in order of start column; r.cigar is then the piece-CIGAR buffer
     unsigned long long* xi; // [L] variant 3: packed X (low 32 bits) | I (high 32 bits) event counters per column
     const tc_piece* pieces;
