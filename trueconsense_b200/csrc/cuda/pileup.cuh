@@ -14,7 +14,10 @@ struct tc_piece {
     int32_t y0;             // query index of the piece's first base, relative to seq_beg's first nibble (0..7)
     int32_t pad;
 };
-constexpr int PIECE_COLS = 256;
+#ifndef TC_PIECE_COLS
+#define TC_PIECE_COLS 400
+#endif
+constexpr int PIECE_COLS = TC_PIECE_COLS;         // a multiple of 8, at most 440 (the 512-column window minus its slack)
 
 struct pileup_args {
     dreads r;
