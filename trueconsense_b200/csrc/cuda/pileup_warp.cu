@@ -347,28 +347,51 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             const uint32_t cdst = cig_s + 8u * (uint32_t)(c_inc - cv);
             if (lane < n) {
                 const int64_t sb = (int64_t)(so & ~3u);
-                for (int v = 0; v < sv; ++v) {
-                    uint4 q;
-                    if (sb + 4 * v + 4 <= n_seq_words) q = __ldg(reinterpret_cast<const uint4*>(a.r.seq4 + sb) + v);
-                    else {              // the last words of the batch: do not read past the array
-                        q.x = sb + 4 * v + 0 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 0) : 0u;
-                        q.y = sb + 4 * v + 1 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 1) : 0u;
-                        q.z = sb + 4 * v + 2 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 2) : 0u;
-                        q.w = sb + 4 * v + 3 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 3) : 0u;
+                // a piece's words and ops are a gather (the pieces of a sub-tile come from 32 different reads): the loads
+                // go out four at a time before any of them is consumed — one at a time, their latencies were half of
+                // this kernel's stall samples
+                constexpr int SB = 4;           // loads in flight per lane (8 spill)
+                const bool whole = sb + 4ll * sv <= n_seq_words;        // (the last words of the batch: do not read past the array)
+                for (int v0 = 0; v0 < sv; v0 += SB) {
+                    uint4 q[SB];
+#pragma unroll
+                    for (int u = 0; u < SB; ++u) {
+                        const int v = v0 + u;
+                        if (v < sv) {
+                            if (whole) q[u] = __ldg(reinterpret_cast<const uint4*>(a.r.seq4 + sb) + v);
+                            else {
+                                q[u].x = sb + 4 * v + 0 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 0) : 0u;
+                                q[u].y = sb + 4 * v + 1 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 1) : 0u;
+                                q[u].z = sb + 4 * v + 2 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 2) : 0u;
+                                q[u].w = sb + 4 * v + 3 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 3) : 0u;
+                            }
+                        }
                     }
-                    if (multibit(q.x) | multibit(q.y) | multibit(q.z) | multibit(q.w)) {
-                        q.x = clear_multibit(q.x); q.y = clear_multibit(q.y); q.z = clear_multibit(q.z); q.w = clear_multibit(q.w);
+#pragma unroll
+                    for (int u = 0; u < SB; ++u) {
+                        const int v = v0 + u;
+                        if (v < sv) {
+                            if (multibit(q[u].x) | multibit(q[u].y) | multibit(q[u].z) | multibit(q[u].w)) {
+                                q[u].x = clear_multibit(q[u].x); q[u].y = clear_multibit(q[u].y); q[u].z = clear_multibit(q[u].z); q[u].w = clear_multibit(q[u].w);
+                            }
+                            q[u].x = __byte_perm(q[u].x, 0, 0x0123); q[u].y = __byte_perm(q[u].y, 0, 0x0123);
+                            q[u].z = __byte_perm(q[u].z, 0, 0x0123); q[u].w = __byte_perm(q[u].w, 0, 0x0123);
+                            sts4(sdst + 16 * v, q[u]);
+                        }
                     }
-                    q.x = __byte_perm(q.x, 0, 0x0123); q.y = __byte_perm(q.y, 0, 0x0123);
-                    q.z = __byte_perm(q.z, 0, 0x0123); q.w = __byte_perm(q.w, 0, 0x0123);
-                    sts4(sdst + 16 * v, q);
                 }
                 // the piece-CIGAR buffer is padded to whole vectors behind its last op
                 const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + (co & ~3u));
-                for (int v = 0; v < cv; ++v) {
-                    const uint4 q = __ldg(csrc + v);
-                    big |= q.x | q.y | q.z | q.w;
-                    sts2(cdst + 8 * v, pack_ops(q.x, q.y), pack_ops(q.z, q.w));
+                for (int v0 = 0; v0 < cv; v0 += 4) {
+                    uint4 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (v0 + u < cv) q[u] = __ldg(csrc + v0 + u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (v0 + u < cv) {
+                            big |= q[u].x | q[u].y | q[u].z | q[u].w;
+                            sts2(cdst + 8 * (v0 + u), pack_ops(q[u].x, q[u].y), pack_ops(q[u].z, q[u].w));
+                        }
                 }
             }
             __syncwarp();
