@@ -64,6 +64,9 @@ constexpr int CHUNK_WORDS = TC_CHUNK_WORDS;     // row words per emitted chunk o
 #ifndef TC_SEQ_PER_WC
 #define TC_SEQ_PER_WC 26
 #endif
+#ifndef TC_STAGE_UNROLL
+#define TC_STAGE_UNROLL 4
+#endif
 #ifndef TC_PHASE_WORDS
 #define TC_PHASE_WORDS 32                       // 32: 256-column phases; 0: one phase (rows as wide as the window)
 #endif
@@ -480,12 +483,13 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
                     const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
                     int t = 0;
-                    for (int i = lane; i < nv; i += 128, t += 4) {
-                        uint4 v[4];
+                    constexpr int SU = TC_STAGE_UNROLL;     // vectors in flight per lane
+                    for (int i = lane; i < nv; i += 32 * SU, t += SU) {
+                        uint4 v[SU];
     #pragma unroll
-                        for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
+                        for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
     #pragma unroll
-                        for (int u = 0; u < 4; ++u) if (i + 32 * u < nv) {
+                        for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) {
                             const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
                             dirty |= (z != 0 ? 1u : 0u) << (t + u);
                             v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
