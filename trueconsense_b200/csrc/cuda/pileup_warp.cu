@@ -64,6 +64,9 @@ constexpr int CHUNK_WORDS = TC_CHUNK_WORDS;     // row words per emitted chunk o
 #ifndef TC_SEQ_PER_WC
 #define TC_SEQ_PER_WC 26
 #endif
+#ifndef TC_TMA_STAGING
+#define TC_TMA_STAGING 1                        // 1: sub-tiles are staged with cp.async.bulk (TMA), 0: with LDG.128 + STS
+#endif
 #ifndef TC_STAGE_UNROLL
 #define TC_STAGE_UNROLL 4
 #endif
@@ -87,7 +90,10 @@ template <int WC> struct geom {
     static constexpr int SEQ_WORDS = SEQ_PAD + SEQ_CAP + 8;
     static constexpr int CIG_WORDS = CIG_CAP / 2 + 4;
     static constexpr int WARP_WORDS = 32 * RS + SEQ_WORDS + CIG_WORDS;
-    static constexpr int WARPS = (227 * 1024 / 4) / WARP_WORDS > TC_MAX_WARPS ? TC_MAX_WARPS : (227 * 1024 / 4) / WARP_WORDS;
+    // + 2 words per warp: its mbarrier (TMA staging)
+    static constexpr int WARPS = (227 * 1024 / 4) / (WARP_WORDS + 2) > TC_MAX_WARPS ? TC_MAX_WARPS : (227 * 1024 / 4) / (WARP_WORDS + 2);
+    // the raw CIGAR ops of a sub-tile land in the rows (idle while staging) before they are packed to 16 bits
+    static constexpr bool TMA = TC_TMA_STAGING && (CIG_CAP + 4 <= 32 * RS);
 };
 
 __device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
@@ -134,6 +140,26 @@ __device__ __forceinline__ uint32_t pack_ops(uint32_t c0, uint32_t c1) { return 
 __device__ __forceinline__ uint32_t op_exotic_min(uint32_t c) { return min((c & 15u) ^ 6u, c >> 4); }
 constexpr uint32_t OP_BIG = 1u << 16;           // an op of 4096+ bases does not fit 16 bits
 constexpr uint32_t S_SATURATED = (4095u << 4) | OP_S;
+
+// ---- TMA (cp.async.bulk) staging: one lane asks for the sub-tile's SEQ words and CIGAR ops as two bulk copies that
+// complete on the warp's mbarrier; nothing is held in registers while they are in flight
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "TC_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra TC_MBAR_DONE;\n\t"
+        "bra TC_MBAR_WAIT;\n\t"
+        "TC_MBAR_DONE:\n\t"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
 
 // A lane's walk over its read, resumable between phases.
 struct lane_walk {
@@ -250,6 +276,10 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     const uint32_t cig_s = seq_s + 4u * G::SEQ_WORDS;
     for (int i = lane; i < 32 * RS; i += 32) sts(rows + 4 * i, 0u);
     if (lane < G::SEQ_PAD) sts(seq_s + 4 * lane, 0u);
+    // the warp's mbarrier sits behind all slices
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem) + 4u * G::WARPS * G::WARP_WORDS + 8u * (threadIdx.x >> 5);
+    uint32_t tma_parity = 0;
+    if (G::TMA && !PIECES && lane == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
 
     const int64_t n_reads = PIECES ? a.n_pieces : a.r.n;
@@ -462,6 +492,23 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 const int nv = (int)((send - sbase_al + 3) >> 2);
                 const uint32_t cend = __shfl_sync(FULL, co_next, n - 1);
                 const int ncv = (int)((cend - cbase_al + 3) >> 2);
+                uint32_t dirty = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
+                const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
+                uint32_t exmin = 1u;         // pads and zero-length ops: min over the ops of min((op ^ P), len) is 0 exactly when one is present
+                // TMA staging: the two contiguous ranges are requested as bulk copies (SEQ to its place, the raw CIGAR ops
+                // into the rows, which are idle and all zero here) — every byte of the sub-tile is in flight at once and no
+                // register holds any of it.  (The last sub-tile of a batch, whose vectors may reach past the arrays, and
+                // the 1024-column geometry, whose ops do not fit the rows, take the LDG path below.)
+                const bool use_tma = G::TMA && (int64_t)sbase_al + 4ll * nv <= n_seq_words && (int64_t)cbase_al + 4ll * ncv <= n_ops_total;
+                if (use_tma) {
+                    fence_proxy_async();        // the warp's earlier accesses to these buffers come before the copies' writes
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(mbar, 16u * (uint32_t)(nv + ncv));
+                        tma_bulk_g2s(sdst, a.r.seq4 + sbase_al, 16u * (uint32_t)nv, mbar);
+                        if (ncv > 0) tma_bulk_g2s(rows, a.r.cigar + cbase_al, 16u * (uint32_t)ncv, mbar);
+                    }
+                }
                 // the next sub-tile starts where this one ends and is about as large: pull its lines (and the
                 // metadata lines two sub-tiles ahead) towards L2 while this one is being processed
                 {
@@ -478,62 +525,82 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                         if (lane == 4) prefetch_l2(a.r.flag + rm);
                     }
                 }
-                uint32_t dirty = 0;          // dirty: bit t <=> the lane's t-th vector holds a code that is not one-hot
-                const uint32_t sdst = seq_s + 4u * G::SEQ_PAD;
-                if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
-                    int t = 0;
-                    constexpr int SU = TC_STAGE_UNROLL;     // vectors in flight per lane
-                    for (int i = lane; i < nv; i += 32 * SU, t += SU) {
-                        uint4 v[SU];
-    #pragma unroll
-                        for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
-    #pragma unroll
-                        for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) {
-                            const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
-                            dirty |= (z != 0 ? 1u : 0u) << (t + u);
-                            v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
-                            v[u].z = __byte_perm(v[u].z, 0, 0x0123); v[u].w = __byte_perm(v[u].w, 0, 0x0123);
-                            sts4(sdst + 16 * (i + 32 * u), v[u]);
+                if (use_tma) {
+                    mbar_wait(mbar, tma_parity);
+                    tma_parity ^= 1u;
+                    // SEQ in place: one-hot check (codes that are not are cleared at once: rare), first base to the top nibble
+                    for (int i = lane; i < nv; i += 32) {
+                        uint4 v = lds4(sdst + 16 * i);
+                        if (multibit(v.x) | multibit(v.y) | multibit(v.z) | multibit(v.w)) {
+                            v.x = clear_multibit(v.x); v.y = clear_multibit(v.y); v.z = clear_multibit(v.z); v.w = clear_multibit(v.w);
                         }
+                        v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+                        v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+                        sts4(sdst + 16 * i, v);
                     }
-                } else {            // the last sub-tile of the batch: do not read past the array
-                    int t = 0;
-                    for (int i = lane; i < nv; i += 32, ++t) {
-                        uint32_t w[4];
-    #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int64_t wi = (int64_t)sbase_al + 4 * i + u;
-                            w[u] = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
-                        }
-                        const uint32_t z = multibit(w[0]) | multibit(w[1]) | multibit(w[2]) | multibit(w[3]);
-                        dirty |= (z != 0 ? 1u : 0u) << t;
-    #pragma unroll
-                        for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
-                    }
-                }
-                // CIGAR ops, packed to 16 bits.  Pads and zero-length ops: min over the ops of min((op ^ P), len) is 0
-                // exactly when one is present
-                uint32_t exmin = 1u;
-                if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
-                    const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
-                    for (int i = lane; i < ncv; i += 64) {
-                        uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
-                        const bool b1 = i + 32 < ncv;
-                        if (b1) v1 = __ldg(csrc + i + 32);
+                    // CIGAR ops: rows -> 16 bits each in their place; the rows are cleared again
+                    for (int i = lane; i < ncv; i += 32) {
+                        const uint4 v0 = lds4(rows + 16 * i);
                         exmin = min(exmin, min(min(op_exotic_min(v0.x), op_exotic_min(v0.y)), min(op_exotic_min(v0.z), op_exotic_min(v0.w))));
-                        exmin = min(exmin, min(min(op_exotic_min(v1.x), op_exotic_min(v1.y)), min(op_exotic_min(v1.z), op_exotic_min(v1.w))));
-                        big |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                        big |= v0.x | v0.y | v0.z | v0.w;
                         sts2(cig_s + 8 * i, pack_ops(v0.x, v0.y), pack_ops(v0.z, v0.w));
-                        if (b1) sts2(cig_s + 8 * (i + 32), pack_ops(v1.x, v1.y), pack_ops(v1.z, v1.w));
+                        sts4(rows + 16 * i, make_uint4(0u, 0u, 0u, 0u));
                     }
                 } else {
-                    for (int i = lane; i < 4 * ncv; i += 32) {
-                        const int64_t oi = (int64_t)cbase_al + i;
-                        const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
-                        exmin = min(exmin, op_exotic_min(c));
-                        big |= c;
-                        sts16(cig_s + 2 * i, c);
+                    if ((int64_t)sbase_al + 4ll * nv <= n_seq_words) {
+                        const uint4* src = reinterpret_cast<const uint4*>(a.r.seq4 + sbase_al);
+                        int t = 0;
+                        constexpr int SU = TC_STAGE_UNROLL;     // vectors in flight per lane
+                        for (int i = lane; i < nv; i += 32 * SU, t += SU) {
+                            uint4 v[SU];
+        #pragma unroll
+                            for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) v[u] = __ldg(src + i + 32 * u);
+        #pragma unroll
+                            for (int u = 0; u < SU; ++u) if (i + 32 * u < nv) {
+                                const uint32_t z = multibit(v[u].x) | multibit(v[u].y) | multibit(v[u].z) | multibit(v[u].w);
+                                dirty |= (z != 0 ? 1u : 0u) << (t + u);
+                                v[u].x = __byte_perm(v[u].x, 0, 0x0123); v[u].y = __byte_perm(v[u].y, 0, 0x0123);
+                                v[u].z = __byte_perm(v[u].z, 0, 0x0123); v[u].w = __byte_perm(v[u].w, 0, 0x0123);
+                                sts4(sdst + 16 * (i + 32 * u), v[u]);
+                            }
+                        }
+                    } else {            // the last sub-tile of the batch: do not read past the array
+                        int t = 0;
+                        for (int i = lane; i < nv; i += 32, ++t) {
+                            uint32_t w[4];
+        #pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int64_t wi = (int64_t)sbase_al + 4 * i + u;
+                                w[u] = wi < n_seq_words ? __ldg(a.r.seq4 + wi) : 0u;
+                            }
+                            const uint32_t z = multibit(w[0]) | multibit(w[1]) | multibit(w[2]) | multibit(w[3]);
+                            dirty |= (z != 0 ? 1u : 0u) << t;
+        #pragma unroll
+                            for (int u = 0; u < 4; ++u) sts(sdst + 16 * i + 4 * u, __byte_perm(w[u], 0, 0x0123));
+                        }
+                    }
+                    // CIGAR ops, packed to 16 bits.  Pads and zero-length ops: min over the ops of min((op ^ P), len) is 0
+                    // exactly when one is present
+                    if ((int64_t)cbase_al + 4ll * ncv <= n_ops_total) {
+                        const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + cbase_al);
+                        for (int i = lane; i < ncv; i += 64) {
+                            uint4 v0 = __ldg(csrc + i), v1 = make_uint4(16u, 16u, 16u, 16u);
+                            const bool b1 = i + 32 < ncv;
+                            if (b1) v1 = __ldg(csrc + i + 32);
+                            exmin = min(exmin, min(min(op_exotic_min(v0.x), op_exotic_min(v0.y)), min(op_exotic_min(v0.z), op_exotic_min(v0.w))));
+                            exmin = min(exmin, min(min(op_exotic_min(v1.x), op_exotic_min(v1.y)), min(op_exotic_min(v1.z), op_exotic_min(v1.w))));
+                            big |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                            sts2(cig_s + 8 * i, pack_ops(v0.x, v0.y), pack_ops(v0.z, v0.w));
+                            if (b1) sts2(cig_s + 8 * (i + 32), pack_ops(v1.x, v1.y), pack_ops(v1.z, v1.w));
+                        }
+                    } else {
+                        for (int i = lane; i < 4 * ncv; i += 32) {
+                            const int64_t oi = (int64_t)cbase_al + i;
+                            const uint32_t c = oi < n_ops_total ? __ldg(a.r.cigar + oi) : 16u;
+                            exmin = min(exmin, op_exotic_min(c));
+                            big |= c;
+                            sts16(cig_s + 2 * i, c);
+                        }
                     }
                 }
                 declined = exmin == 0u;
@@ -681,7 +748,7 @@ bool tc_pileup_warp_supported(const pileup_args& a) {
 template <int WC, bool PIECES>
 static int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
     using G = geom<WC>;
-    const size_t smem = sizeof(uint32_t) * (size_t)G::WARP_WORDS * G::WARPS;
+    const size_t smem = sizeof(uint32_t) * (size_t)(G::WARP_WORDS + 2) * G::WARPS;
     TC_CUDA(cudaFuncSetAttribute(warp_pileup_kernel<WC, PIECES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     warp_pileup_kernel<WC, PIECES><<<ctx->sm_count, G::WARPS * 32, smem, s>>>(a);
     TC_LAUNCH_CHECK();
