@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
     // the warp's mbarrier sits behind all slices
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem) + 4u * G::WARPS * G::WARP_WORDS + 8u * (threadIdx.x >> 5);
     uint32_t tma_parity = 0;
-    if (G::TMA && !PIECES && lane == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (G::TMA && lane == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
 
     const int64_t n_reads = PIECES ? a.n_pieces : a.r.n;
@@ -378,53 +378,87 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
             }
             const uint32_t sdst = seq_s + 4u * G::SEQ_PAD + 16u * (uint32_t)(s_inc - sv);
             const uint32_t cdst = cig_s + 8u * (uint32_t)(c_inc - cv);
-            if (lane < n) {
-                const int64_t sb = (int64_t)(so & ~3u);
-                // a piece's words and ops are a gather (the pieces of a sub-tile come from 32 different reads): the loads
-                // go out four at a time before any of them is consumed — one at a time, their latencies were half of
-                // this kernel's stall samples
-                constexpr int SB = 4;           // loads in flight per lane (8 spill)
-                const bool whole = sb + 4ll * sv <= n_seq_words;        // (the last words of the batch: do not read past the array)
-                for (int v0 = 0; v0 < sv; v0 += SB) {
-                    uint4 q[SB];
-#pragma unroll
-                    for (int u = 0; u < SB; ++u) {
-                        const int v = v0 + u;
-                        if (v < sv) {
-                            if (whole) q[u] = __ldg(reinterpret_cast<const uint4*>(a.r.seq4 + sb) + v);
-                            else {
-                                q[u].x = sb + 4 * v + 0 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 0) : 0u;
-                                q[u].y = sb + 4 * v + 1 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 1) : 0u;
-                                q[u].z = sb + 4 * v + 2 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 2) : 0u;
-                                q[u].w = sb + 4 * v + 3 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 3) : 0u;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < SB; ++u) {
-                        const int v = v0 + u;
-                        if (v < sv) {
-                            if (multibit(q[u].x) | multibit(q[u].y) | multibit(q[u].z) | multibit(q[u].w)) {
-                                q[u].x = clear_multibit(q[u].x); q[u].y = clear_multibit(q[u].y); q[u].z = clear_multibit(q[u].z); q[u].w = clear_multibit(q[u].w);
-                            }
-                            q[u].x = __byte_perm(q[u].x, 0, 0x0123); q[u].y = __byte_perm(q[u].y, 0, 0x0123);
-                            q[u].z = __byte_perm(q[u].z, 0, 0x0123); q[u].w = __byte_perm(q[u].w, 0, 0x0123);
-                            sts4(sdst + 16 * v, q[u]);
-                        }
-                    }
+            // TMA staging: every lane asks for its own piece's words and ops as bulk copies (SEQ to its place, the raw ops
+            // into the rows) that complete on the warp's mbarrier — the whole gather in flight at once
+            const int64_t sb_p = (int64_t)(so & ~3u);
+            const bool tma_p = G::TMA && __all_sync(FULL, lane >= n || sb_p + 4ll * sv <= n_seq_words);
+            if (tma_p) {
+                const int s_tot = __shfl_sync(FULL, s_inc, n - 1), c_tot = __shfl_sync(FULL, c_inc, n - 1);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(mbar, 16u * (uint32_t)(s_tot + c_tot));
+                __syncwarp();
+                if (lane < n) {
+                    tma_bulk_g2s(sdst, a.r.seq4 + sb_p, 16u * (uint32_t)sv, mbar);
+                    if (cv > 0) tma_bulk_g2s(rows + 16u * (uint32_t)(c_inc - cv), a.r.cigar + (co & ~3u), 16u * (uint32_t)cv, mbar);
                 }
-                // the piece-CIGAR buffer is padded to whole vectors behind its last op
-                const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + (co & ~3u));
-                for (int v0 = 0; v0 < cv; v0 += 4) {
-                    uint4 q[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (v0 + u < cv) q[u] = __ldg(csrc + v0 + u);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (v0 + u < cv) {
-                            big |= q[u].x | q[u].y | q[u].z | q[u].w;
-                            sts2(cdst + 8 * (v0 + u), pack_ops(q[u].x, q[u].y), pack_ops(q[u].z, q[u].w));
+                mbar_wait(mbar, tma_parity);
+                tma_parity ^= 1u;
+                const uint32_t sbase = seq_s + 4u * G::SEQ_PAD;
+                for (int i = lane; i < s_tot; i += 32) {
+                    uint4 v = lds4(sbase + 16 * i);
+                    if (multibit(v.x) | multibit(v.y) | multibit(v.z) | multibit(v.w)) {
+                        v.x = clear_multibit(v.x); v.y = clear_multibit(v.y); v.z = clear_multibit(v.z); v.w = clear_multibit(v.w);
+                    }
+                    v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+                    v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+                    sts4(sbase + 16 * i, v);
+                }
+                for (int i = lane; i < c_tot; i += 32) {
+                    const uint4 v0 = lds4(rows + 16 * i);
+                    big |= v0.x | v0.y | v0.z | v0.w;
+                    sts2(cig_s + 8 * i, pack_ops(v0.x, v0.y), pack_ops(v0.z, v0.w));
+                    sts4(rows + 16 * i, make_uint4(0u, 0u, 0u, 0u));
+                }
+            } else {
+                if (lane < n) {
+                    const int64_t sb = (int64_t)(so & ~3u);
+                    // a piece's words and ops are a gather (the pieces of a sub-tile come from 32 different reads): the loads
+                    // go out four at a time before any of them is consumed — one at a time, their latencies were half of
+                    // this kernel's stall samples
+                    constexpr int SB = 4;           // loads in flight per lane (8 spill)
+                    const bool whole = sb + 4ll * sv <= n_seq_words;        // (the last words of the batch: do not read past the array)
+                    for (int v0 = 0; v0 < sv; v0 += SB) {
+                        uint4 q[SB];
+    #pragma unroll
+                        for (int u = 0; u < SB; ++u) {
+                            const int v = v0 + u;
+                            if (v < sv) {
+                                if (whole) q[u] = __ldg(reinterpret_cast<const uint4*>(a.r.seq4 + sb) + v);
+                                else {
+                                    q[u].x = sb + 4 * v + 0 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 0) : 0u;
+                                    q[u].y = sb + 4 * v + 1 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 1) : 0u;
+                                    q[u].z = sb + 4 * v + 2 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 2) : 0u;
+                                    q[u].w = sb + 4 * v + 3 < n_seq_words ? __ldg(a.r.seq4 + sb + 4 * v + 3) : 0u;
+                                }
+                            }
                         }
+    #pragma unroll
+                        for (int u = 0; u < SB; ++u) {
+                            const int v = v0 + u;
+                            if (v < sv) {
+                                if (multibit(q[u].x) | multibit(q[u].y) | multibit(q[u].z) | multibit(q[u].w)) {
+                                    q[u].x = clear_multibit(q[u].x); q[u].y = clear_multibit(q[u].y); q[u].z = clear_multibit(q[u].z); q[u].w = clear_multibit(q[u].w);
+                                }
+                                q[u].x = __byte_perm(q[u].x, 0, 0x0123); q[u].y = __byte_perm(q[u].y, 0, 0x0123);
+                                q[u].z = __byte_perm(q[u].z, 0, 0x0123); q[u].w = __byte_perm(q[u].w, 0, 0x0123);
+                                sts4(sdst + 16 * v, q[u]);
+                            }
+                        }
+                    }
+                    // the piece-CIGAR buffer is padded to whole vectors behind its last op
+                    const uint4* csrc = reinterpret_cast<const uint4*>(a.r.cigar + (co & ~3u));
+                    for (int v0 = 0; v0 < cv; v0 += 4) {
+                        uint4 q[4];
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) if (v0 + u < cv) q[u] = __ldg(csrc + v0 + u);
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (v0 + u < cv) {
+                                big |= q[u].x | q[u].y | q[u].z | q[u].w;
+                                sts2(cdst + 8 * (v0 + u), pack_ops(q[u].x, q[u].y), pack_ops(q[u].z, q[u].w));
+                            }
+                    }
                 }
             }
             __syncwarp();
