@@ -116,6 +116,7 @@ extern __shared__ __align__(16) uint32_t smem[];
 // the lane-private rows, descriptor lists and counters are indexed with data-dependent offsets in every
 // inner loop, and this keeps each access at one address add + one LDS/STS/ATOMS.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
 __device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // X and I events go straight to a packed global counter per column (X count in the low, I count in the high 32
@@ -546,10 +547,13 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
                 // the next sub-tile starts where this one ends and is about as large: pull its lines (and the
                 // metadata lines two sub-tiles ahead) towards L2 while this one is being processed
                 {
-                    const int64_t s_lo = (int64_t)send - 1, s_len = (int64_t)send - sbase_al;
-                    for (int64_t o = 32 * lane; o < s_len && s_lo + o < n_seq_words; o += 1024) prefetch_l2(a.r.seq4 + s_lo + o);
-                    const int64_t c_len = (int64_t)cend - cbase_al;
-                    for (int64_t o = 32 * lane; o < c_len && (int64_t)cend + o < n_ops_total; o += 1024) prefetch_l2(a.r.cigar + cend + o);
+                    const int64_t s_lo = ((int64_t)send - 1) & ~3ll, s_len = (int64_t)send - sbase_al;
+                    const int64_t c_lo = (int64_t)cend & ~3ll, c_len = (int64_t)cend - cbase_al;
+                    if (lane == 0) {        // two bulk prefetches instead of one prefetch instruction per 128-byte line
+                        const int64_t sw = min(s_len + 4, n_seq_words - s_lo) & ~3ll, cw = min(c_len + 4, n_ops_total - c_lo) & ~3ll;
+                        if (sw > 0) prefetch_l2_bulk(a.r.seq4 + s_lo, (uint32_t)(4 * sw));
+                        if (cw > 0) prefetch_l2_bulk(a.r.cigar + c_lo, (uint32_t)(4 * cw));
+                    }
                     const int64_t rm = r + n + 64;
                     if (rm < n_reads) {
                         if (lane == 0) prefetch_l2(a.r.pos + rm);
