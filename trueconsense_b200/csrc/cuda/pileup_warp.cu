@@ -14,12 +14,13 @@
 //               (longest reference span) - 8, so every column they touch is inside the window.  When a
 //               read starts beyond it the counters are flushed to HBM (one red.add per non-zero cell)
 //               and the window moves.  Deep data flushes once per thousands of reads.
-//   stage       the packed SEQ words and CIGAR ops of the <= 32 reads are contiguous in HBM: the warp
-//               copies them to its shared-memory slice as 16-byte vectors, byte-swapping SEQ words to
-//               "first base in the top nibble" and packing CIGAR ops to 16 bits (length < 4096 inside a
-//               window); the next sub-tile's lines are prefetched to L2.  Codes that are not one-hot (N,
-//               IUPAC) are detected on the way (3 ops per word) and cleared afterwards, one dirty vector
-//               per lane and iteration.
+//   stage       the packed SEQ words and CIGAR ops of the <= 32 reads are contiguous in HBM: one lane requests the two
+//               ranges as TMA bulk copies (cp.async.bulk) that complete on the warp's mbarrier — SEQ to its place,
+//               the raw CIGAR ops into the rows, idle and all zero at that point — and the next sub-tile's ranges
+//               as two bulk L2 prefetches.  Then, in place: SEQ words byte-swapped to "first base in the top
+//               nibble", codes that are not one-hot (N, IUPAC) cleared (3 ops per word to detect), CIGAR ops packed
+//               to 16 bits (length < 4096 inside a window), the rows cleared again.  (LDG.128 + STS remains for the
+//               1024-column geometry and for a batch's last sub-tile.)
 //   emit        one lane per read, walk and expansion fused (emit_phase): lanes stay in step on
 //               chunks of match ops — the part of an M/=/X op inside CW consecutive 8-column row words —
 //               consuming the I / D / S op in front of it first (deletion columns and insertion anchors,
