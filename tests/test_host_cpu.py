@@ -265,3 +265,21 @@ def test_gff_writer_and_fasta_reader(tmp_path):
     fa = tmp_path / "r.fa"
     fa.write_text(">chr1 some description\nACGT\nacgt\n>chr2\nTTTT\n")
     assert Outputs._first_fasta_record(str(fa)) == ("chr1", list("ACGTacgt"))
+
+
+def test_bench_reference_arm_line(host_libs):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    on a tiny slice so the CPU suite stays short."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--scale", "0.005", "--ref-reads", "2000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "aligned_bases_per_sec_pileup_consensus"
+    assert line["unit"] == "aligned bases/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("cfg2")
