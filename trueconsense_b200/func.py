@@ -24,14 +24,15 @@ class MyHelpFormatter(argparse.RawTextHelpFormatter):
         return text
 
 
+def _sgr(code: int) -> str:
+    return f"\033[{code}m"
+
+
 class color:
-    PURPLE = "\033[95m"
-    CYAN = "\033[96m"
-    DARKCYAN = "\033[36m"
-    BLUE = "\033[94m"
-    GREEN = "\033[92m"
-    YELLOW = "\033[93m"
-    RED = "\033[91m"
-    BOLD = "\033[1m"
-    UNDERLINE = "\033[4m"
-    END = "\033[0m"
+    """ANSI escape sequences under the reference's attribute names (func.py:31-40): ``color.RED + text + color.END``."""
+
+
+for _name, _code in (("PURPLE", 95), ("CYAN", 96), ("DARKCYAN", 36), ("BLUE", 94), ("GREEN", 92), ("YELLOW", 93),
+                     ("RED", 91), ("BOLD", 1), ("UNDERLINE", 4), ("END", 0)):
+    setattr(color, _name, _sgr(_code))
+del _name, _code
