@@ -122,8 +122,8 @@ __device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("
 __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // X and I events go straight to a packed global counter per column (X count in the low, I count in the high 32
 // bits): they are sparse (a few per read), and keeping them out of shared memory buys another resident warp.
-// One add serves both kinds: +1 (a deletion column), +2^32 (an insertion anchor), +2^32 - 1 (an anchor on a
-// deletion's last column: that column reads "*+n..", no longer "*").
+// 32-bit adds on the halves: +1 X (a deletion column), +1 I (an insertion anchor), and -1 X as well when the anchor
+// is a deletion's last column (that column reads "*+n..", no longer "*").
 __device__ __forceinline__ void red_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds4(uint32_t a) {
