@@ -593,17 +593,34 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     const size_t tbl_smem = (size_t)INS_TBL * 16;
     int32_t h_over = 0;
     int32_t h_layout[3] = {0, 0, 0};
+    // the calls, their inserted characters, the overflow flag and the layout come back through pinned memory: copies
+    // into the caller's (pageable) buffers would each wait for the stream
+    const size_t calls_bytes = sizeof(tc_insert_call_t) * (size_t)n_cand, fixed_bytes = (size_t)n_cand * INS_BASES_FIXED;
+    const bool via_pinned = calls_bytes + fixed_bytes + 16 <= TC_HOST_SCRATCH;
+    uint8_t* pin = (uint8_t*)ctx->host_scratch;
+    void* dst_calls = via_pinned ? (void*)pin : (void*)calls;
+    void* dst_fixed = via_pinned ? (void*)(pin + calls_bytes) : (void*)h_fixed;
+    int32_t* dst_over = via_pinned ? (int32_t*)(pin + calls_bytes + fixed_bytes) : &h_over;
+    int32_t* dst_layout = via_pinned ? dst_over + 1 : h_layout;
+    if (via_pinned) { *dst_over = 0; dst_layout[0] = dst_layout[1] = dst_layout[2] = 0; }
     if (!sorted_form) {
-        INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
+        if (!ctx->ins_attr_set) {
+            INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
+            ctx->ins_attr_set = 1;
+        }
         ins_count_kernel<<<n_cand, 1024, tbl_smem, s>>>(a, d_calls);
         ctx->launches++;
-        INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
-        if (spec) INS_CUDA(cudaMemcpyAsync(h_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
+        INS_CUDA(cudaMemcpyAsync(dst_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
+        if (spec) INS_CUDA(cudaMemcpyAsync(dst_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
     }
-    INS_CUDA(cudaMemcpyAsync(calls, d_calls, sizeof(tc_insert_call_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "insert calls readback");
-    INS_CUDA(cudaMemcpyAsync(h_fixed, a.bases_fixed, (size_t)n_cand * INS_BASES_FIXED, cudaMemcpyDeviceToHost, s), "inserted bases readback");
+    INS_CUDA(cudaMemcpyAsync(dst_calls, d_calls, calls_bytes, cudaMemcpyDeviceToHost, s), "insert calls readback");
+    INS_CUDA(cudaMemcpyAsync(dst_fixed, a.bases_fixed, fixed_bytes, cudaMemcpyDeviceToHost, s), "inserted bases readback");
     INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
     INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
+    if (via_pinned) {
+        memcpy(calls, dst_calls, calls_bytes); memcpy(h_fixed, dst_fixed, fixed_bytes);
+        h_over = *dst_over; h_layout[0] = dst_layout[0]; h_layout[1] = dst_layout[1]; h_layout[2] = dst_layout[2];
+    }
     ctx->d2h_bytes += (int64_t)(sizeof(tc_insert_call_t) + INS_BASES_FIXED) * n_cand + (int64_t)sizeof(tc_status) + 4;
     if (spec) {
         if (h_layout[2] || h_over) {

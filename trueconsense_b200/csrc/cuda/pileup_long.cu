@@ -226,7 +226,7 @@ int tc_pileup_long_launch(tc_ctx* ctx, const pileup_args& a0, cudaStream_t s) {
     TC_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_pieces, piece_base, (int)(n + 1), s));
     TC_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_ops, ops_base, (int)(n + 1), s));
     ctx->launches += 2;
-    uint32_t totals[2];
+    uint32_t* totals = (uint32_t*)ctx->host_status;        // pinned: the two copies do not wait for the stream one by one
     TC_CUDA(cudaMemcpyAsync(&totals[0], piece_base + n, 4, cudaMemcpyDeviceToHost, s));
     TC_CUDA(cudaMemcpyAsync(&totals[1], ops_base + n, 4, cudaMemcpyDeviceToHost, s));
     TC_CUDA(cudaStreamSynchronize(s));

@@ -788,15 +788,27 @@ template <int WC, bool PIECES>
 static int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
     using G = geom<WC>;
     const size_t smem = sizeof(uint32_t) * (size_t)(G::WARP_WORDS + 2) * G::WARPS;
-    TC_CUDA(cudaFuncSetAttribute(warp_pileup_kernel<WC, PIECES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t bit = 1u << ((WC == 32 ? 0 : WC == 64 ? 1 : 2) + (PIECES ? 3 : 0));
+    if (!(ctx->warp_attr_set & bit)) {
+        TC_CUDA(cudaFuncSetAttribute(warp_pileup_kernel<WC, PIECES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->warp_attr_set |= bit;
+    }
     warp_pileup_kernel<WC, PIECES><<<ctx->sm_count, G::WARPS * 32, smem, s>>>(a);
     TC_LAUNCH_CHECK();
     return TC_OK;
 }
 
-// All geometries are enqueued; each reads the longest reference span the span pass left in
-// a.status and returns at once unless it is the one that fits (no host round trip in between).
+// Without a span bound all geometries are enqueued: each reads the longest reference span the span pass left in
+// a.status and returns at once unless it is the one that fits (no host round trip in between).  With the caller's
+// bound the host knows which one that is.
 int tc_pileup_warp_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
+    if (a.span_hint > 0) {
+        const int ms = (a.span_hint + 7) & ~7;
+        const int slack32 = (256 - ms - 8) & ~7, slack64 = (512 - ms - 8) & ~7;
+        if (slack32 >= MIN_SLACK) return launch_geom<32, false>(ctx, a, s);
+        if (slack64 >= MIN_SLACK) return launch_geom<64, false>(ctx, a, s);
+        return launch_geom<128, false>(ctx, a, s);
+    }
     int rc = launch_geom<32, false>(ctx, a, s);
     if (rc) return rc;
     rc = launch_geom<64, false>(ctx, a, s);

@@ -22,6 +22,7 @@ enum tc_slot {
 
 struct tc_buf { void* p; size_t cap; };
 
+constexpr size_t TC_HOST_SCRATCH = 64 * 1024;
 struct tc_ctx {
     int device;
     int sm_count;
@@ -29,7 +30,11 @@ struct tc_ctx {
     int64_t launches;
     int64_t h2d_bytes, d2h_bytes;
     tc_buf bufs[SLOT_COUNT];
+    int ins_attr_set;       // ins_count_kernel's shared-memory attribute has been set
+    uint32_t warp_attr_set; // ... and those of the warp_pileup_kernel instances (one bit each)
     void* host_status;      // pinned, 256 bytes
+    void* host_scratch;     // pinned, TC_HOST_SCRATCH bytes: small results come back here in truly asynchronous copies
+                            // (a cudaMemcpyAsync into pageable memory waits for the stream)
     int timing;             // bracket the pileup kernel with events
     cudaEvent_t ev0, ev1;
     int ev_valid;

@@ -137,6 +137,8 @@ TC_API int tc_ctx_create(int device, tc_ctx_t** out) {
     }
     e = cudaMallocHost(&ctx->host_status, 256);
     if (e != cudaSuccess) { free(ctx); return tc_cuda_fail(NULL, e, "cudaMallocHost"); }
+    e = cudaMallocHost(&ctx->host_scratch, TC_HOST_SCRATCH);
+    if (e != cudaSuccess) { cudaFreeHost(ctx->host_status); free(ctx); return tc_cuda_fail(NULL, e, "cudaMallocHost"); }
     *out = ctx;
     return TC_OK;
 }
@@ -147,6 +149,7 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     for (int i = 0; i < SLOT_COUNT; ++i)
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
+    if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     free(ctx);
     return TC_OK;
