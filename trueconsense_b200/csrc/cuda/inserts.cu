@@ -482,11 +482,19 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     const int64_t n = a.r.n;
     for (int i = 0; i < n_cand; ++i) { calls[i].pos = cand_pos[i]; calls[i].n_entries = 0; calls[i].mode_count = 0; calls[i].first_read = -1; calls[i].head = 0; calls[i].indel = 0; calls[i].bases_off = -1; }
     if (n == 0) return TC_OK;
-    tc_status* d_status = (tc_status*)tc_dev_buf(ctx, SLOT_STATUS, sizeof(tc_status));
+    // results block: status, layout, overflow flag, admitted counts, the calls and their inserted characters — one
+    // memset in front, one copy back
+    const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_SEG = 96;
+    const size_t rb_calls = RB_SEG + ((4 * ((size_t)n_cand + 1) + 15) & ~(size_t)15);
+    const size_t rb_fixed = rb_calls + sizeof(tc_insert_call_t) * (size_t)n_cand;
+    const size_t rb_bytes = rb_fixed + (size_t)n_cand * INS_BASES_FIXED;
+    static_assert(sizeof(tc_status) <= 64, "tc_status outgrew its place in the results block");
+    uint8_t* d_rb = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_E, rb_bytes + 16);
+    tc_status* d_status = (tc_status*)d_rb;
     int32_t* d_cand = (int32_t*)tc_dev_buf(ctx, SLOT_INS_A, 4 * (size_t)n_cand);
     int32_t* d_range = (int32_t*)tc_dev_buf(ctx, SLOT_INS_B, 24 * (size_t)n_cand);       // [n_cand][2] ranges, then [n_cand][4] offsets
     if (!d_status || !d_cand || !d_range) return TC_ERR_NOMEM;
-    TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
+    TC_CUDA(cudaMemsetAsync(d_rb, 0, rb_calls, s));
     TC_CUDA(cudaMemcpyAsync(d_cand, cand_pos, 4 * (size_t)n_cand, cudaMemcpyHostToDevice, s));
     ctx->h2d_bytes += 4 * (int64_t)n_cand;
     a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
@@ -560,18 +568,17 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     // one slab: keys, indel, qpos, head, sel per slot; tile tables; per-candidate offsets, counts
     const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + (size_t)n_cand * INS_BASES_FIXED + 256 + 16;
     uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
-    tc_insert_call_t* d_calls = (tc_insert_call_t*)tc_dev_buf(ctx, SLOT_INS_E, sizeof(tc_insert_call_t) * (size_t)n_cand);
-    if (!slab || !d_calls) { INS_FREE(); return TC_ERR_NOMEM; }
+    tc_insert_call_t* d_calls = (tc_insert_call_t*)(d_rb + rb_calls);
+    if (!slab) { INS_FREE(); return TC_ERR_NOMEM; }
     uint64_t* d_key = (uint64_t*)slab;
     int64_t* d_off = (int64_t*)(d_key + T);
     a.ent_indel = (int32_t*)(d_off + n_cand + 1); a.ent_qpos = a.ent_indel + T;
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + n_cand + 1; a.tile_last = a.tile_sel + NT;
-    a.seg_count = a.tile_last + NT; a.overflow = a.seg_count + n_cand;
-    int32_t* d_layout = a.overflow + 1;         // [3], speculative layout only
-    a.ent_head = (uint8_t*)(d_layout + 3); a.ent_sel = a.ent_head + T; a.bases_fixed = a.ent_sel + T;
+    a.seg_count = (int32_t*)(d_rb + RB_SEG); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    int32_t* d_layout = (int32_t*)(d_rb + RB_LAYOUT);         // [3], speculative layout only
+    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.bases_fixed = d_rb + rb_fixed;
     a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst;
-    INS_CUDA(cudaMemsetAsync(a.seg_count, 0, 4 * ((size_t)n_cand + 1), s), "memset");
     if (spec) {
         a.layout = d_layout;
         ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT);
@@ -593,16 +600,10 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     const size_t tbl_smem = (size_t)INS_TBL * 16;
     int32_t h_over = 0;
     int32_t h_layout[3] = {0, 0, 0};
-    // the calls, their inserted characters, the overflow flag and the layout come back through pinned memory: copies
-    // into the caller's (pageable) buffers would each wait for the stream
+    // the results block comes back in one copy through pinned memory (copies into the caller's pageable buffers
+    // would each wait for the stream)
     const size_t calls_bytes = sizeof(tc_insert_call_t) * (size_t)n_cand, fixed_bytes = (size_t)n_cand * INS_BASES_FIXED;
-    const bool via_pinned = calls_bytes + fixed_bytes + 16 <= TC_HOST_SCRATCH;
-    uint8_t* pin = (uint8_t*)ctx->host_scratch;
-    void* dst_calls = via_pinned ? (void*)pin : (void*)calls;
-    void* dst_fixed = via_pinned ? (void*)(pin + calls_bytes) : (void*)h_fixed;
-    int32_t* dst_over = via_pinned ? (int32_t*)(pin + calls_bytes + fixed_bytes) : &h_over;
-    int32_t* dst_layout = via_pinned ? dst_over + 1 : h_layout;
-    if (via_pinned) { *dst_over = 0; dst_layout[0] = dst_layout[1] = dst_layout[2] = 0; }
+    const bool via_pinned = rb_bytes <= TC_HOST_SCRATCH;
     if (!sorted_form) {
         if (!ctx->ins_attr_set) {
             INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
@@ -610,16 +611,25 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
         }
         ins_count_kernel<<<n_cand, 1024, tbl_smem, s>>>(a, d_calls);
         ctx->launches++;
-        INS_CUDA(cudaMemcpyAsync(dst_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
-        if (spec) INS_CUDA(cudaMemcpyAsync(dst_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
     }
-    INS_CUDA(cudaMemcpyAsync(dst_calls, d_calls, calls_bytes, cudaMemcpyDeviceToHost, s), "insert calls readback");
-    INS_CUDA(cudaMemcpyAsync(dst_fixed, a.bases_fixed, fixed_bytes, cudaMemcpyDeviceToHost, s), "inserted bases readback");
-    INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
-    INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
     if (via_pinned) {
-        memcpy(calls, dst_calls, calls_bytes); memcpy(h_fixed, dst_fixed, fixed_bytes);
-        h_over = *dst_over; h_layout[0] = dst_layout[0]; h_layout[1] = dst_layout[1]; h_layout[2] = dst_layout[2];
+        uint8_t* pin = (uint8_t*)ctx->host_scratch;
+        INS_CUDA(cudaMemcpyAsync(pin, d_rb, rb_bytes, cudaMemcpyDeviceToHost, s), "results readback");
+        INS_CUDA(cudaStreamSynchronize(s), "results readback");
+        memcpy(ctx->host_status, pin, sizeof(tc_status));
+        memcpy(h_layout, pin + RB_LAYOUT, 12); memcpy(&h_over, pin + RB_OVER, 4);
+        memcpy(calls, pin + rb_calls, calls_bytes); memcpy(h_fixed, pin + rb_fixed, fixed_bytes);
+        if (sorted_form) { h_over = 0; }
+        if (!spec) { h_layout[0] = h_layout[1] = h_layout[2] = 0; }
+    } else {
+        if (!sorted_form) {
+            INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
+            if (spec) INS_CUDA(cudaMemcpyAsync(h_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
+        }
+        INS_CUDA(cudaMemcpyAsync(calls, d_calls, calls_bytes, cudaMemcpyDeviceToHost, s), "insert calls readback");
+        INS_CUDA(cudaMemcpyAsync(h_fixed, a.bases_fixed, fixed_bytes, cudaMemcpyDeviceToHost, s), "inserted bases readback");
+        INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
+        INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
     }
     ctx->d2h_bytes += (int64_t)(sizeof(tc_insert_call_t) + INS_BASES_FIXED) * n_cand + (int64_t)sizeof(tc_status) + 4;
     if (spec) {
