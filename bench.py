@@ -58,33 +58,63 @@ def ncu_traffic():
 
 
 class ClockSampler:
+    """nvidia-smi polled in the background.  It is started (and its first sample awaited) BEFORE the timed regions:
+    the start-up of one nvidia-smi per rank (NVML initialisation) inside a timed region of a few milliseconds
+    disturbed the launches of every rank.  Only samples taken inside the marked windows are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
+        self.rows = []          # (time, fields)
+        self.windows = []       # [t0, t1]
+        self.thread = None
 
     def start(self):
+        import threading
+
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+        t_end = time.time() + 10.0
+        while not self.rows and time.time() < t_end:        # NVML is up once the first sample is out
+            time.sleep(0.01)
+
+    def open_window(self):
+        self.windows.append([time.time(), None])
+
+    def close_window(self):
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        # a window shorter than the polling interval may hold no sample: widen it by one interval on both sides
+        wins = [(a - 0.06, (b if b is not None else time.time()) + 0.06) for a, b in self.windows]
         sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
+        for t, f in self.rows:
+            if wins and not any(a <= t <= b for a, b in wins):
+                continue
             if len(f) < 9:
                 continue
             try:
@@ -201,6 +231,15 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU implementation")
     torch.cuda.set_device(local)
     if world > 1:
+        # one rank per GPU on a shared host: give every rank its own slice of the host cores — the tail of a step is a
+        # handful of small launches and read-backs, and ranks migrating over each other's cores showed in the max over ranks
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 1:
+                os.sched_setaffinity(0, cpus[local * per:(local + 1) * per])
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gpu.Context(local)
     w, batch = make_sample(args.scale, rank)
@@ -230,11 +269,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     ctx.set_timing(True)
     params = gpu.buildindex_params(args.kernel)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.open_window()
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -244,6 +284,7 @@ def run_ours(args):
         kernel_ms.append(ctx.last_pileup_kernel_ms())
     ev1.record()
     barrier()
+    sampler.close_window()
     launches = ctx.launches - launches0
     ms_total = ev0.elapsed_time(ev1)
     # ---------------- end to end through the C-ABI with host buffers: `e2e`
@@ -264,11 +305,13 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     xfer0 = ctx.transfer_bytes()
+    sampler.open_window()
     e0.record()
     for _ in range(args.steps):
         h, res, ins = e2e_step()
     e1.record()
     barrier()
+    sampler.close_window()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()          # sampled over both timed regions (device-resident steps, then end-to-end steps)
     h2d, d2h_lib = (b - a_ for a_, b in zip(xfer0, ctx.transfer_bytes()))
