@@ -231,15 +231,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU implementation")
     torch.cuda.set_device(local)
     if world > 1:
-        # one rank per GPU on a shared host: give every rank its own slice of the host cores — the tail of a step is a
-        # handful of small launches and read-backs, and ranks migrating over each other's cores showed in the max over ranks
-        try:
-            cpus = sorted(os.sched_getaffinity(0))
-            per = len(cpus) // world
-            if per >= 1:
-                os.sched_setaffinity(0, cpus[local * per:(local + 1) * per])
-        except (AttributeError, OSError):
-            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gpu.Context(local)
     w, batch = make_sample(args.scale, rank)
@@ -271,6 +262,11 @@ def run_ours(args):
     params = gpu.buildindex_params(args.kernel)
     sampler = ClockSampler(local)
     sampler.start()
+    # spin-up (not steps): W warm-up passes are 2-3 ms of GPU work, far less than a cold GPU needs to reach its clocks and
+    # the driver to settle — the first run on a fresh box measured 0.93 ms per step where every later run measured 0.74
+    t_spin = time.time() + args.spinup
+    while time.time() < t_spin:
+        hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
     for _ in range(args.warmup):
         calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
     barrier()
@@ -375,6 +371,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="pileup kernel variant (0 = library's choice; A/B measurements only)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 2 M reads of configs[1] (tests only)")
+    ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed passes before the warm-up steps (clock / driver spin-up of a cold GPU)")
     ap.add_argument("--cpu-reads", type=float, default=1_000_000, help="reads in the cpu_baseline sample (1 M reads = 400 M aligned bases, 10-15 s on one core)")
     ap.add_argument("--ref-reads", type=float, default=400_000, help="reads per step of the --impl reference arm")
     args = ap.parse_args()
