@@ -283,3 +283,46 @@ def test_bench_reference_arm_line(host_libs):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("cfg2")
+
+
+def test_bench_needs_a_gpu_and_says_so():
+    """Our arm of bench.py has no CPU path: without a CUDA device it stops with a message instead of printing a line."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--scale", "0.001"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "CUDA device" in (out.stderr + out.stdout)
+    assert not out.stdout.strip().startswith("{")
+
+
+def test_clock_sampler_reports_only_samples_inside_the_timed_windows():
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("tc_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Quiet:
+        stdout = ()
+
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    s = bench.ClockSampler(0)
+    s.proc = Quiet()
+    now = time.time()
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700", "0x0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(now - 10.0, row(300, "Not Active")),            # idle, long before the timed region: ignored
+              (now - 1.00, row(1965, "Not Active")), (now - 0.98, row(1950, "Active")),
+              (now + 30.0, row(200, "Not Active"))]
+    s.windows = [[now - 1.01, now - 0.97]]
+    r = s.stop()
+    assert r["samples"] == 2 and r["sm_mhz"] == pytest.approx(1957.5) and r["sm_max_mhz"] == 1965.0
+    assert r["reasons"] == ["sw_power_cap"]
