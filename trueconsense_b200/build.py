@@ -36,8 +36,8 @@ def _run(cmd: list[str]) -> None:
     if proc.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
         raise RuntimeError(f"build failed: {cmd[0]} exited {proc.returncode}")
-    if proc.stderr.strip() and os.environ.get("TC_BUILD_VERBOSE"):
-        sys.stderr.write(proc.stderr)
+    if (proc.stderr.strip() or proc.stdout.strip()) and (os.environ.get("TC_BUILD_VERBOSE") or os.environ.get("TC_PTXAS_V")):
+        sys.stderr.write(proc.stdout + proc.stderr)
 
 
 def _sources(subdir: str, exts: tuple[str, ...]) -> list[str]:
@@ -62,18 +62,35 @@ def nvcc_path() -> str:
 
 
 def build_cuda(force: bool = False) -> str:
+    """Every .cu is compiled to its own object (in parallel, only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+
     cu = _sources("cuda", (".cu",))
     hdrs = _sources("cuda", (".cuh", ".h")) + [os.path.join(INCLUDE, "trueconsense_b200.h")]
-    if force or _newer(CUDA_LIB, cu + hdrs):
-        cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-               "-Xcompiler", "-fvisibility=hidden", "-cudart", "static", "--fmad=false",
-               "-I", INCLUDE, "-I", os.path.join(CSRC, "cuda")] + CUDA_ARCH_FLAGS
-        if os.environ.get("TC_NVCC_DEFS"):           # e.g. "-DTC_CHUNK_WORDS=6" (tuning experiments)
-            cmd += os.environ["TC_NVCC_DEFS"].split()
-        if os.environ.get("TC_PTXAS_V"):
-            cmd += ["-Xptxas", "-v"]
-        cmd += ["-o", CUDA_LIB] + cu + ["-ldl"]
-        _run(cmd)
+    objdir = os.path.join(ROOT, "build", "cuda")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+             "--fmad=false", "-I", INCLUDE, "-I", os.path.join(CSRC, "cuda")] + CUDA_ARCH_FLAGS
+    if os.environ.get("TC_NVCC_DEFS"):           # e.g. "-DTC_FLAT_CW=6" (tuning experiments)
+        flags += os.environ["TC_NVCC_DEFS"].split()
+        force = True
+    if os.environ.get("TC_PTXAS_V"):
+        flags += ["-Xptxas", "-v"]
+        force = True
+    objs, jobs = [], []
+    for src in cu:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + hdrs):
+            jobs.append([nvcc_path()] + flags + ["-c", "-o", obj, src])
+    stale = [o for o in os.listdir(objdir) if o.endswith(".o") and os.path.join(objdir, o) not in objs]
+    for o in stale:
+        os.remove(os.path.join(objdir, o))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(_run, jobs))
+    if jobs or stale or not os.path.exists(CUDA_LIB) or _newer(CUDA_LIB, objs):
+        _run([nvcc_path(), "-shared", "-cudart", "static"] + CUDA_ARCH_FLAGS + ["-o", CUDA_LIB] + objs + ["-ldl"])
     return CUDA_LIB
 
 

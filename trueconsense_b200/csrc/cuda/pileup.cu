@@ -295,18 +295,22 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     int variant = p->kernel;
     // reads longer than variant 3's widest window are cut into pieces first (variant 4, pileup_long.cu)
     const int LONG_SPAN = 1024 - 8 - 64;
-    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? (a.span_hint > LONG_SPAN ? 4 : 3) : 1;
-    if (variant < 1 || variant > 4) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
-    if (variant != 1 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels have no base-quality filter; use kernel=1");
-    if (variant != 1 && !tc_pileup_swar_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the SWAR kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
+    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? (a.span_hint > LONG_SPAN ? 4 : 5) : 1;
+    if (variant < 1 || variant > 6 || variant == 2) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
+    if (variant != 1 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the bit-parallel kernels have no base-quality filter; use kernel=1");
+    if (variant != 1 && !tc_pileup_warp_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the bit-parallel kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
+    // 4 / 6: long reads cut into pieces, the pieces piled up by variant 5 / 3
+    a.piece_kernel = variant == 6 ? 3 : 5;
+    const bool is_long = variant == 4 || variant == 6;
+    const bool direct = variant == 3 || variant == 5;
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
         if (variant != 1) {
             // coverage ends, span statistics and the sortedness / range checks: one thread per read — unless the
             // caller bounded the longest span, then variant 3 does all of that while it walks the CIGARs anyway
-            if (variant != 3 || a.span_hint == 0 || a.span_hint > LONG_SPAN) {
+            if (!direct || a.span_hint == 0 || a.span_hint > LONG_SPAN) {
                 a.span_hint = 0;
-                if (variant == 4) {         // the long-read split needs every read's span: one walk over the CIGARs serves both
+                if (is_long) {         // the long-read split needs every read's span: one walk over the CIGARs serves both
                     a.span_out = (int32_t*)tc_dev_buf(ctx, SLOT_SPAN_END, sizeof(int32_t) * (size_t)a.r.n);
                     if (!a.span_out) return TC_ERR_NOMEM;
                 }
@@ -314,7 +318,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
                 TC_LAUNCH_CHECK();
             }
             a.pieces = nullptr; a.piece_order = nullptr; a.n_pieces = 0;
-            rc = variant == 4 ? tc_pileup_long_launch(ctx, a, s) : variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_swar_launch(ctx, a, s);
+            rc = is_long ? tc_pileup_long_launch(ctx, a, s) : variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_flat_launch(ctx, a, s);
             if (rc) return rc;
         } else {
             int n_chunks = (int)((a.r.n + SC_CHUNK - 1) / SC_CHUNK);
@@ -332,7 +336,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         if (ctx->timing) { TC_CUDA(cudaEventRecord(ctx->ev1, s)); ctx->ev_valid = 1; }
     }
     if (!per_entry) {
-        rc = coverage_scan(ctx, d_diff, d_counts, L, d_status, (variant == 3 || variant == 4) ? a.xi : nullptr, s);
+        rc = coverage_scan(ctx, d_diff, d_counts, L, d_status, variant != 1 ? a.xi : nullptr, s);
         if (rc) return rc;
     }
     tc_status st;
@@ -343,7 +347,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         // reads spanning more than variant 3's window: cut them into pieces (variant 4); anything else the SWAR
         // kernels decline (pads in long reads, a single read beyond the staging buffers): the scatter kernel
         tc_pileup_params_t q = *p;
-        q.kernel = (variant == 3 && a.span_hint == 0 && st.max_span > LONG_SPAN) ? 4 : 1;
+        q.kernel = (direct && a.span_hint == 0 && st.max_span > LONG_SPAN) ? 4 : 1;
         if (q.kernel == 4) {
             const int rc4 = tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
             if (rc4 != TC_ERR_CAPACITY) return rc4;
@@ -352,7 +356,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         return tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
     }
     if (st.err == TC_ERR_CAPACITY)
-        return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the SWAR kernels' windows or staging buffers; use kernel=1 (or 0)");
+        return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the bit-parallel kernels' windows or staging buffers; use kernel=1 (or 0)");
     if (per_entry) {
         // coverage was counted entry by entry, so max_cov is not the live depth; fall back to the
         // trivial bound (every read live at once)
