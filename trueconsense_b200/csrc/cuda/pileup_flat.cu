@@ -10,16 +10,19 @@
 // partition / window / TMA staging, but:
 //
 //   walk        lane = read.  The walk only computes where things are: every maximal run of M/=/X ops becomes a
-//               SEGMENT descriptor (window column, length, row, query nibble address: 8 bytes) appended to the
-//               list of the read's row group (ballot + popcount; lists live in shared memory); D / I events go
-//               to the packed global X | I counters.  No SEQ word is touched, no row is written.  The raw
+//               SEGMENT descriptor of 8 bytes — shared address of its first row word, columns from that word's
+//               start to the segment's end, query nibble under the word's first column, first column inside the
+//               word — appended to the list of the read's row group (ballot + popcount; lists live in shared
+//               memory): segments that end within 4 row words to the SHORT list (from the front of the group's
+//               buffer), longer ones to the LONG list (from its back).  D / I events go to the packed global
+//               X | I counters as one 64-bit add each.  No SEQ word is touched, no row is written.  The raw
 //               32-bit ops are read where the bulk copy put them (the rows, idle at that point): no 16-bit
 //               repacking pass, no limit on an op's length.
-//   expand      lane = descriptor, 32 at a time from the head of the list — all lanes busy whatever the reads'
-//               op counts.  A lane emits the first CW row words of its segment (CW + 1 source words, CW funnel
-//               shifts, head / tail masks, CW red.shared.or into the segment's row) and, if the segment is
-//               longer, writes the remainder back as a descriptor into the slots the iteration just consumed
-//               (the list is its own work queue and never grows).
+//   expand      lane = descriptor, 32 at a time — all lanes busy whatever the reads' op counts.  Short list:
+//               5 source words, 4 funnel shifts, a head mask and 4 tail masks (one vector load from a 33-entry
+//               table), 4 red.shared.or into the segment's row; no branches.  Long list: 8 words per iteration,
+//               the remainder of a still longer segment goes back as a descriptor into the slots the iteration
+//               just consumed (the list is its own work queue and never grows).
 //   column sum  lane = NW consecutive row words (one vector load per row), RP rows per pass through 16-input
 //               carry-save trees into the counters.  A 512-column window sums its 32 reads as two groups of 16
 //               rows — the rows take 4 KB of the warp's slice instead of 8.
@@ -69,7 +72,9 @@ template <int WC> struct fgeom {
     static constexpr int DCAP = (GROUP_OPS + RP) / 2 + 4;
     static constexpr int DESC_WORDS = 2 * NG * DCAP;
     static constexpr int WARP_WORDS = ROW_WORDS + SEQ_WORDS + DESC_WORDS;
-    static constexpr int WARPS = (227 * 1024 / 4) / (WARP_WORDS + 2) > TC_FLAT_MAX_WARPS ? TC_FLAT_MAX_WARPS : (227 * 1024 / 4) / (WARP_WORDS + 2);
+    static constexpr int LUT_WORDS = 33 * 4 + 4;            // tail masks of 4 row words for 0..32 columns (CTA-wide, behind the warps' slices)
+    static constexpr int WARPS = (227 * 1024 / 4 - LUT_WORDS) / (WARP_WORDS + 2) > TC_FLAT_MAX_WARPS ? TC_FLAT_MAX_WARPS : (227 * 1024 / 4 - LUT_WORDS) / (WARP_WORDS + 2);
+    static constexpr int SMEM_WORDS = (WARP_WORDS + 2) * WARPS + LUT_WORDS;
     static_assert(CIG_CAP + 4 <= ROW_WORDS, "the raw ops of a sub-tile are staged in the rows");
     static_assert(ROW_WORDS % 4 == 0 && SEQ_WORDS % 4 == 0 && DESC_WORDS % 4 == 0, "16-byte aligned regions");
     static_assert(DCAP % 2 == 0, "8-byte descriptors, 16-byte aligned lists");
@@ -81,9 +86,43 @@ __device__ __forceinline__ uint2 lds2(uint32_t a) {
     uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v;
 }
 
-// descriptor word 0: window column (10 bits) | length (12 bits) << 10 | row inside its group << 22; word 1: nibble
-// address of the segment's first base, relative to the warp's SEQ region
-constexpr int D_LEN_SHIFT = 10, D_ROW_SHIFT = 22;
+// Segment descriptor.  Word 0: shared address of the segment's first row word (18 bits) | E << 18, E = columns from
+// that word's first column to the segment's end.  Word 1: query nibble under that word's first column, relative to
+// the warp's SEQ region (16 bits) | the segment's first column inside the word << 16.
+constexpr int D_E_SHIFT = 18, D_KB_SHIFT = 16;
+constexpr uint32_t D_ADDR_MASK = (1u << D_E_SHIFT) - 1u;
+
+// X | I event: one 64-bit add to the column's packed counter (X in the low, I in the high 32 bits), predicated
+__device__ __forceinline__ void red_xi_if(bool p, unsigned long long* cell, uint32_t lo, uint32_t hi) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.u32 p, %0, 0;\n\tmov.b64 v, {%2, %3};\n\t@p red.global.add.u64 [%1], v;\n\t}"
+                 ::"r"((uint32_t)p), "l"(cell), "r"(lo), "r"(hi) : "memory");
+}
+
+// NWORDS row words of a segment (NWORDS = 4: E <= 32): NWORDS + 1 source words, funnel shifts, head / tail masks,
+// red.shared.or.  Words behind the segment's end get an empty mask (they may lie past the row: in the pad, the next
+// row or the SEQ pad — inside the warp's slice, and OR-ing zero changes nothing).
+template <int NWORDS>
+__device__ __forceinline__ void emit_words(const uint2 d, const uint32_t seq_s, const uint32_t lut) {
+    const uint32_t ro = d.x & D_ADDR_MASK, E = d.x >> D_E_SHIFT;
+    const uint32_t src = seq_s + ((d.y >> 1) & 0x7ffcu);        // word holding nibble d.y & 0xffff
+    const uint32_t sh = d.y << 2;                               // funnel shifts take it modulo 32: 4 * (nibble & 7)
+    const uint32_t head = 0xffffffffu >> (4u * (d.y >> D_KB_SHIFT));
+    uint32_t w[NWORDS + 1];
+#pragma unroll
+    for (int j = 0; j <= NWORDS; ++j) w[j] = lds(src + 4 * j);
+    uint32_t t[NWORDS];
+    {
+        const uint4 v = lds4(lut + 16u * (NWORDS == 4 ? E : min(E, 32u)));
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+    if constexpr (NWORDS == 8) {
+        const uint4 v = lds4(lut + 16u * (min(max(E, 32u), 64u) - 32u));
+        t[4] = v.x; t[5] = v.y; t[6] = v.z; t[7] = v.w;
+    }
+    reds_or(ro, __funnelshift_l(w[1], w[0], sh) & head & t[0]);
+#pragma unroll
+    for (int j = 1; j < NWORDS; ++j) reds_or(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh) & t[j]);
+}
 
 template <int NW> struct rowvec;
 template <> struct rowvec<1> {
@@ -131,7 +170,13 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem) + 4u * G::WARPS * G::WARP_WORDS + 8u * (threadIdx.x >> 5);
     uint32_t tma_parity = 0;
     if (lane == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncwarp();
+    // tail masks: entry E, word j = the leading clamp(4 * E - 32 * j, 0, 32) bits
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(smem) + 4u * ((G::WARPS * (G::WARP_WORDS + 2) + 3) & ~3);      // 16-byte aligned
+    if (threadIdx.x < 33 * 4) {
+        const int bits = min(max(4 * (int)(threadIdx.x >> 2) - 32 * (int)(threadIdx.x & 3), 0), 32);
+        sts(lut + 4 * threadIdx.x, bits == 0 ? 0u : 0xffffffffu << (32 - bits));
+    }
+    __syncthreads();            // the only CTA-wide barrier: from here on a warp never waits for another
 
     const int64_t n_reads = PIECES ? a.n_pieces : a.r.n;
     const int64_t n_seq_words = (int64_t)a.r.seq_off[a.r.n];
@@ -154,7 +199,7 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
     // lanes of my row group, and those of them below me
     const uint32_t gmask = (NG == 1) ? FULL : (((1u << RP) - 1u) << (lane & ~(RP - 1)));
     const uint32_t glt = ((1u << lane) - 1u) & gmask;
-    const uint32_t my_list = desc_s + 8u * G::DCAP * (uint32_t)(lane / RP);
+    const uint32_t my_list = desc_s + 8u * G::DCAP * (uint32_t)(lane / RP), my_list_end = my_list + 8u * G::DCAP;
 
     auto flush = [&]() {
         __syncwarp();
@@ -385,71 +430,77 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
             ops_vecs = ncv;
         }
 
-        // ---- walk: lane = read.  Segments -> descriptors in the row group's list; D / I events -> global counters
+        // ---- walk: lane = read.  Segments -> descriptors in the row group's lists; D / I events -> global counters.
+        // One iteration takes a match op (opening or extending the lane's segment) and then the op behind it that is
+        // none (which closes the segment: its descriptor goes out with its final length) — the common M I M D M shape
+        // costs one iteration per segment; anything else simply takes another iteration.
         const bool act = lane < n && passes;
         const int x0 = p - w0;
         int x = x0, y = y0;
-        int gcount = 0;                 // descriptors in my group's list (the same in all lanes of the group)
+        int cntS = 0, cntL = 0;         // descriptors in my group's short / long list (the same in all lanes of the group)
         {
             uint32_t cp = act ? ops_lane : rows;
             const uint32_t cend = cp + 4u * (uint32_t)(act ? nops_lane : 0);
             const uint32_t qn = 2u * (sq_lane - seq_s);            // nibble address of the read's first base
-            uint32_t* const xi = reinterpret_cast<uint32_t*>(a.xi + w0);
-            const int xi_n = L - w0;
+            unsigned long long* const xi = a.xi + w0;
+            const int xi_last = L - w0 - 1;
+            const uint32_t rowbase = rows + 4u * (uint32_t)((lane & (RP - 1)) * RS);
+            const bool hasseq = lq > 0;         // reads without SEQ ('*': every base reads 'N') count coverage and events only
             uint32_t c0 = lds(cp), c1 = lds(cp + 4);
-            uint32_t prev = 0;          // bit 1: the op before consumed the reference, bit 0: it was a deletion, bit 2: it was a match op (its segment is open)
-            uint32_t segw = 0, segq = 0, segslot = my_list;
-            bool bad = false;           // pads, zero-length ops: declined
+            uint32_t prev = 0;          // bit 1: the op before consumed the reference, bit 0: it was a deletion
+            int xo = 0, yo = 0, lo = 0; // the open segment: first column, first query base, length (0: none open)
+            int ym = 0;                 // query index behind the last match op
+            uint32_t exmin = 0xffffffffu;       // min over the ops of (len << 4 | op), pads counted as 0: < 16 <=> a pad or a zero-length op
             while (__any_sync(FULL, cp < cend)) {
-                uint32_t c = c0;
-                uint32_t op = c & 15u;
-                uint32_t fl = op_flags(op);
-                bool live = cp < cend;
-                if (live && !(fl & 1u)) {
+                const uint32_t f0 = op_flags(c0 & 15u), f1 = op_flags(c1 & 15u);
+                const bool is_m = cp < cend && (f0 & 1u);
+                if (is_m) {
+                    const int l = (int)(c0 >> 4);
+                    if (lo == 0) { xo = x; yo = y; }
+                    lo += l; x += l; y += l; ym = y;
+                    cp += 4; prev = 2u;
+                    exmin = min(exmin, c0);
+                }
+                const uint32_t c = is_m ? c1 : c0, fl = is_m ? f1 : f0;
+                const bool live = cp < cend;
+                const bool nm = live && !(fl & 1u);
+                const bool closing = lo > 0 && !(live && (fl & 1u));
+                const int kb = xo & 7, E = kb + lo;
+                const bool emit_s = closing && hasseq && E <= 32, emit_l = closing && hasseq && E > 32;
+                const unsigned bs = __ballot_sync(FULL, emit_s), bl = __ballot_sync(FULL, emit_l);
+                if (emit_s || emit_l) {
+                    const uint32_t slot = emit_s ? my_list + 8u * (uint32_t)(cntS + __popc(bs & glt))
+                                                 : my_list_end - 8u * (uint32_t)(cntL + __popc(bl & glt) + 1);
+                    sts2(slot, (rowbase + (uint32_t)((xo >> 3) << 2)) | ((uint32_t)E << D_E_SHIFT),
+                         (qn + (uint32_t)(yo - kb)) | ((uint32_t)kb << D_KB_SHIFT));
+                }
+                cntS += __popc(bs & gmask); cntL += __popc(bl & gmask);
+                if (closing) lo = 0;
+                if (nm) {
+                    const uint32_t op = c & 15u;
                     const int l = (int)(c >> 4);
-                    bad |= (l == 0) | (op == OP_P);
+                    exmin = min(exmin, op == OP_P ? 0u : c);
                     // X / I events: a deletion's columns count +1 X each; an insertion counts +1 I on its anchor column x - 1 —
                     // and -1 X there when that column belongs to a deletion (it reads "*+n..", not "*").  Without zero-length
                     // ops the anchor exists whenever the previous op consumed the reference; a column past the reference is
                     // clamped (such a read is a TC_ERR_RANGE, the counts are void).
                     const bool is_d = (op == OP_D);
                     const bool ev = is_d || (op == OP_I && (prev & 2u));
-                    const int col = min(is_d ? x : x - 1, xi_n - 1);
-                    uint32_t* cell = xi + 2 * col;               // [0] X, [1] I
-                    if (ev) red_u32(cell + (is_d ? 0 : 1), 1u);
-                    if (ev && !is_d && (prev & 1u)) red_u32(cell, 0xffffffffu);
-                    if (is_d && l > 1) for (int k = x + 1; k < min(x + l, xi_n); ++k) red_u32(xi + 2 * k, 1u);
+                    const int col = min(x - (is_d ? 0 : 1), xi_last);
+                    red_xi_if(ev, xi + col, is_d ? 1u : 0u - (prev & 1u), (is_d || (prev & 1u)) ? 0u : 1u);
+                    if (is_d && l > 1) for (int k = x + 1; k <= min(x + l - 1, xi_last); ++k) red_xi_if(true, xi + k, 1u, 0u);
                     prev = (fl & 2u) | (is_d ? 1u : 0u);
                     if (fl & 2u) x += l;
                     if (fl & 4u) y += l;
                     cp += 4;
-                    c = c1; op = c & 15u; fl = op_flags(op);
-                    live = cp < cend;
                 }
-                bool m = live && (fl & 1u);
-                const int l = (int)(c >> 4);
-                if (m) {
-                    bad |= (l == 0);
-                    // beyond the window, or a CIGAR that consumes more query than SEQ holds: the scatter kernel's business
-                    if (x + l > ROWW || (lq > 0 && y + l > lq)) { atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); cp = cend; m = false; }
-                }
-                const bool emit = m && lq > 0;          // reads without SEQ ('*': every base reads 'N') count coverage and events only
-                const bool fresh_seg = emit && !(prev & 4u);
-                __syncwarp();
-                const unsigned nb = __ballot_sync(FULL, fresh_seg);
-                if (fresh_seg) {
-                    segslot = my_list + 8u * (uint32_t)(gcount + __popc(nb & glt));
-                    segw = (uint32_t)x | ((uint32_t)(lane & (RP - 1)) << D_ROW_SHIFT);
-                    segq = qn + (uint32_t)y;
-                }
-                gcount += __popc(nb & gmask);
-                if (emit) { segw += (uint32_t)l << D_LEN_SHIFT; sts2(segslot, segw, segq); }
-                if (m) { x += l; y += l; cp += 4; prev = 6u; }
                 c0 = lds(cp); c1 = lds(cp + 4);
             }
-            if (__any_sync(FULL, bad)) {
+            // beyond the window, a CIGAR that consumes more query than SEQ holds, pads, zero-length ops: the scatter kernel's business
+            const bool over = act && (x > ROWW || (hasseq && ym > lq));
+            if (__any_sync(FULL, over || exmin < 16u)) {
                 if (lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
-                gcount = 0;
+                cntS = cntL = 0;
             }
         }
         const int x_end = x;
@@ -461,45 +512,31 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
         // ---- per row group: expand its descriptors into its rows (lane = descriptor), then sum the rows (lane = row words)
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            const int nd = __shfl_sync(FULL, gcount, g * RP);
-            if (nd == 0) continue;
-            const uint32_t list = desc_s + 8u * G::DCAP * (uint32_t)g;
-            int h = 0;
-            while (h < nd) {
-                const int cnt = min(32, nd - h);
-                uint2 d = make_uint2(0u, 0u);
-                if (lane < cnt) d = lds2(list + 8u * (uint32_t)(h + lane));
-                const int xs = (int)(d.x & 1023u);
-                const int len = (int)((d.x >> D_LEN_SHIFT) & 4095u);
-                const int kb = xs & 7;
-                const int cl = min(len, 8 * CW - kb);
-                const int q0 = (int)d.y - kb;                           // query nibble under the first column of row word xs >> 3
-                const uint32_t src = seq_s + (uint32_t)((q0 >> 3) << 2);
-                const int sh4 = (q0 & 7) << 2;
-                uint32_t w[CW + 1];
-#pragma unroll
-                for (int j = 0; j <= CW; ++j) w[j] = lds(src + 4 * j);
-                const int rem4 = 4 * (kb + cl);                         // 4 * columns from the first row word's start to the piece's end
-                const uint32_t ro = rows + 4u * ((d.x >> D_ROW_SHIFT) * RS + (uint32_t)(xs >> 3));
-                if (len > 0) {
-                    reds_or(ro, __funnelshift_l(w[1], w[0], sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
-#pragma unroll
-                    for (int j = 1; j < CW; ++j) {
-                        const uint32_t v = __funnelshift_l(w[j + 1], w[j], sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32 * j, 0));
-                        if (rem4 > 32 * j) reds_or(ro + 4 * j, v);
-                    }
-                }
-                // a longer segment: its remainder goes back into the slots this iteration consumed
-                const bool more = len > cl;
+            const int ns = __shfl_sync(FULL, cntS, g * RP), nl = __shfl_sync(FULL, cntL, g * RP);
+            if (ns + nl == 0) continue;
+            const uint32_t list = desc_s + 8u * G::DCAP * (uint32_t)g, list_end = list + 8u * G::DCAP;
+            // short segments: 4 row words each, no branches (lanes without a descriptor run on an empty one)
+            for (int h = lane; h < ns + lane; h += 32) {
+                uint2 d = make_uint2(rows, 0u);
+                if (h < ns) d = lds2(list + 8u * (uint32_t)h);
+                emit_words<4>(d, seq_s, lut);
+            }
+            // long segments: 8 row words per iteration; what is left of a still longer one goes back into the slots this
+            // iteration consumed (the list is stored from the back of the buffer: entry k at list_end - 8 (k + 1))
+            for (int h = 0; h < nl;) {
+                const int cnt = min(32, nl - h);
+                uint2 d = make_uint2(rows, 0u);
+                if (lane < cnt) d = lds2(list_end - 8u * (uint32_t)(h + lane + 1));
+                emit_words<8>(d, seq_s, lut);
+                const bool more = (d.x >> D_E_SHIFT) > 64u;
                 const unsigned mb = __ballot_sync(FULL, more);
                 const int k = __popc(mb);
-                if (more) {
-                    const uint32_t slot = list + 8u * (uint32_t)(h + cnt - k + __popc(mb & ((1u << lane) - 1u)));
-                    sts2(slot, (d.x & ~((4095u << D_LEN_SHIFT) | 1023u)) | (uint32_t)(xs + cl) | ((uint32_t)(len - cl) << D_LEN_SHIFT), d.y + (uint32_t)cl);
-                }
+                if (more) sts2(list_end - 8u * (uint32_t)(h + cnt - k + __popc(mb & ((1u << lane) - 1u)) + 1),
+                               d.x + 32u - (64u << D_E_SHIFT), (d.y & 0xffffu) + 64u);
                 h += cnt - k;
                 __syncwarp();
             }
+            __syncwarp();
             // column sum: lane owns row words NW * lane .. NW * lane + NW - 1, all RP rows of the group
             const int ng = min(n - g * RP, RP);
 #pragma unroll
@@ -572,7 +609,7 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
 template <int WC, bool PIECES>
 int launch_geom(tc_ctx* ctx, const pileup_args& a, cudaStream_t s) {
     using G = fgeom<WC>;
-    const size_t smem = sizeof(uint32_t) * (size_t)(G::WARP_WORDS + 2) * G::WARPS;
+    const size_t smem = sizeof(uint32_t) * (size_t)G::SMEM_WORDS;
     const uint32_t bit = 1u << (8 + (WC == 32 ? 0 : WC == 64 ? 1 : 2) + (PIECES ? 3 : 0));
     if (!(ctx->warp_attr_set & bit)) {
         TC_CUDA(cudaFuncSetAttribute(flat_pileup_kernel<WC, PIECES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
