@@ -9,14 +9,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from trueconsense_b200 import gpu, synth  # noqa: E402
 
 ctx = gpu.Context(0)
-for idx, scale in ((0, 1.0), (2, 1.0), (3, 0.1), (4, 0.5)):
+KERNELS = [int(k) for k in sys.argv[1].split(',')] if len(sys.argv) > 1 else [0, 1]
+for idx, scale in ((0, 1.0), (1, 1.0), (2, 1.0), (3, 0.1), (4, 0.5)):
     w = synth.config(idx, scale=scale)
     b = synth.generate_reads(w.params, w.ref)
     L = len(w.ref)
     dev = ctx.upload(b, with_qual=False)
     out = torch.empty((8, L), dtype=torch.int32, device="cuda")
     bases = b.count_aligned_bases(0x4)
-    for kernel in (0, 1):
+    for kernel in KERNELS:
+        if idx == 4 and kernel in (3, 5):
+            kernel = 4 if kernel == 5 else 6     # long reads: pieces through variant 5 (kernel 4) / variant 3 (kernel 6)
         p = gpu.buildindex_params(kernel)
         for _ in range(3):
             ctx.pileup_counts(dev, L, p, out=out)

@@ -93,17 +93,23 @@ constexpr int D_E_SHIFT = 18, D_KB_SHIFT = 16;
 constexpr uint32_t D_ADDR_MASK = (1u << D_E_SHIFT) - 1u;
 
 // X | I event: one 64-bit add to the column's packed counter (X in the low, I in the high 32 bits), predicated
-__device__ __forceinline__ void red_xi_if(bool p, unsigned long long* cell, uint32_t lo, uint32_t hi) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v;\n\tsetp.ne.u32 p, %0, 0;\n\tmov.b64 v, {%2, %3};\n\t@p red.global.add.u64 [%1], v;\n\t}"
-                 ::"r"((uint32_t)p), "l"(cell), "r"(lo), "r"(hi) : "memory");
+__device__ __forceinline__ void red_xi_if(bool p, unsigned long long* xi, uint32_t col, uint32_t lo, uint32_t hi) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v, q;\n\tsetp.ne.u32 p, %0, 0;\n\tmov.b64 v, {%3, %4};\n\tmad.wide.u32 q, %2, 8, %1;\n\t@p red.global.add.u64 [q], v;\n\t}"
+                 ::"r"((uint32_t)p), "l"(xi), "r"(col), "r"(lo), "r"(hi) : "memory");
+}
+
+// red.shared.or of a word that has any bit set (predicated, no branch): words behind a segment's end, and the lanes
+// of an iteration that hold no descriptor, cost no shared-memory cycles — 24 idle lanes OR-ing zero into one
+// address were 24 serialised atomics (profiles/r2_v2: shared-memory pipe at 72 %, 63 M conflict cycles on atomics)
+__device__ __forceinline__ void reds_or_nz(uint32_t a, uint32_t v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(a), "r"(v) : "memory");
 }
 
 // NWORDS row words of a segment (NWORDS = 4: E <= 32): NWORDS + 1 source words, funnel shifts, head / tail masks,
-// red.shared.or.  Words behind the segment's end get an empty mask (they may lie past the row: in the pad, the next
-// row or the SEQ pad — inside the warp's slice, and OR-ing zero changes nothing).
+// red.shared.or.  Words behind the segment's end get an empty mask and are not written.
 template <int NWORDS>
 __device__ __forceinline__ void emit_words(const uint2 d, const uint32_t seq_s, const uint32_t lut) {
-    const uint32_t ro = d.x & D_ADDR_MASK, E = d.x >> D_E_SHIFT;
+    const uint32_t ro = d.x & D_ADDR_MASK, E = d.x >> D_E_SHIFT;        // (an empty descriptor: E = 0, every mask empty)
     const uint32_t src = seq_s + ((d.y >> 1) & 0x7ffcu);        // word holding nibble d.y & 0xffff
     const uint32_t sh = d.y << 2;                               // funnel shifts take it modulo 32: 4 * (nibble & 7)
     const uint32_t head = 0xffffffffu >> (4u * (d.y >> D_KB_SHIFT));
@@ -112,16 +118,16 @@ __device__ __forceinline__ void emit_words(const uint2 d, const uint32_t seq_s, 
     for (int j = 0; j <= NWORDS; ++j) w[j] = lds(src + 4 * j);
     uint32_t t[NWORDS];
     {
-        const uint4 v = lds4(lut + 16u * (NWORDS == 4 ? E : min(E, 32u)));
+        const uint4 v = lds4(lut + 16u * min(E, 32u));
         t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
     }
     if constexpr (NWORDS == 8) {
         const uint4 v = lds4(lut + 16u * (min(max(E, 32u), 64u) - 32u));
         t[4] = v.x; t[5] = v.y; t[6] = v.z; t[7] = v.w;
     }
-    reds_or(ro, __funnelshift_l(w[1], w[0], sh) & head & t[0]);
+    reds_or_nz(ro, __funnelshift_l(w[1], w[0], sh) & head & t[0]);
 #pragma unroll
-    for (int j = 1; j < NWORDS; ++j) reds_or(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh) & t[j]);
+    for (int j = 1; j < NWORDS; ++j) reds_or_nz(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh) & t[j]);
 }
 
 template <int NW> struct rowvec;
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
     // lanes of my row group, and those of them below me
     const uint32_t gmask = (NG == 1) ? FULL : (((1u << RP) - 1u) << (lane & ~(RP - 1)));
     const uint32_t glt = ((1u << lane) - 1u) & gmask;
-    const uint32_t my_list = desc_s + 8u * G::DCAP * (uint32_t)(lane / RP), my_list_end = my_list + 8u * G::DCAP;
+    const uint32_t my_list = desc_s + 8u * G::DCAP * (uint32_t)(lane / RP);
 
     auto flush = [&]() {
         __syncwarp();
@@ -430,52 +436,48 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
             ops_vecs = ncv;
         }
 
-        // ---- walk: lane = read.  Segments -> descriptors in the row group's lists; D / I events -> global counters.
-        // One iteration takes a match op (opening or extending the lane's segment) and then the op behind it that is
-        // none (which closes the segment: its descriptor goes out with its final length) — the common M I M D M shape
+        // ---- walk: lane = read.  Segments -> descriptors in the row group's list; D / I events -> global counters.
+        // One iteration takes a match op (extending the lane's run of match ops) and then the op behind it that is
+        // none (which ends the run: its descriptor goes out with its final length) — the common M I M D M shape
         // costs one iteration per segment; anything else simply takes another iteration.
         const bool act = lane < n && passes;
         const int x0 = p - w0;
         int x = x0, y = y0;
-        int cntS = 0, cntL = 0;         // descriptors in my group's short / long list (the same in all lanes of the group)
+        int cnt = 0;                    // descriptors in my group's list (the same in all lanes of the group)
         {
             uint32_t cp = act ? ops_lane : rows;
             const uint32_t cend = cp + 4u * (uint32_t)(act ? nops_lane : 0);
             const uint32_t qn = 2u * (sq_lane - seq_s);            // nibble address of the read's first base
-            unsigned long long* const xi = a.xi + w0;
-            const int xi_last = L - w0 - 1;
             const uint32_t rowbase = rows + 4u * (uint32_t)((lane & (RP - 1)) * RS);
             const bool hasseq = lq > 0;         // reads without SEQ ('*': every base reads 'N') count coverage and events only
             uint32_t c0 = lds(cp), c1 = lds(cp + 4);
-            uint32_t prev = 0;          // bit 1: the op before consumed the reference, bit 0: it was a deletion
-            int xo = 0, yo = 0, lo = 0; // the open segment: first column, first query base, length (0: none open)
+            uint32_t pr = 0, pd = 0;    // the op before consumed the reference / was a deletion
+            int xo = x, yo = y, lo = 0; // the current run of match ops: first column, first query base, length (0: none)
             int ym = 0;                 // query index behind the last match op
             uint32_t exmin = 0xffffffffu;       // min over the ops of (len << 4 | op), pads counted as 0: < 16 <=> a pad or a zero-length op
+#pragma unroll 1
             while (__any_sync(FULL, cp < cend)) {
                 const uint32_t f0 = op_flags(c0 & 15u), f1 = op_flags(c1 & 15u);
                 const bool is_m = cp < cend && (f0 & 1u);
-                if (is_m) {
-                    const int l = (int)(c0 >> 4);
-                    if (lo == 0) { xo = x; yo = y; }
-                    lo += l; x += l; y += l; ym = y;
-                    cp += 4; prev = 2u;
-                    exmin = min(exmin, c0);
-                }
+                const int lm = is_m ? (int)(c0 >> 4) : 0;
+                lo += lm; x += lm; y += lm;
+                ym = is_m ? y : ym;
+                exmin = is_m ? min(exmin, c0) : exmin;
+                pr = is_m ? 1u : pr; pd = is_m ? 0u : pd;
+                cp += is_m ? 4u : 0u;
                 const uint32_t c = is_m ? c1 : c0, fl = is_m ? f1 : f0;
-                const bool live = cp < cend;
-                const bool nm = live && !(fl & 1u);
-                const bool closing = lo > 0 && !(live && (fl & 1u));
-                const int kb = xo & 7, E = kb + lo;
-                const bool emit_s = closing && hasseq && E <= 32, emit_l = closing && hasseq && E > 32;
-                const unsigned bs = __ballot_sync(FULL, emit_s), bl = __ballot_sync(FULL, emit_l);
-                if (emit_s || emit_l) {
-                    const uint32_t slot = emit_s ? my_list + 8u * (uint32_t)(cntS + __popc(bs & glt))
-                                                 : my_list_end - 8u * (uint32_t)(cntL + __popc(bl & glt) + 1);
-                    sts2(slot, (rowbase + (uint32_t)((xo >> 3) << 2)) | ((uint32_t)E << D_E_SHIFT),
+                const bool more_m = cp < cend && (fl & 1u);     // another match op follows: the run goes on
+                const bool nm = cp < cend && !(fl & 1u);
+                const bool emit = lo > 0 && !more_m && hasseq;
+                const unsigned eb = __ballot_sync(FULL, emit);
+                if (emit) {
+                    const int kb = xo & 7;
+                    sts2(my_list + 8u * (uint32_t)(cnt + __popc(eb & glt)),
+                         (rowbase + (uint32_t)((xo >> 3) << 2)) | ((uint32_t)(kb + lo) << D_E_SHIFT),
                          (qn + (uint32_t)(yo - kb)) | ((uint32_t)kb << D_KB_SHIFT));
                 }
-                cntS += __popc(bs & gmask); cntL += __popc(bl & gmask);
-                if (closing) lo = 0;
+                cnt += __popc(eb & gmask);
+                lo = more_m ? lo : 0;
                 if (nm) {
                     const uint32_t op = c & 15u;
                     const int l = (int)(c >> 4);
@@ -483,15 +485,17 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
                     // X / I events: a deletion's columns count +1 X each; an insertion counts +1 I on its anchor column x - 1 —
                     // and -1 X there when that column belongs to a deletion (it reads "*+n..", not "*").  Without zero-length
                     // ops the anchor exists whenever the previous op consumed the reference; a column past the reference is
-                    // clamped (such a read is a TC_ERR_RANGE, the counts are void).
+                    // clamped (such a read is a TC_ERR_RANGE, the counts are void).  One 64-bit add per event: X is the low,
+                    // I the high half of the column's counter, and 2^32 - 1 is "+1 I, -1 X" (the sums are exact modulo 2^64).
                     const bool is_d = (op == OP_D);
-                    const bool ev = is_d || (op == OP_I && (prev & 2u));
-                    const int col = min(x - (is_d ? 0 : 1), xi_last);
-                    red_xi_if(ev, xi + col, is_d ? 1u : 0u - (prev & 1u), (is_d || (prev & 1u)) ? 0u : 1u);
-                    if (is_d && l > 1) for (int k = x + 1; k <= min(x + l - 1, xi_last); ++k) red_xi_if(true, xi + k, 1u, 0u);
-                    prev = (fl & 2u) | (is_d ? 1u : 0u);
-                    if (fl & 2u) x += l;
-                    if (fl & 4u) y += l;
+                    const bool ev = is_d || (op == OP_I && pr);
+                    const uint32_t col = (uint32_t)min(w0 + x - (is_d ? 0 : 1), L - 1);
+                    red_xi_if(ev, a.xi, col, is_d ? 1u : 0u - pd, (is_d ? 1u : pd) ^ 1u);
+                    if (is_d && l > 1) for (int k = w0 + x + 1; k <= min(w0 + x + l - 1, L - 1); ++k) red_xi_if(true, a.xi, (uint32_t)k, 1u, 0u);
+                    pr = (fl >> 1) & 1u; pd = is_d ? 1u : 0u;
+                    x += (fl & 2u) ? l : 0;
+                    y += (fl & 4u) ? l : 0;
+                    xo = x; yo = y;             // a run can only start behind an op that is no match
                     cp += 4;
                 }
                 c0 = lds(cp); c1 = lds(cp + 4);
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
             const bool over = act && (x > ROWW || (hasseq && ym > lq));
             if (__any_sync(FULL, over || exmin < 16u)) {
                 if (lane == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY);
-                cntS = cntL = 0;
+                cnt = 0;
             }
         }
         const int x_end = x;
@@ -512,31 +516,38 @@ __global__ void __launch_bounds__(fgeom<WC>::WARPS * 32, 1) flat_pileup_kernel(p
         // ---- per row group: expand its descriptors into its rows (lane = descriptor), then sum the rows (lane = row words)
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            const int ns = __shfl_sync(FULL, cntS, g * RP), nl = __shfl_sync(FULL, cntL, g * RP);
-            if (ns + nl == 0) continue;
-            const uint32_t list = desc_s + 8u * G::DCAP * (uint32_t)g, list_end = list + 8u * G::DCAP;
-            // short segments: 4 row words each, no branches (lanes without a descriptor run on an empty one)
+            const int ns = __shfl_sync(FULL, cnt, g * RP);
+            if (ns == 0) continue;
+            const uint32_t list = desc_s + 8u * G::DCAP * (uint32_t)g;
+            // every segment: its first 4 row words, no branches (lanes without a descriptor run on an empty one).  What is
+            // left of a longer segment goes to the LONG list — which grows, in place, over the slots already consumed
+            int nl = 0;
+#pragma unroll 1
             for (int h = lane; h < ns + lane; h += 32) {
                 uint2 d = make_uint2(rows, 0u);
                 if (h < ns) d = lds2(list + 8u * (uint32_t)h);
                 emit_words<4>(d, seq_s, lut);
+                const bool more = (d.x >> D_E_SHIFT) > 32u;
+                const unsigned mb = __ballot_sync(FULL, more);
+                if (more) sts2(list + 8u * (uint32_t)(nl + __popc(mb & ((1u << lane) - 1u))), d.x + 16u - (32u << D_E_SHIFT), (d.y & 0xffffu) + 32u);
+                nl += __popc(mb);
             }
-            // long segments: 8 row words per iteration; what is left of a still longer one goes back into the slots this
-            // iteration consumed (the list is stored from the back of the buffer: entry k at list_end - 8 (k + 1))
+            __syncwarp();
+            // long segments: 8 more row words per iteration; what is left of a still longer one goes back into the slots the
+            // iteration consumed (the list is its own work queue and never grows)
+#pragma unroll 1
             for (int h = 0; h < nl;) {
-                const int cnt = min(32, nl - h);
+                const int c32 = min(32, nl - h);
                 uint2 d = make_uint2(rows, 0u);
-                if (lane < cnt) d = lds2(list_end - 8u * (uint32_t)(h + lane + 1));
+                if (lane < c32) d = lds2(list + 8u * (uint32_t)(h + lane));
                 emit_words<8>(d, seq_s, lut);
                 const bool more = (d.x >> D_E_SHIFT) > 64u;
                 const unsigned mb = __ballot_sync(FULL, more);
                 const int k = __popc(mb);
-                if (more) sts2(list_end - 8u * (uint32_t)(h + cnt - k + __popc(mb & ((1u << lane) - 1u)) + 1),
-                               d.x + 32u - (64u << D_E_SHIFT), (d.y & 0xffffu) + 64u);
-                h += cnt - k;
+                if (more) sts2(list + 8u * (uint32_t)(h + c32 - k + __popc(mb & ((1u << lane) - 1u))), d.x + 32u - (64u << D_E_SHIFT), (d.y & 0xffffu) + 64u);
+                h += c32 - k;
                 __syncwarp();
             }
-            __syncwarp();
             // column sum: lane owns row words NW * lane .. NW * lane + NW - 1, all RP rows of the group
             const int ng = min(n - g * RP, RP);
 #pragma unroll
