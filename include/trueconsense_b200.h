@@ -99,7 +99,7 @@ typedef struct tc_pileup_params {
     int32_t  min_base_quality;  /* entries with qual < this are skipped. BuildIndex: 0; ExtractInserts: 13 */
     int32_t  ignore_orphans;    /* skip PAIRED && !PROPER_PAIR reads. BuildIndex (nofilter): 0; ExtractInserts: 1 */
     int64_t  max_depth;         /* BuildIndex: 10000000; ExtractInserts: 8000 */
-    int32_t  kernel;            /* 0 = library's choice; 1 = scatter (smem atomics); 2 = SWAR, CTA-wide tiles; 3 = SWAR, one warp per read stream;
+    int32_t  kernel;            /* 0 = library's choice; 1 = scatter (smem atomics); 3 = bit-parallel, one warp per read stream;
                                    4 = long reads: cut into pieces, then 3 */
     int32_t  reserved;          /* must be 0 (bit 0 is used by the library when it re-enters itself) */
 } tc_pileup_params_t;

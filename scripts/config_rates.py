@@ -18,8 +18,8 @@ for idx, scale in ((0, 1.0), (1, 1.0), (2, 1.0), (3, 0.1), (4, 0.5)):
     out = torch.empty((8, L), dtype=torch.int32, device="cuda")
     bases = b.count_aligned_bases(0x4)
     for kernel in KERNELS:
-        if idx == 4 and kernel in (3, 5):
-            kernel = 4 if kernel == 5 else 6     # long reads: pieces through variant 5 (kernel 4) / variant 3 (kernel 6)
+        if idx == 4 and kernel == 3:
+            kernel = 4                           # long reads: pieces through variant 3
         p = gpu.buildindex_params(kernel)
         for _ in range(3):
             ctx.pileup_counts(dev, L, p, out=out)

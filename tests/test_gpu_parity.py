@@ -15,8 +15,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 pytestmark = pytest.mark.gpu
 
 MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
-KERNELS = [1, 3, 4, 5, 6]   # pileup kernel variants: 1 scatter (smem atomics), 3 warp streams (walk + expand fused), 5 walk / expand / column sum
-                            # as separate loops (default), 4 / 6 pieces of long reads + 5 / 3
+KERNELS = [1, 3, 4]   # pileup kernel variants: 1 scatter (smem atomics), 3 bit-parallel warp streams, 4 pieces of long reads + 3
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +45,7 @@ def _pileup(ctx, b, L, kernel):
     try:
         return ctx.pileup_counts(b, L, gpu.buildindex_params(kernel))
     except gpu.TcError as e:
-        if kernel in (3, 4, 5, 6) and e.code == -8:
+        if kernel in (3, 4) and e.code == -8:
             return ctx.pileup_counts(b, L, gpu.buildindex_params(0))
         raise
 
@@ -84,10 +83,10 @@ def test_pileup_quirk_batch_direct(ctx, orc, kernel):
     assert np.array_equal(got, pileup.pileup_counts(b, fixtures.QUIRK_REF_LEN))
 
 
-@pytest.mark.parametrize("kernel", [3, 5])
+@pytest.mark.parametrize("kernel", [3])
 def test_pileup_warp_kernel_takes_plain_quirks_itself(ctx, orc, kernel):
-    """Variants 3 and 5 decline only pads and zero-length ops (TC_ERR_CAPACITY -> scatter kernel).  Everything else of
-    the quirk set — SEQ '*', IUPAC codes, leading deletions, D/N/I adjacencies, clips, flags — they must take themselves
+    """Variant 3 declines only pads and zero-length ops (TC_ERR_CAPACITY -> scatter kernel).  Everything else of
+    the quirk set — SEQ '*', IUPAC codes, leading deletions, D/N/I adjacencies, clips, flags — it must take itself
     (explicit kernel, no fallback), bit-exact with the oracle."""
     from oracle import fixtures
     from trueconsense_b200 import gpu
@@ -130,16 +129,11 @@ def test_pileup_ops_longer_than_16_bits(ctx, orc):
         ctx.pileup_counts(b2, L, gpu.buildindex_params(3))
     assert e.value.code == -8
     assert np.array_equal(ctx.pileup_counts(b2, L, gpu.buildindex_params(0)), exp2)
-    # variant 5 reads the raw 32-bit ops: no limit on an op's length, nothing to decline
-    assert np.array_equal(ctx.pileup_counts(b, L, gpu.buildindex_params(5)), exp)
-    assert np.array_equal(ctx.pileup_counts(b2, L, gpu.buildindex_params(5)), exp2)
 
-
-@pytest.mark.parametrize("kernel", [3, 5])
+@pytest.mark.parametrize("kernel", [3])
 @pytest.mark.parametrize("span,seed", [(390, 1), (390, 2), (200, 3), (880, 4), (880, 5)])
 def test_pileup_phase_boundaries_fuzz(ctx, orc, span, seed, kernel):
-    """Variant 3 walks a window in phases of 256 columns; variant 5 cuts segments into pieces of a few row words and
-    sums the rows of a 512- / 1024-column window in groups of 16.  Reads that all start within a few columns of each other
+    """Variant 3 walks a window in phases of 256 columns.  Reads that all start within a few columns of each other
     (one window) with random CIGARs — match ops, deletions and reference skips that end on, start on or straddle
     the phase borders, insertions and clips anywhere — must give the oracle's table, without falling back."""
     from trueconsense_b200 import gpu
@@ -631,9 +625,8 @@ def test_span_bound_hint(ctx, orc):
         assert b.max_ref_span > 0
         nb = copy.copy(b)
         nb.max_ref_span = -1
-        assert np.array_equal(_pileup(ctx, b, len(ref), 3), _pileup(ctx, nb, len(ref), 3))
-        with_hint = _pileup(ctx, b, len(ref), 5)
-        without = _pileup(ctx, nb, len(ref), 5)
+        with_hint = _pileup(ctx, b, len(ref), 3)
+        without = _pileup(ctx, nb, len(ref), 3)
         assert np.array_equal(with_hint, without)
         assert np.array_equal(with_hint, pileup.pileup_counts(b, len(ref), threads=4))
         assert np.array_equal(ctx.depth(b, len(ref)), with_hint[0])
@@ -775,8 +768,7 @@ def test_long_reads_take_the_pieces_path(ctx, orc):
     nb = copy.copy(b)
     nb.max_ref_span = -1
     l0 = ctx.launches
-    assert np.array_equal(ctx.pileup_counts(b, L, gpu.buildindex_params(6)), exp)      # ... the pieces through variant 3
-    assert np.array_equal(ctx.pileup_counts(nb, L), exp)                                # no bound: 5 declines, 4 takes over
+    assert np.array_equal(ctx.pileup_counts(nb, L), exp)                                # no bound: 3 declines, 4 takes over
     assert ctx.launches - l0 < 40
     ref, _, s = _synth("long_reads")
     assert np.array_equal(ctx.pileup_counts(s, len(ref), gpu.buildindex_params(4)), pileup.pileup_counts(s, len(ref), threads=4))

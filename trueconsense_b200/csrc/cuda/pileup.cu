@@ -295,14 +295,12 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     int variant = p->kernel;
     // reads longer than variant 3's widest window are cut into pieces first (variant 4, pileup_long.cu)
     const int LONG_SPAN = 1024 - 8 - 64;
-    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? (a.span_hint > LONG_SPAN ? 4 : 5) : 1;
-    if (variant < 1 || variant > 6 || variant == 2) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
+    if (variant == 0) variant = (!per_entry && tc_pileup_warp_supported(a)) ? (a.span_hint > LONG_SPAN ? 4 : 3) : 1;
+    if (variant != 1 && variant != 3 && variant != 4) return tc_fail(ctx, TC_ERR_ARG, "unknown pileup kernel variant %d", variant);
     if (variant != 1 && per_entry) return tc_fail(ctx, TC_ERR_ARG, "the bit-parallel kernels have no base-quality filter; use kernel=1");
     if (variant != 1 && !tc_pileup_warp_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the bit-parallel kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
-    // 4 / 6: long reads cut into pieces, the pieces piled up by variant 5 / 3
-    a.piece_kernel = variant == 6 ? 3 : 5;
-    const bool is_long = variant == 4 || variant == 6;
-    const bool direct = variant == 3 || variant == 5;
+    const bool is_long = variant == 4;      // long reads cut into pieces, the pieces piled up by variant 3
+    const bool direct = variant == 3;
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
         if (variant != 1) {
@@ -318,7 +316,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
                 TC_LAUNCH_CHECK();
             }
             a.pieces = nullptr; a.piece_order = nullptr; a.n_pieces = 0;
-            rc = is_long ? tc_pileup_long_launch(ctx, a, s) : variant == 3 ? tc_pileup_warp_launch(ctx, a, s) : tc_pileup_flat_launch(ctx, a, s);
+            rc = is_long ? tc_pileup_long_launch(ctx, a, s) : tc_pileup_warp_launch(ctx, a, s);
             if (rc) return rc;
         } else {
             int n_chunks = (int)((a.r.n + SC_CHUNK - 1) / SC_CHUNK);

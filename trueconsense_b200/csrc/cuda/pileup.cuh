@@ -34,7 +34,6 @@ struct pileup_args {
     const tc_piece* pieces;
     const uint32_t* piece_order;
     int64_t n_pieces;
-    int32_t piece_kernel;   // which kernel runs over the pieces: 3 (pileup_warp.cu) or 5 (pileup_flat.cu)
 };
 
 __device__ __forceinline__ bool read_passes(const pileup_args& a, int64_t r) {
@@ -54,7 +53,3 @@ bool tc_pileup_warp_supported(const pileup_args& a);
 int tc_pileup_long_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);
 int tc_pileup_warp_launch_pieces(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);
 
-// variant 5 (pileup_flat.cu): walk (lane = read) / expand (lane = segment) / column sum (lane = row words) as separate
-// loops of a warp over its sub-tile; fills every row except coverage.  Same requirements as variant 3.
-int tc_pileup_flat_launch(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);
-int tc_pileup_flat_launch_pieces(tc_ctx* ctx, const pileup_args& a, cudaStream_t s);

@@ -259,5 +259,5 @@ int tc_pileup_long_launch(tc_ctx* ctx, const pileup_args& a0, cudaStream_t s) {
     a.pieces = pieces; a.piece_order = idx_out; a.n_pieces = (int64_t)NP;
     a.r.cigar = pcig;
     a.span_hint = 0;
-    return a.piece_kernel == 3 ? tc_pileup_warp_launch_pieces(ctx, a, s) : tc_pileup_flat_launch_pieces(ctx, a, s);
+    return tc_pileup_warp_launch_pieces(ctx, a, s);
 }

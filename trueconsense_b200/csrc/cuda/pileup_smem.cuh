@@ -1,4 +1,4 @@
-// pileup_smem.cuh — device helpers shared by the warp-stream pileup kernels (pileup_warp.cu, pileup_flat.cu):
+// pileup_smem.cuh — device helpers shared by the warp-stream pileup kernels (pileup_warp.cu):
 // CIGAR op classes, carry-save adders, one-hot checks of packed base codes, explicit shared-window
 // loads / stores / reductions, and TMA bulk copies (cp.async.bulk) completing on an mbarrier.  sm_100a only.
 #pragma once
@@ -40,6 +40,16 @@ __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.s
 // is a deletion's last column (that column reads "*+n..", no longer "*").
 __device__ __forceinline__ void red_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// red.shared.or of a word that has any bit set (predicated, no branch): an empty word costs no shared-memory cycle
+__device__ __forceinline__ void reds_or_nz(uint32_t a, uint32_t v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(a), "r"(v) : "memory");
+}
+// X | I event: one 64-bit add to column col's packed counter (X in the low, I in the high 32 bits), predicated.  lo = 1: +1 X;
+// hi = 1: +1 I; lo = 2^32 - 1, hi = 0: +1 I and -1 X (the carry does it; the sums are exact modulo 2^64).
+__device__ __forceinline__ void red_xi_if(bool p, unsigned long long* xi, uint32_t col, uint32_t lo, uint32_t hi) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 v, q;\n\tsetp.ne.u32 p, %0, 0;\n\tmov.b64 v, {%3, %4};\n\tmad.wide.u32 q, %2, 8, %1;\n\t@p red.global.add.u64 [q], v;\n\t}"
+                 ::"r"((uint32_t)p), "l"(xi), "r"(col), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ uint4 lds4(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
 }

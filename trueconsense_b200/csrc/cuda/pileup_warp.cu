@@ -115,7 +115,7 @@ struct lane_walk {
 // lane did anything (the rows are then summed).
 template <int ROWW, int CW, bool LIMIT>
 __device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uint32_t rowp, const int xlim,
-                                           uint32_t* xi, const int xi_n, const uint32_t sq, int* err) {
+                                           unsigned long long* xi, const int xi_n, const uint32_t sq, int* err) {
     bool any_iter = false;
     // LIMIT: the phase ends at column xlim (otherwise it runs to the end of the reads and xlim plays no part)
     while (__any_sync(FULL, (s.cp < s.cend || s.rem > 0) && (!LIMIT || s.x < xlim))) {
@@ -132,11 +132,11 @@ __device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uin
                 // the reference is clamped (such a read is a TC_ERR_RANGE, the counts are void).
                 const bool is_d = (op == OP_D);
                 const bool ev = is_d || (op == OP_I && (s.prev & 2u));
-                const int col = min(is_d ? s.x : s.x - 1, xi_n - 1);
-                uint32_t* cell = xi + 2 * col;               // [0] X, [1] I
-                if (ev) red_u32(cell + (is_d ? 0 : 1), 1u);
-                if (ev && !is_d && (s.prev & 1u)) red_u32(cell, 0xffffffffu);
-                if (is_d && l > 1) for (int k = s.x + 1; k < min(s.x + l, xi_n); ++k) red_u32(xi + 2 * k, 1u);
+                const uint32_t col = (uint32_t)min(is_d ? s.x : s.x - 1, xi_n - 1);
+                const uint32_t pd = s.prev & 1u;
+                // one 64-bit add per event: +1 X, +1 I, or "+1 I, -1 X" (2^32 - 1; exact modulo 2^64)
+                red_xi_if(ev, xi, col, is_d ? 1u : 0u - pd, (is_d ? 1u : pd) ^ 1u);
+                if (is_d && l > 1) for (int k = s.x + 1; k < min(s.x + l, xi_n); ++k) red_xi_if(true, xi, (uint32_t)k, 1u, 0u);
                 s.prev = (fl & 2u) | (is_d ? 1u : 0u);
                 if (fl & 2u) s.x += l;
                 if (fl & 4u) s.y += l;
@@ -167,8 +167,7 @@ __device__ __forceinline__ bool emit_phase(lane_walk& s, const int lq, const uin
                 const int rem4 = 4 * (kb + cl);                     // 4 * columns from the first row word's start to the chunk's end
                 const uint32_t ro = rowp + (uint32_t)((x >> 3) << 2);
                 reds_or(ro, __funnelshift_l(w[1], w[0], sh4) & (0xffffffffu >> (4 * kb)) & ~__funnelshift_rc(0xffffffffu, 0u, rem4));
-                // words behind the chunk's end get an empty mask (a cut at xlim may leave them past the row: they
-                // land, as zeros, in the pad / the next row / the SEQ pad — inside the warp's slice)
+                // words behind the chunk's end get an empty mask and are not written
 #pragma unroll
                 for (int j = 1; j < CW; ++j)
                     reds_or(ro + 4 * j, __funnelshift_l(w[j + 1], w[j], sh4) & ~__funnelshift_rc(0xffffffffu, 0u, max(rem4 - 32 * j, 0)));
@@ -636,7 +635,7 @@ __global__ void __launch_bounds__(geom<WC>::WARPS * 32, 1) warp_pileup_kernel(pi
 #pragma unroll
         for (int ph = 0; ph < NPH; ++ph) {
             const int xlim = (ph == NPH - 1) ? INT_MAX : 8 * PW * (ph + 1);      // the last phase runs to the end of the reads
-            const bool did = emit_phase<ROWW, CHUNK_WORDS, (NPH > 1)>(st, lq, row - 4u * PW * ph, xlim, reinterpret_cast<uint32_t*>(a.xi + w0), L - w0, sq, &a.status->err);
+            const bool did = emit_phase<ROWW, CHUNK_WORDS, (NPH > 1)>(st, lq, row - 4u * PW * ph, xlim, a.xi + w0, L - w0, sq, &a.status->err);
             __syncwarp();
             if (!did) continue;
             // column sum: lane owns row words lane + 32 k of the phase, all 32 rows
