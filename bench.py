@@ -137,8 +137,11 @@ def make_sample(scale: float, sample: int):
     return w, batch
 
 
-def hot_path(ctx, reads, L, mincov, counts_dev, table, flags_dev, stream, params=None):
-    """One pass: pileup -> call -> insertion candidates -> insertion calls.  Returns the calls."""
+def hot_path(ctx, reads, L, mincov, counts_dev, table, flags_dev, stream, params=None, chained=True):
+    """One pass: pileup -> call -> insertion candidates -> insertion calls.  Returns the calls.
+    chained: tc_pileup_call_inserts (one enqueue, one synchronisation per sample); otherwise the four separate calls."""
+    if chained:
+        return ctx.pileup_call_inserts(reads, L, mincov, True, counts_dev, table, pileup=params, stream=stream)
     ctx.pileup_counts(reads, L, params, out=counts_dev, stream=stream)
     ctx.call_device(counts_dev, L, mincov, True, table, stream=stream)
     cands = ctx.list_insert_candidates(flags_dev, L)
@@ -249,6 +252,10 @@ def run_ours(args):
     ambig = torch.empty(L, dtype=torch.uint8, device="cuda")
     table = gpu.CallTable(call_char.data_ptr(), flags_dev.data_ptr(), xrun.data_ptr(), rank_letter.data_ptr(),
                           rank_count.data_ptr(), ambig.data_ptr())
+    # a second set of outputs: two samples are in flight at a time
+    counts_dev2 = torch.empty_like(counts_dev)
+    out2 = [torch.empty_like(x) for x in (call_char, flags_dev, xrun, rank_letter, rank_count, ambig)]
+    table2 = gpu.CallTable(*[x.data_ptr() for x in out2])
 
     def barrier():
         if world > 1:
@@ -275,9 +282,22 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     ev0.record()
-    for _ in range(args.steps):
-        calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params)
-        kernel_ms.append(ctx.last_pileup_kernel_ms())
+    if args.unchained:
+        for _ in range(args.steps):
+            calls = hot_path(ctx, dev, L, w.mincov, counts_dev, table, flags_dev, stream, params, chained=False)
+            kernel_ms.append(ctx.last_pileup_kernel_ms())
+    else:
+        # one enqueue per sample, and the host's share of a step (unpacking the calls, the next enqueue) behind the device's
+        # work on the next step: step i + 1 is enqueued (same stream, its own count / call tables) before step i is finished
+        ticket = ctx.sample_enqueue(dev, L, w.mincov, True, counts_dev, table, pileup=params, stream=stream)
+        for i in range(1, args.steps + 1):
+            nxt = None
+            if i < args.steps:
+                c2, t2 = (counts_dev2, table2) if i % 2 else (counts_dev, table)
+                nxt = ctx.sample_enqueue(dev, L, w.mincov, True, c2, t2, pileup=params, stream=stream)
+            calls = ctx.sample_finish(ticket)
+            kernel_ms.append(ctx.last_pileup_kernel_ms())
+            ticket = nxt
     ev1.record()
     barrier()
     sampler.close_window()
@@ -370,6 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="pileup kernel variant (0 = library's choice; A/B measurements only)")
+    ap.add_argument("--unchained", action="store_true", help="the four separate calls per step (three synchronisations) instead of tc_sample_enqueue / tc_sample_finish")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 2 M reads of configs[1] (tests only)")
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed passes before the warm-up steps (clock / driver spin-up of a cold GPU)")
     ap.add_argument("--cpu-reads", type=float, default=1_000_000, help="reads in the cpu_baseline sample (1 M reads = 400 M aligned bases, 10-15 s on one core)")

@@ -160,7 +160,8 @@ const char* tc_last_error(const tc_ctx_t* ctx);
 int64_t tc_launch_count(const tc_ctx_t* ctx);
 /* Measurement aid (no counterpart in the reference): when enabled, tc_pileup_counts brackets its
  * dominant kernel (the pileup kernel proper, without memsets / scan / copies) with CUDA events on
- * the launching stream; tc_last_pileup_kernel_ms returns the duration of the most recent one. */
+ * the launching stream; tc_last_pileup_kernel_ms returns the duration of the most recent one (after tc_sample_finish:
+ * of the sample that call finished). */
 /* bytes this context has copied host->device / device->host so far (bench.py's e2e accounting) */
 int  tc_transfer_bytes(const tc_ctx_t* ctx, int64_t* h2d, int64_t* d2h);
 int  tc_ctx_set_timing(tc_ctx_t* ctx, int enabled);
@@ -209,6 +210,30 @@ int  tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len,
  * (cand_pos capacity `cap`; TC_ERR_CAPACITY if more). */
 int  tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_t ref_len,
                                int32_t* cand_pos, int32_t cap, int32_t* n_out, void* stream);
+
+/* ---- one enqueue per sample: (1) -> (4) -> candidates -> (2) chained on the device ----
+ * What TrueConsense.py:225-252 runs as separate steps (BuildIndex, then BuildConsensus -> ListInserts -> ExtractInserts),
+ * for device-resident reads (tc_reads_upload, QUAL included): tc_pileup_counts (params `pileup`) into counts,
+ * tc_call (`call`) into *table, the TC_CF_INS_CANDIDATE positions, and tc_extract_inserts (`inserts`) for exactly those —
+ * with no host round trip in between and ONE synchronisation at the end.  counts and every non-NULL member of *table
+ * must be device pointers (table->flags is required).  calls[calls_cap] / bases[bases_cap] are host buffers;
+ * *n_calls receives the number of candidates (calls[i].pos ascending).  Results and errors are those of the separate
+ * calls in that order; inputs the chained form does not take (host arrays, a base-quality filter in `pileup`, more
+ * than 256 candidates, ...) run through the separate calls internally. */
+int  tc_pileup_call_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* pileup,
+                            const tc_call_params_t* call, const tc_pileup_params_t* inserts, int32_t* counts,
+                            const tc_call_table_t* table, tc_insert_call_t* calls, int32_t calls_cap, int32_t* n_calls,
+                            uint8_t* bases, int64_t bases_cap, void* stream);
+
+/* The same in two halves, so that the host's share of one sample (unpacking the results, preparing the next call) hides
+ * behind the device's work on the next: tc_sample_enqueue returns as soon as everything is enqueued, tc_sample_finish
+ * waits for that sample only.  At most two samples may be in flight on a context, enqueued on the same stream; the reads,
+ * counts and table buffers of a sample must stay valid (and untouched by the caller) until its tc_sample_finish returns. */
+int  tc_sample_enqueue(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* pileup,
+                       const tc_call_params_t* call, const tc_pileup_params_t* inserts, int32_t* counts,
+                       const tc_call_table_t* table, void* stream, int32_t* ticket);
+int  tc_sample_finish(tc_ctx_t* ctx, int32_t ticket, tc_insert_call_t* calls, int32_t calls_cap, int32_t* n_calls,
+                      uint8_t* bases, int64_t bases_cap);
 
 /* ---- multi-GPU: read-range sharding (ultra-deep single sample) ----
  * Sum the count tables of all ranks in place.  `comm` is an ncclComm_t created by the caller

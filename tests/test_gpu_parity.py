@@ -772,3 +772,107 @@ def test_long_reads_take_the_pieces_path(ctx, orc):
     assert ctx.launches - l0 < 40
     ref, _, s = _synth("long_reads")
     assert np.array_equal(ctx.pileup_counts(s, len(ref), gpu.buildindex_params(4)), pileup.pileup_counts(s, len(ref), threads=4))
+
+
+def _chained(ctx, b, L, mincov, dev_reads, pileup=None):
+    import torch
+
+    from trueconsense_b200 import gpu
+
+    counts = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")
+    flags = torch.empty(L, dtype=torch.uint8, device="cuda")
+    cc = torch.empty(L, dtype=torch.uint8, device="cuda")
+    xrun = torch.empty(L, dtype=torch.int32, device="cuda")
+    table = gpu.CallTable(cc.data_ptr(), flags.data_ptr(), xrun.data_ptr(), None, None, None)
+    ins = ctx.pileup_call_inserts(dev_reads, L, mincov, True, counts, table, pileup=pileup)
+    torch.cuda.synchronize()
+    return counts.cpu().numpy(), flags.cpu().numpy(), cc.cpu().numpy(), xrun.cpu().numpy(), ins
+
+
+@pytest.mark.parametrize("name", MINIS)
+def test_chained_sample_equals_separate_calls(ctx, orc, name):
+    """tc_pileup_call_inserts (one enqueue, one synchronisation per sample) == tc_pileup_counts -> tc_call ->
+    tc_list_insert_candidates -> tc_extract_inserts, for device-resident reads and — through its internal fallback —
+    for host arrays; both == the oracle's table."""
+    pileup, _ = orc
+    b = _mini_batch(name)
+    exp = load_golden_counts(name)
+    L = exp.shape[1]
+    mincov = 10
+    counts = ctx.pileup_counts(b, L)
+    res = ctx.call(counts, L, mincov, True)
+    cands = ctx.list_insert_candidates(res.flags, L)
+    sep = ctx.extract_inserts(b, L, cands)
+    for reads in (ctx.upload(b), b):
+        c2, f2, cc2, x2, ins = _chained(ctx, b, L, mincov, reads)
+        assert np.array_equal(c2, counts) and np.array_equal(c2[:7], exp)
+        assert np.array_equal(f2, res.flags) and np.array_equal(cc2, res.call_char) and np.array_equal(x2, res.xrun)
+        assert ins == sep
+        assert [d["pos"] for d in ins] == list(cands)
+
+
+def test_chained_sample_config2_slice_and_fallbacks(ctx, orc):
+    """The chained form on a deep amplicon sample (insertion candidates present, the 8000-read depth cap binding), on a
+    batch the bit-parallel kernel declines (pads -> scatter kernel), and its error reporting."""
+    from oracle import fixtures
+    from trueconsense_b200 import gpu, synth
+
+    pileup, call = orc
+    w = synth.config(1, scale=0.02)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    counts = ctx.pileup_counts(b, L)
+    assert np.array_equal(counts, pileup.pileup_counts(b, L, threads=8))
+    res = ctx.call(counts, L, w.mincov, True)
+    cands = ctx.list_insert_candidates(res.flags, L)
+    assert len(cands) > 0
+    sep = ctx.extract_inserts(b, L, cands)
+    l0 = ctx.launches
+    c2, f2, _, _, ins = _chained(ctx, b, L, w.mincov, ctx.upload(b))
+    assert ctx.launches - l0 <= 16              # nothing ran twice
+    assert np.array_equal(c2, counts) and np.array_equal(f2, res.flags) and ins == sep
+    # pads: variant 3 declines, the chained form redoes the sample through the separate calls
+    q = fixtures.quirk_batch()
+    Lq = fixtures.QUIRK_REF_LEN
+    cq = ctx.pileup_counts(q, Lq)
+    rq = ctx.call(cq, Lq, 2, True)
+    sq = ctx.extract_inserts(q, Lq, ctx.list_insert_candidates(rq.flags, Lq))
+    c3, f3, _, _, ins3 = _chained(ctx, q, Lq, 2, ctx.upload(q))
+    assert np.array_equal(c3, cq) and np.array_equal(f3, rq.flags) and ins3 == sq
+    # errors of the pileup surface from the chained call as they do from tc_pileup_counts
+    from trueconsense_b200.reads import ReadBatch
+
+    unsorted = ReadBatch.from_records([dict(pos=50, cigar="10M", seq="A" * 10), dict(pos=10, cigar="10M", seq="A" * 10)])
+    with pytest.raises(gpu.TcError) as ei:
+        _chained(ctx, unsorted, 100, 2, ctx.upload(unsorted))
+    assert ei.value.code == -3
+
+
+def test_two_samples_in_flight(ctx, orc):
+    """tc_sample_enqueue / tc_sample_finish: two samples in flight on one stream give what they give one at a time; a third
+    enqueue is refused."""
+    import torch
+
+    from trueconsense_b200 import gpu, synth
+
+    w = synth.config(1, scale=0.01)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    dev = ctx.upload(b)
+    ref_counts, ref_flags, _, _, ref_ins = _chained(ctx, b, L, w.mincov, dev)
+    bufs = []
+    for _ in range(2):
+        counts = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")
+        flags = torch.empty(L, dtype=torch.uint8, device="cuda")
+        xrun = torch.empty(L, dtype=torch.int32, device="cuda")
+        bufs.append((counts, flags, gpu.CallTable(None, flags.data_ptr(), xrun.data_ptr(), None, None, None), xrun))
+    t0 = ctx.sample_enqueue(dev, L, w.mincov, True, bufs[0][0], bufs[0][2])
+    t1 = ctx.sample_enqueue(dev, L, w.mincov, True, bufs[1][0], bufs[1][2])
+    with pytest.raises(gpu.TcError):
+        ctx.sample_enqueue(dev, L, w.mincov, True, bufs[0][0], bufs[0][2])
+    for t, (counts, flags, _, _) in zip((t0, t1), bufs):
+        assert ctx.sample_finish(t) == ref_ins
+        assert np.array_equal(counts.cpu().numpy(), ref_counts) and np.array_equal(flags.cpu().numpy(), ref_flags)
+    for i in range(5):          # steady state: enqueue i + 1, finish i
+        t = ctx.sample_enqueue(dev, L, w.mincov, True, bufs[i % 2][0], bufs[i % 2][2])
+        assert ctx.sample_finish(t) == ref_ins

@@ -273,6 +273,20 @@ TC_API int tc_is_ambiguous(tc_ctx_t* ctx, const uint8_t* letters, const int32_t*
     return TC_OK;
 }
 
+// INS_CANDIDATE positions, ascending, left on the device together with their number: [unordered: cap] [count] [sorted: cap]
+int tc_candidates_enqueue(tc_ctx* ctx, const uint8_t* d_flags, int32_t ref_len, int32_t cap, int32_t** d_count, int32_t** d_sorted, cudaStream_t s) {
+    int32_t* d_buf = (int32_t*)tc_dev_buf(ctx, SLOT_TMP_B, 4 * (2 * (size_t)cap + 1) + 64);
+    if (!d_buf) return TC_ERR_NOMEM;
+    int32_t* d_cnt = d_buf + cap;
+    TC_CUDA(cudaMemsetAsync(d_cnt, 0, 4, s));
+    list_candidates_kernel<<<(unsigned)((ref_len + 255) / 256), 256, 0, s>>>(d_flags, ref_len, d_buf, cap, d_cnt);
+    TC_LAUNCH_CHECK();
+    rank_sort_kernel<<<32, 256, 0, s>>>(d_buf, d_cnt, cap, d_cnt + 1);
+    TC_LAUNCH_CHECK();
+    *d_count = d_cnt; *d_sorted = d_cnt + 1;
+    return TC_OK;
+}
+
 TC_API int tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_t ref_len, int32_t* cand_pos, int32_t cap,
                                      int32_t* n_out, void* stream) {
     if (!ctx) return TC_ERR_ARG;
@@ -281,16 +295,9 @@ TC_API int tc_list_insert_candidates(tc_ctx_t* ctx, const uint8_t* flags, int32_
     TC_CUDA(cudaSetDevice(ctx->device));
     int rc;
     const uint8_t* df = (const uint8_t*)tc_stage_in(ctx, SLOT_TMP_A, flags, (size_t)ref_len, s, &rc); if (rc) return rc;
-    // layout: [unordered: cap] [count] [sorted: cap]
-    int32_t* d_buf = (int32_t*)tc_dev_buf(ctx, SLOT_TMP_B, 4 * (2 * (size_t)cap + 1) + 64);
-    if (!d_buf) return TC_ERR_NOMEM;
-    int32_t* d_cnt = d_buf + cap;
-    int32_t* d_sorted = d_cnt + 1;
-    TC_CUDA(cudaMemsetAsync(d_cnt, 0, 4, s));
-    list_candidates_kernel<<<(unsigned)((ref_len + 255) / 256), 256, 0, s>>>(df, ref_len, d_buf, cap, d_cnt);
-    TC_LAUNCH_CHECK();
-    rank_sort_kernel<<<32, 256, 0, s>>>(d_buf, d_cnt, cap, d_sorted);
-    TC_LAUNCH_CHECK();
+    int32_t *d_cnt, *d_sorted;
+    rc = tc_candidates_enqueue(ctx, df, ref_len, cap, &d_cnt, &d_sorted, s);
+    if (rc) return rc;
     // the count and the first candidates come back in one copy (there are rarely more than a handful)
     const int first = cap < 63 ? cap : 63;
     TC_D2H(ctx->host_status, d_cnt, 4 * (size_t)(1 + first), s);

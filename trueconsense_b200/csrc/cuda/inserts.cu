@@ -35,7 +35,9 @@ constexpr int INS_BASES_FIXED = 64;         // inserted characters returned with
 struct ins_args {
     dreads r;
     const int32_t* cand;            // [n_cand] 1-based positions
-    int n_cand;
+    int n_cand;                     // their number — or, with n_cand_dev, the capacity the buffers were sized for
+    const int32_t* n_cand_dev;      // not NULL: the number of candidates lives on the device (tc_pileup_call_inserts: the list comes
+                                    // straight from the call kernel's flags, nothing is read back in between)
     uint32_t flag_filter; int min_mapq, min_bq, ignore_orphans; long long max_depth;
     int32_t span_hint;              // > 0: caller's upper bound of the longest reference span (tc_reads_t.max_ref_span)
     int32_t* range;                 // [n_cand][2] lo, hi read indices: the reads with pos in (c - longest span, c]
@@ -53,6 +55,8 @@ struct ins_args {
     uint8_t* bases_fixed;           // [n_cand][INS_BASES_FIXED] inserted characters of each winner (longer ones: ins_bases_kernel)
     tc_status* status;
 };
+
+__device__ __forceinline__ int ins_ncand(const ins_args& a) { return a.n_cand_dev ? min(*a.n_cand_dev, a.n_cand) : a.n_cand; }
 
 // longest reference span when the caller gave no bound: one thread per read (also checks the sort order)
 __global__ void max_span_kernel(dreads r, tc_status* status) {
@@ -90,7 +94,7 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t* __restrict__ pos,
 __global__ void cand_range_kernel(ins_args a) {
     const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (ci >= a.n_cand) return;
+    if (ci >= ins_ncand(a)) return;
     const int c = a.cand[ci] - 1;
     const int ms = max(a.span_hint > 0 ? a.span_hint : a.status->max_span, 1);
     const int lo = warp_lower_bound(a.r.pos, a.r.n, c - ms + 1, lane);
@@ -144,17 +148,25 @@ __device__ __forceinline__ read_syms read_syms_of(const ins_args& a, uint32_t re
 // and first tiles per candidate (serial, a handful of candidates), then the candidate of every tile.  When the
 // layout does not fit the buffers the host sized speculatively, layout[2] says so and no tile runs.
 __global__ void __launch_bounds__(256) ins_layout_kernel(ins_args a, int64_t* __restrict__ seg_off, int32_t* __restrict__ tile_first,
-                                                         int32_t* __restrict__ tile_cand, int32_t* __restrict__ layout, int64_t slot_cap, int tile_cap) {
+                                                         int32_t* __restrict__ tile_cand, int32_t* __restrict__ layout, int64_t slot_cap, int tile_cap,
+                                                         const tc_status* __restrict__ pileup_status, int32_t* __restrict__ rb_extra) {
     __shared__ int n_tiles_s;
+    const int n_cand = ins_ncand(a);
+    // device-side candidates: their number and positions, and the pileup's status block, travel back with the results
+    if (rb_extra) {
+        if (threadIdx.x == 0) rb_extra[0] = *a.n_cand_dev;
+        if (threadIdx.x < 16) rb_extra[16 + threadIdx.x] = pileup_status ? reinterpret_cast<const int32_t*>(pileup_status)[threadIdx.x] : 0;
+        for (int i = threadIdx.x; i < n_cand; i += blockDim.x) rb_extra[32 + i] = a.cand[i];
+    }
     if (threadIdx.x == 0) {
         int64_t off = 0; int64_t tiles = 0;
-        for (int i = 0; i < a.n_cand; ++i) {
+        for (int i = 0; i < n_cand; ++i) {
             seg_off[i] = off; tile_first[i] = (int32_t)min(tiles, (int64_t)0x7fffffff);
             const int64_t len = a.range[2 * i + 1] - a.range[2 * i];
             off += len; tiles += (len + INS_TILE - 1) / INS_TILE;
         }
-        seg_off[a.n_cand] = off; tile_first[a.n_cand] = (int32_t)min(tiles, (int64_t)0x7fffffff);
-        const bool fits = off <= slot_cap && tiles <= tile_cap;
+        seg_off[n_cand] = off; tile_first[n_cand] = (int32_t)min(tiles, (int64_t)0x7fffffff);
+        const bool fits = off <= slot_cap && tiles <= tile_cap && !(a.n_cand_dev && *a.n_cand_dev > a.n_cand);
         layout[0] = fits ? (int32_t)tiles : 0;
         layout[1] = (int32_t)min(off, (int64_t)0x7fffffff);
         layout[2] = fits ? 0 : 1;
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(256) ins_layout_kernel(ins_args a, int64_t* __
     }
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles_s; t += blockDim.x) {
-        int lo = 0, hi = a.n_cand - 1;          // last candidate whose first tile is <= t
+        int lo = 0, hi = n_cand - 1;            // last candidate whose first tile is <= t
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_first[mid] <= t) lo = mid; else hi = mid - 1; }
         tile_cand[t] = lo;
     }
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_c
     __shared__ unsigned long long best_s;
     __shared__ int over_s, hashed_s;
     const int ci = blockIdx.x;
+    if (ci >= ins_ncand(a)) return;
     if (a.layout && a.layout[2]) return;        // the speculative layout did not fit: the host sizes it and runs again
     const int64_t off = a.seg_off[ci];
     const int lo = a.range[2 * ci];
@@ -581,7 +594,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst;
     if (spec) {
         a.layout = d_layout;
-        ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT);
+        ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT, nullptr, nullptr);
         ctx->launches++;
     } else {
         a.layout = nullptr;
@@ -712,4 +725,111 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
 #undef INS_CUDA
     if (rc == TC_OK) { cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) rc = tc_cuda_fail(ctx, le, "insert kernels"); }
     return rc;
+}
+
+
+// ---------------------------------------------------------------- candidates that never leave the device
+// tc_pileup_call_inserts (sample.cu): the candidate list is what the call kernel flagged; its length is only known on
+// the device.  Everything is enqueued for up to `cap` candidates into buffers sized from earlier calls, and ONE block
+// of results travels back: the insertion calls, the candidate list, and the pileup's status.  Whatever does not fit this
+// speculative layout (more candidates than cap, more entry slots than the buffers hold, a column with thousands of
+// distinct strings, an insertion longer than INS_BASES_FIXED characters) is reported as TC_ERR_CAPACITY in `fit` and the
+// caller runs tc_extract_inserts with the list it got back.
+int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* d_cand, const int32_t* d_ncand, int cap,
+                           const tc_pileup_params_t* p, const tc_status* d_pileup_status, void* host_block, cudaStream_t s, tc_ins_pending* pend) {
+    ins_args a;
+    memset(&a, 0, sizeof(a));
+    memset(pend, 0, sizeof(*pend));
+    int rc = tc_resolve_reads(ctx, reads, &a.r, NEED_QUAL, s);       // every array is a device pointer already: nothing is copied
+    if (rc) return rc;
+    const int64_t n = a.r.n;
+    const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_EXTRA = 128;      // extra: [0] n_cand, [16..32) pileup status, [32..32+cap) candidates
+    const size_t rb_seg = RB_EXTRA + 4 * (32 + (size_t)cap);
+    const size_t rb_calls = rb_seg + ((4 * ((size_t)cap + 1) + 15) & ~(size_t)15);
+    const size_t rb_fixed = rb_calls + sizeof(tc_insert_call_t) * (size_t)cap;
+    const size_t rb_bytes = rb_fixed + (size_t)cap * INS_BASES_FIXED;
+    if (rb_bytes > TC_HOST_SCRATCH) return tc_fail(ctx, TC_ERR_ARG, "candidate capacity %d too large for the pinned results block", cap);
+    uint8_t* d_rb = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_E, rb_bytes + 16);
+    int32_t* d_range = (int32_t*)tc_dev_buf(ctx, SLOT_INS_B, 24 * (size_t)cap);
+    if (!d_rb || !d_range) return TC_ERR_NOMEM;
+    TC_CUDA(cudaMemsetAsync(d_rb, 0, rb_calls, s));
+    a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
+    a.status = (tc_status*)d_rb;
+    if (a.span_hint == 0 && n > 0) {
+        max_span_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.r, a.status);
+        TC_LAUNCH_CHECK();
+    }
+    a.cand = d_cand; a.n_cand = cap; a.n_cand_dev = d_ncand; a.range = d_range; a.range_off = (uint32_t*)(d_range + 2 * (size_t)cap);
+    a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality; a.ignore_orphans = p->ignore_orphans;
+    a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
+    cand_range_kernel<<<(cap + 3) / 4, 128, 0, s>>>(a);
+    TC_LAUNCH_CHECK();
+    if (ctx->ins_slot_cap <= 0) ctx->ins_slot_cap = 1 << 16;
+    const size_t T = (size_t)ctx->ins_slot_cap, NT = T / INS_TILE + (size_t)cap + 1;
+    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)cap + 1) * 16 + 256 + 16;
+    uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
+    if (!slab) return TC_ERR_NOMEM;
+    uint64_t* d_key = (uint64_t*)slab;
+    int64_t* d_off = (int64_t*)(d_key + T);
+    a.ent_indel = (int32_t*)(d_off + cap + 1); a.ent_qpos = a.ent_indel + T;
+    int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
+    a.tile_sel = d_tfirst + cap + 1; a.tile_last = a.tile_sel + NT;
+    a.seg_count = (int32_t*)(d_rb + rb_seg); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    int32_t* d_layout = (int32_t*)(d_rb + RB_LAYOUT);
+    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.bases_fixed = d_rb + rb_fixed;
+    a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst; a.layout = d_layout;
+    ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT, d_pileup_status, (int32_t*)(d_rb + RB_EXTRA));
+    TC_LAUNCH_CHECK();
+    if (n > 0) {
+        ins_select_kernel<<<(unsigned)NT, INS_TILE, 0, s>>>(a);
+        TC_LAUNCH_CHECK();
+        ins_admit_kernel<<<(unsigned)NT, INS_TILE, 0, s>>>(a);
+        TC_LAUNCH_CHECK();
+        const size_t tbl_smem = (size_t)INS_TBL * 16;
+        if (!ctx->ins_attr_set) {
+            TC_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem));
+            ctx->ins_attr_set = 1;
+        }
+        ins_count_kernel<<<cap, 1024, tbl_smem, s>>>(a, (tc_insert_call_t*)(d_rb + rb_calls));
+        TC_LAUNCH_CHECK();
+    }
+    TC_CUDA(cudaMemcpyAsync(host_block, d_rb, rb_bytes, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += (int64_t)rb_bytes;
+    pend->rb_extra = RB_EXTRA; pend->rb_layout = RB_LAYOUT; pend->rb_over = RB_OVER; pend->rb_calls = rb_calls; pend->rb_fixed = rb_fixed;
+    pend->cap = cap; pend->n_reads = n;
+    return TC_OK;
+}
+
+// After the sample's event has completed: unpack its results block.  *fit = 0 when the speculative layout
+// did not hold everything (cands / n_cand are valid all the same whenever n_cand <= cap).
+int tc_inserts_finish_dev(tc_ctx* ctx, const tc_ins_pending* pend, const void* host_block, tc_status* pileup_status, int32_t* cands, int32_t* n_cand,
+                          tc_insert_call_t* calls, uint8_t* bases, int64_t bases_cap, int* fit) {
+    const uint8_t* pin = (const uint8_t*)host_block;
+    const int32_t* extra = (const int32_t*)(pin + pend->rb_extra);
+    tc_status st; memcpy(&st, pin, sizeof(st));
+    memcpy(pileup_status, extra + 16, sizeof(tc_status));
+    int32_t layout[3]; memcpy(layout, pin + pend->rb_layout, 12);
+    int32_t over; memcpy(&over, pin + pend->rb_over, 4);
+    const int n = extra[0];
+    *n_cand = n;
+    *fit = 1;
+    if (n > pend->cap) { *fit = 0; return TC_OK; }
+    memcpy(cands, extra + 32, 4 * (size_t)n);
+    if (layout[2]) { ctx->ins_slot_cap = 2 * (int64_t)layout[1] + 4096; *fit = 0; return TC_OK; }
+    if (over) { *fit = 0; return TC_OK; }
+    if (st.err == TC_ERR_UNSORTED) return tc_fail(ctx, TC_ERR_UNSORTED, "Unsorted input. Pileup aborts");
+    if (st.err) return tc_fail(ctx, st.err, "insertion key collision or device-side failure %d", st.err);
+    memcpy(calls, pin + pend->rb_calls, sizeof(tc_insert_call_t) * (size_t)n);
+    int64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        if (pend->n_reads == 0) { calls[i].pos = cands[i]; calls[i].n_entries = 0; calls[i].mode_count = 0; calls[i].first_read = -1; calls[i].head = 0; calls[i].indel = 0; }
+        if (calls[i].indel > INS_BASES_FIXED) { *fit = 0; return TC_OK; }       // rare: the separate call fetches long insertions
+        if (calls[i].indel > 0) { calls[i].bases_off = need; need += calls[i].indel; } else calls[i].bases_off = -1;
+    }
+    if (need > 0) {
+        if (!bases || need > bases_cap) return tc_fail(ctx, TC_ERR_CAPACITY, "bases buffer too small: need %lld bytes", (long long)need);
+        for (int i = 0; i < n; ++i)
+            if (calls[i].indel > 0) memcpy(bases + calls[i].bases_off, pin + pend->rb_fixed + (size_t)i * INS_BASES_FIXED, (size_t)calls[i].indel);
+    }
+    return TC_OK;
 }

@@ -266,27 +266,27 @@ static int check_common(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, c
     return TC_OK;
 }
 
-TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p,
-                            int32_t* counts, void* stream) {
-    int rc = check_common(ctx, reads, ref_len, p, counts);
-    if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    TC_CUDA(cudaSetDevice(ctx->device));
+// Everything of tc_pileup_counts up to (not including) the read-back of the status block: memsets, the span pass if one is
+// needed, the pileup kernel, the coverage scan.  `counts` may be a host pointer (the table is then built in a context buffer).
+int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p, int32_t* counts, cudaStream_t s,
+                      tc_pileup_pending* pend) {
     const int L = ref_len;
     pileup_args a;
-    rc = tc_resolve_reads(ctx, reads, &a.r, p->min_base_quality > 0 ? NEED_QUAL : 0, s);
+    int rc = tc_resolve_reads(ctx, reads, &a.r, p->min_base_quality > 0 ? NEED_QUAL : 0, s);
     if (rc) return rc;
     const bool out_dev = tc_is_device_ptr(counts);
     int32_t* d_counts = out_dev ? counts : (int32_t*)tc_dev_buf(ctx, SLOT_COUNTS, sizeof(int32_t) * TC_NROWS * (size_t)L);
-    // the coverage difference array and, behind it, variant 3's packed X | I event counters: one buffer, one memset
+    // one buffer, one memset: the status block, the coverage difference array and, behind it, variant 3's packed X | I event counters
     const size_t diff_words = ((size_t)L + 2) & ~(size_t)1;
-    int32_t* d_diff = (int32_t*)tc_dev_buf(ctx, SLOT_DIFF, sizeof(int32_t) * diff_words + 8 * ((size_t)L + 1));
-    tc_status* d_status = (tc_status*)tc_dev_buf(ctx, SLOT_STATUS, sizeof(tc_status));
-    if (!d_counts || !d_diff || !d_status) return TC_ERR_NOMEM;
+    const size_t head_words = 16;                   // tc_status
+    static_assert(sizeof(tc_status) == 64, "tc_status is 16 words");
+    int32_t* d_head = (int32_t*)tc_dev_buf(ctx, SLOT_DIFF, sizeof(int32_t) * (head_words + diff_words) + 8 * ((size_t)L + 1));
+    if (!d_counts || !d_head) return TC_ERR_NOMEM;
+    tc_status* d_status = (tc_status*)d_head;
+    int32_t* d_diff = d_head + head_words;
     TC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * TC_NROWS * (size_t)L, s));
-    TC_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(int32_t) * diff_words + 8 * ((size_t)L + 1), s));
+    TC_CUDA(cudaMemsetAsync(d_head, 0, sizeof(int32_t) * (head_words + diff_words) + 8 * ((size_t)L + 1), s));
     a.xi = (unsigned long long*)(d_diff + diff_words);
-    TC_CUDA(cudaMemsetAsync(d_status, 0, sizeof(tc_status), s));
     a.L = L; a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality;
     a.ignore_orphans = p->ignore_orphans; a.counts = d_counts; a.diff = d_diff; a.status = d_status;
     a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
@@ -301,6 +301,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     if (variant != 1 && !tc_pileup_warp_supported(a)) return tc_fail(ctx, TC_ERR_ARG, "the bit-parallel kernels need 16-byte aligned seq4 / cigar arrays; use kernel=1");
     const bool is_long = variant == 4;      // long reads cut into pieces, the pieces piled up by variant 3
     const bool direct = variant == 3;
+    pend->span_hint = a.span_hint;
     if (a.r.n > 0) {
         if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
         if (variant != 1) {
@@ -315,6 +316,7 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
                 launch_depth_diff(a, reads->n_cigar_ops, s);
                 TC_LAUNCH_CHECK();
             }
+            pend->span_hint = a.span_hint;
             a.pieces = nullptr; a.piece_order = nullptr; a.n_pieces = 0;
             rc = is_long ? tc_pileup_long_launch(ctx, a, s) : tc_pileup_warp_launch(ctx, a, s);
             if (rc) return rc;
@@ -337,15 +339,23 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
         rc = coverage_scan(ctx, d_diff, d_counts, L, d_status, variant != 1 ? a.xi : nullptr, s);
         if (rc) return rc;
     }
-    tc_status st;
-    if (!out_dev) TC_D2H(counts, d_counts, sizeof(int32_t) * TC_NROWS * (size_t)L, s);
-    rc = fetch_status(ctx, d_status, &st, s);
-    if (rc) return rc;
+    pend->d_status = d_status; pend->d_counts = d_counts; pend->variant = variant; pend->per_entry = per_entry ? 1 : 0;
+    pend->out_dev = out_dev ? 1 : 0; pend->n_reads = a.r.n;
+    return TC_OK;
+}
+
+// The host side of tc_pileup_counts once the status block has come back: errors, the depth-cap proof, and the re-run
+// through another kernel variant when the bit-parallel kernel declined the batch.
+int tc_pileup_finish(tc_ctx* ctx, const tc_status& st_in, const tc_pileup_pending* pend, const tc_reads_t* reads, int32_t ref_len,
+                     const tc_pileup_params_t* p, int32_t* counts, void* stream) {
+    tc_status st = st_in;
+    const int variant = pend->variant;
+    const int LONG_SPAN = 1024 - 8 - 64;
     if (st.err == TC_ERR_CAPACITY && variant != 1 && p->kernel == 0) {
-        // reads spanning more than variant 3's window: cut them into pieces (variant 4); anything else the SWAR
+        // reads spanning more than variant 3's window: cut them into pieces (variant 4); anything else the bit-parallel
         // kernels decline (pads in long reads, a single read beyond the staging buffers): the scatter kernel
         tc_pileup_params_t q = *p;
-        q.kernel = (direct && a.span_hint == 0 && st.max_span > LONG_SPAN) ? 4 : 1;
+        q.kernel = (variant == 3 && pend->span_hint == 0 && st.max_span > LONG_SPAN) ? 4 : 1;
         if (q.kernel == 4) {
             const int rc4 = tc_pileup_counts(ctx, reads, ref_len, &q, counts, stream);
             if (rc4 != TC_ERR_CAPACITY) return rc4;
@@ -355,17 +365,33 @@ TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_
     }
     if (st.err == TC_ERR_CAPACITY)
         return tc_fail(ctx, TC_ERR_CAPACITY, "a read exceeds the bit-parallel kernels' windows or staging buffers; use kernel=1 (or 0)");
-    if (per_entry) {
+    if (pend->per_entry) {
         // coverage was counted entry by entry, so max_cov is not the live depth; fall back to the
         // trivial bound (every read live at once)
         st.max_cov = 0;
-        if (p->max_depth > 0 && a.r.n + 1 > p->max_depth && st.err == 0)
+        if (p->max_depth > 0 && pend->n_reads + 1 > p->max_depth && st.err == 0)
             return tc_fail(ctx, TC_ERR_DEPTH_CAP, "%lld reads with a base-quality filter: the depth cap %lld may bind and is not emulated by the bulk kernel",
-                           (long long)a.r.n, (long long)p->max_depth);
+                           (long long)pend->n_reads, (long long)p->max_depth);
     }
     if (st.err == 0 && reads->max_ref_span > 0 && st.max_span > reads->max_ref_span)
         return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t.max_ref_span = %d but a read spans %d reference columns", reads->max_ref_span, st.max_span);
     return status_to_rc(ctx, st, p);
+}
+
+TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p,
+                            int32_t* counts, void* stream) {
+    int rc = check_common(ctx, reads, ref_len, p, counts);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    TC_CUDA(cudaSetDevice(ctx->device));
+    tc_pileup_pending pend;
+    rc = tc_pileup_enqueue(ctx, reads, ref_len, p, counts, s, &pend);
+    if (rc) return rc;
+    tc_status st;
+    if (!pend.out_dev) TC_D2H(counts, pend.d_counts, sizeof(int32_t) * TC_NROWS * (size_t)ref_len, s);
+    rc = fetch_status(ctx, pend.d_status, &st, s);
+    if (rc) return rc;
+    return tc_pileup_finish(ctx, st, &pend, reads, ref_len, p, counts, stream);
 }
 
 TC_API int tc_depth(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p,

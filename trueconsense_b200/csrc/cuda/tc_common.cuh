@@ -39,6 +39,9 @@ struct tc_ctx {
     cudaEvent_t ev0, ev1;
     int ev_valid;
     int64_t ins_slot_cap;   // tc_extract_inserts: entry slots its speculative (no read-back) layout may use; grows on demand
+    struct tc_sample_slot* samples;     // [2] samples in flight (tc_sample_enqueue / tc_sample_finish), allocated on first use
+    int sample_next;
+    float finished_ms;      // timing on: pileup-kernel duration of the sample tc_sample_finish returned last (< 0: none)
 };
 
 // device-side status block written by kernels, read back once per call
@@ -95,6 +98,30 @@ struct dreads {
 #define DEFER_CIGAR 8
 #define DEFER_QUAL  16
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s);
+
+// ---- pieces of the entry points that only ENQUEUE (tc_pileup_call_inserts chains them without a host round trip)
+struct tc_pileup_pending {      // what tc_pileup_finish needs once the status block is on the host
+    tc_status* d_status; int32_t* d_counts; int variant; int per_entry; int out_dev; int64_t n_reads; int32_t span_hint;
+};
+int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p, int32_t* counts, cudaStream_t s,
+                      tc_pileup_pending* pend);
+int tc_pileup_finish(tc_ctx* ctx, const tc_status& st, const tc_pileup_pending* pend, const tc_reads_t* reads, int32_t ref_len,
+                     const tc_pileup_params_t* p, int32_t* counts, void* stream);
+int tc_candidates_enqueue(tc_ctx* ctx, const uint8_t* d_flags, int32_t ref_len, int32_t cap, int32_t** d_count, int32_t** d_sorted, cudaStream_t s);
+struct tc_ins_pending { size_t rb_extra, rb_layout, rb_over, rb_calls, rb_fixed; int cap; int64_t n_reads; };
+int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* d_cand, const int32_t* d_ncand, int cap,
+                           const tc_pileup_params_t* p, const tc_status* d_pileup_status, void* host_block, cudaStream_t s, tc_ins_pending* pend);
+int tc_inserts_finish_dev(tc_ctx* ctx, const tc_ins_pending* pend, const void* host_block, tc_status* pileup_status, int32_t* cands, int32_t* n_cand,
+                          tc_insert_call_t* calls, uint8_t* bases, int64_t bases_cap, int* fit);
+// a sample in flight
+struct tc_sample_slot {
+    int state;                      // 0 free, 1 chained and enqueued, 2 to be run through the separate calls at finish time
+    void* host_block;               // pinned, TC_HOST_SCRATCH bytes: this sample's results block
+    cudaEvent_t done, t0, t1;       // t0 / t1: around this sample's pileup kernel when the context's timing is on
+    int timed;
+    tc_reads_t reads; int32_t ref_len; tc_pileup_params_t pp, ip; tc_call_params_t cp; int32_t* counts; tc_call_table_t table; void* stream;
+    tc_pileup_pending pend; tc_ins_pending ipend;
+};
 
 // ---------------------------------------------------------------- device helpers
 enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };

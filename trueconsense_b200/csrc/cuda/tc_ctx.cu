@@ -5,6 +5,7 @@
 #include "tc_common.cuh"
 
 static char g_create_err[512] = "";
+void tc_sample_slots_free(tc_ctx* ctx);     // sample.cu
 
 int tc_fail(tc_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_err;
@@ -151,6 +152,7 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    tc_sample_slots_free(ctx);
     free(ctx);
     return TC_OK;
 }
@@ -175,6 +177,7 @@ TC_API int tc_ctx_set_timing(tc_ctx_t* ctx, int enabled) {
 }
 
 TC_API float tc_last_pileup_kernel_ms(tc_ctx_t* ctx) {
+    if (ctx && ctx->finished_ms > 0.0f) { const float ms = ctx->finished_ms; ctx->finished_ms = -1.0f; return ms; }     // of the sample finished last
     if (!ctx || !ctx->ev_valid) return -1.0f;
     float ms = -1.0f;
     if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;

@@ -104,8 +104,15 @@ def lib() -> C.CDLL:
                                              C.POINTER(InsertCall), vp, i64, vp]
             l.tc_list_insert_candidates.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32), vp]
             l.tc_allreduce_counts.argtypes = [vp, vp, i64, vp, vp]
+            l.tc_pileup_call_inserts.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
+                                                 C.POINTER(PileupParams), vp, C.POINTER(CallTable), C.POINTER(InsertCall), i32,
+                                                 C.POINTER(i32), vp, i64, vp]
+            l.tc_sample_enqueue.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
+                                            C.POINTER(PileupParams), vp, C.POINTER(CallTable), vp, C.POINTER(i32)]
+            l.tc_sample_finish.argtypes = [vp, i32, C.POINTER(InsertCall), i32, C.POINTER(i32), vp, i64]
+            l.tc_sample_enqueue.restype = l.tc_sample_finish.restype = C.c_int
             for name in ("tc_ctx_create", "tc_ctx_destroy", "tc_reads_upload", "tc_pileup_counts", "tc_depth", "tc_call",
-                         "tc_is_ambiguous", "tc_extract_inserts", "tc_list_insert_candidates", "tc_allreduce_counts"):
+                         "tc_is_ambiguous", "tc_extract_inserts", "tc_list_insert_candidates", "tc_allreduce_counts", "tc_pileup_call_inserts"):
                 getattr(l, name).restype = C.c_int
             _lib = l
     return _lib
@@ -301,6 +308,73 @@ class Context:
         if pos.shape[0] == 0:
             return []
         return self._extract_inserts_raw(reads, ref_len, pos, params)
+
+    @staticmethod
+    def _insert_dicts(calls, n: int, bases: np.ndarray):
+        out = []
+        for c in calls[:n]:
+            if c.n_entries == 0:
+                out.append({"pos": c.pos, "n_entries": 0, "string": None, "mode_count": 0, "first_read": -1})
+                continue
+            s = chr(c.head)
+            if c.indel > 0:
+                s += f"+{c.indel}" + bytes(bases[c.bases_off:c.bases_off + c.indel]).decode("ascii")
+            elif c.indel < 0:
+                s += f"-{-c.indel}" + "N" * (-c.indel)
+            out.append({"pos": c.pos, "n_entries": c.n_entries, "string": s, "mode_count": c.mode_count,
+                        "first_read": c.first_read})
+        return out
+
+    def pileup_call_inserts(self, reads, ref_len: int, mincov: int, include_ambig: bool, counts_dev, table: CallTable,
+                            pileup: PileupParams | None = None, inserts: PileupParams | None = None, stream: int = 0,
+                            maxdist: float = 10.0, minority_del_pct: float = 15.0, insert_pct: float = 55.0, cap: int = 256):
+        """One enqueue per sample (tc_pileup_call_inserts): pileup into ``counts_dev``, the call table into ``table``
+        (device pointers), and the ExtractInserts result of every insertion candidate — one synchronisation.
+        Returns the same list of dicts as :meth:`extract_inserts` for :meth:`list_insert_candidates`' positions."""
+        pileup = pileup or buildindex_params()
+        inserts = inserts or extractinserts_params()
+        cp = CallParams(int(mincov), int(bool(include_ambig)), maxdist, minority_del_pct, insert_pct)
+        rs = self._reads_struct(reads)
+        bcap = 1 << 16
+        while True:
+            calls = (InsertCall * max(cap, 1))()
+            bases = np.zeros(bcap, np.uint8)
+            n = C.c_int32(0)
+            rc = self._lib.tc_pileup_call_inserts(self._h, C.byref(rs), int(ref_len), C.byref(pileup), C.byref(cp), C.byref(inserts),
+                                                  _ptr(counts_dev), C.byref(table), calls, cap, C.byref(n), _ptr(bases), bcap, stream)
+            if rc == -8 and n.value > cap:          # more candidates than the caller made room for
+                cap = n.value
+                continue
+            if rc == -8 and bcap < (1 << 30) and n.value <= cap and "bases buffer" in self._lib.tc_last_error(self._h).decode():
+                bcap *= 16
+                continue
+            self._check(rc)
+            return self._insert_dicts(calls, n.value, bases)
+
+    def sample_enqueue(self, reads, ref_len: int, mincov: int, include_ambig: bool, counts_dev, table: CallTable,
+                       pileup: PileupParams | None = None, inserts: PileupParams | None = None, stream: int = 0,
+                       maxdist: float = 10.0, minority_del_pct: float = 15.0, insert_pct: float = 55.0) -> int:
+        """First half of :meth:`pileup_call_inserts` (tc_sample_enqueue): returns a ticket as soon as the sample's work is
+        enqueued.  At most two samples in flight per context, on one stream; their buffers stay valid until
+        :meth:`sample_finish`."""
+        pileup = pileup or buildindex_params()
+        inserts = inserts or extractinserts_params()
+        cp = CallParams(int(mincov), int(bool(include_ambig)), maxdist, minority_del_pct, insert_pct)
+        rs = self._reads_struct(reads)
+        t = C.c_int32(-1)
+        self._check(self._lib.tc_sample_enqueue(self._h, C.byref(rs), int(ref_len), C.byref(pileup), C.byref(cp), C.byref(inserts),
+                                                _ptr(counts_dev), C.byref(table), stream, C.byref(t)))
+        return int(t.value)
+
+    def sample_finish(self, ticket: int, cap: int = 256):
+        """Second half (tc_sample_finish): waits for that sample only and returns its insertion calls."""
+        buf = getattr(self, "_sample_bufs", None)
+        if buf is None or buf[2] < cap:
+            buf = self._sample_bufs = ((InsertCall * max(cap, 1))(), np.zeros(1 << 16, np.uint8), cap)
+        calls, bases, _ = buf
+        n = C.c_int32(0)
+        self._check(self._lib.tc_sample_finish(self._h, int(ticket), calls, cap, C.byref(n), _ptr(bases), bases.shape[0]))
+        return self._insert_dicts(calls, n.value, bases)
 
     def _extract_inserts_raw(self, reads, ref_len: int, pos: np.ndarray, params: PileupParams):
         n = int(pos.shape[0])
