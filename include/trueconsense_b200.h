@@ -78,10 +78,12 @@ typedef struct tc_reads {
     const uint32_t* seq4;       /* [n_seq_words] */
     const uint8_t*  qual;       /* [8*n_seq_words] phred bytes; may be NULL when no pass reads QUAL */
     const uint32_t* cigar;      /* [n_cigar_ops] */
-    /* mate information: reserved for htslib's mate-overlap quality rewriting, which no kernel emulates yet
-     *  — never read and never copied to the device today; may be NULL */
-    const uint64_t* qname_hash; /* [n] any hash of QNAME that is equal for both mates */
-    const int32_t*  mpos;       /* [n] PNEXT (0-based, -1 if unavailable) */
+    /* mate information, read by tc_extract_inserts' emulation of htslib's mate-overlap quality rewriting (pysam's default
+     * ignore_overlaps=True, Events.py:66); all three NULL: no rewriting */
+    const uint64_t* qname_hash; /* [n] a hash of QNAME, equal for all alignments of a template; its low 32 bits should be htslib's
+                                   own string hash of the name (khash X31: h = c0; h = 31 h + c) — which mate keeps its qualities
+                                   is drawn from it */
+    const int32_t*  mpos;       /* [n] PNEXT (0-based); -1 if unavailable, -2 if the mate maps to another reference */
     const int32_t*  isize;      /* [n] TLEN */
     /* optional: an upper bound of the longest reference span (sum of M,=,X,D,N lengths) of any read, which a
      * BAM decoder knows for free; 0 = unknown (the library then finds it with one more pass over the CIGARs).
@@ -101,7 +103,9 @@ typedef struct tc_pileup_params {
     int64_t  max_depth;         /* BuildIndex: 10000000; ExtractInserts: 8000 */
     int32_t  kernel;            /* 0 = library's choice; 1 = scatter (smem atomics); 3 = bit-parallel, one warp per read stream;
                                    4 = long reads: cut into pieces, then 3 */
-    int32_t  reserved;          /* must be 0 (bit 0 is used by the library when it re-enters itself) */
+    int32_t  reserved;          /* bit 0: used by the library when it re-enters itself (pass 0).  Bits 8-9, only read with a base-quality
+                                   filter: mate-overlap quality rewriting — 0 = as htslib >= 1.13 does it (pysam 0.23.3 bundles 1.21),
+                                   1 = off (pysam's ignore_overlaps=False), 2 = as htslib <= 1.12 did (the first mate keeps its quality) */
 } tc_pileup_params_t;
 
 /* ---- per-position call table (struct of arrays, each of length ref_len) ----

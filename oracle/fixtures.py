@@ -178,3 +178,93 @@ def random_walk_case(rng: np.random.Generator) -> dict:
             cols[j] = strings
     return dict(L=L, mincov=mincov, counts=counts[:7].tolist(), gff=feats, columns=cols,
                 include_ambig=bool(rng.random() < 0.6))
+
+
+# ------------------------------------------------------------------ mate overlaps (htslib tweak_overlap_quality)
+OVERLAP_REF_LEN = 200
+OVERLAP_COL = 100           # 0-based column every read below covers; most carry a 2-base insertion behind it
+
+
+def x31_wang_bit(name: str) -> int:
+    """khash's X31 string hash of a QNAME through __ac_Wang_hash, lowest bit: 1 = the first-arrived mate keeps its
+    qualities (htslib >= 1.13 sam.c tweak_overlap_quality).  Written out here, independently of the C oracle."""
+    bs = name.encode()
+    h = bs[0]
+    for ch in bs[1:]:
+        h = (h * 31 + ch) & 0xFFFFFFFF
+    k = h
+    k = (k + (~(k << 15) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    k ^= k >> 10
+    k = (k + (k << 3)) & 0xFFFFFFFF
+    k ^= k >> 6
+    k = (k + (~(k << 11) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    k ^= k >> 16
+    return k & 1
+
+
+def overlap_pair(name, base_a, qa, base_b, qb, cigar_a="41M2I19M", cigar_b="21M2I39M", pos_a=60, pos_b=80, proper=True, ins="TT"):
+    """Two mates that both cover OVERLAP_COL (a: pos_a + 40, b: pos_b + 20 with the default CIGARs) with the given
+    base / quality there; every other base is 'G' with quality 30."""
+    import re
+
+    def mk(pos, cigar, col_base, col_q, flag, mpos, isize):
+        ops = [(int(l), o) for l, o in re.findall(r"(\d+)([MIDNSHP=X])", cigar)]
+        seq, qual, x = [], [], pos
+        for l, o in ops:
+            if o in "M=X":
+                for j in range(l):
+                    hit = (x + j == OVERLAP_COL)
+                    seq.append(col_base if hit else "G"); qual.append(col_q if hit else 30)
+                x += l
+            elif o in "IS":
+                seq += list((ins * l)[:l]); qual += [30] * l
+            elif o in "DN":
+                x += l
+        return dict(pos=pos, cigar=cigar, seq="".join(seq), qual=qual, flag=flag, qname=name, mpos=mpos, isize=isize)
+
+    fa = 1 | (2 if proper else 0) | 0x20 | 0x40
+    fb = 1 | (2 if proper else 0) | 0x10 | 0x80
+    return [mk(pos_a, cigar_a, base_a, qa, fa, pos_b, 100), mk(pos_b, cigar_b, base_b, qb, fb, pos_a, -100)]
+
+
+def overlap_kat_records():
+    """(records sorted by position, expected strings at OVERLAP_COL under ExtractInserts' filters) — the expectations
+    are derived by hand from htslib's rule, not from the C oracle:
+      bases agree      -> the kept mate reads min(200, qa + qb), the other 0
+      bases disagree   -> the better base keeps int(0.8 q), the other 0; equal qualities: the kept mate int(0.8 q)
+      kept mate        -> the first-arrived one iff Wang(X31(QNAME)) is odd
+    min_base_quality = 13 then decides which entries exist."""
+    recs, exp = [], []
+    for i in range(12):         # the unpaired majority: makes the column an insertion candidate
+        recs.append(dict(pos=70, cigar="31M2I19M", seq="G" * 30 + "A" + "TT" + "G" * 19, qual=30, qname=f"solo{i}"))
+        exp.append("A+2TT")
+
+    def keeper(name):
+        return 0 if x31_wang_bit(name) else 1       # index of the mate that keeps its qualities
+
+    cases = [("agree_low", "A", 8, "A", 8), ("agree_high", "A", 30, "A", 30), ("agree_sum_below", "A", 6, "A", 6),
+             ("dis_a_better", "A", 30, "C", 20), ("dis_b_better", "A", 14, "C", 35), ("dis_lost", "A", 15, "C", 10),
+             ("dis_tie", "A", 20, "C", 20), ("dis_tie_lost", "A", 16, "C", 16)]
+    for name, ba, qa, bb, qb in cases:
+        recs += overlap_pair(name, ba, qa, bb, qb)
+        k = keeper(name)
+        strs = {0: f"{ba}+2TT", 1: f"{bb.lower()}+2tt"}          # mate b is on the reverse strand
+        if ba == bb:
+            if min(200, qa + qb) >= 13:
+                exp.append(strs[k])
+        elif qa > qb:
+            if int(0.8 * qa) >= 13:
+                exp.append(strs[0])
+        elif qb > qa:
+            if int(0.8 * qb) >= 13:
+                exp.append(strs[1])
+        elif int(0.8 * qa) >= 13:
+            exp.append(strs[k])
+    # not a proper pair: orphans are skipped by the samtools stepper altogether (ignore_orphans)
+    recs += overlap_pair("orphans", "A", 30, "A", 30, proper=False)
+    # the mate does not cover the column: it is never fetched, nothing is rewritten
+    far = overlap_pair("mate_far", "A", 30, "A", 30, cigar_b="20M", pos_b=120)
+    recs += far
+    exp.append("A+2TT")
+    recs.sort(key=lambda r: r["pos"])
+    return recs, exp

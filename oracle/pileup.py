@@ -67,9 +67,17 @@ def _reads_struct(b) -> OReads:
     s.n_reads = len(b.pos)
     s.n_seq_words = len(b.seq4)
     s.n_cigar_ops = len(b.cigar)
+    keep = []
     for n in ("pos", "flag", "mapq", "l_seq", "seq_off", "cigar_off", "seq4", "qual", "cigar", "qname_hash", "mpos", "isize"):
         a = getattr(b, n, None)
+        if n == "mpos" and a is not None and getattr(b, "tid", None) is not None and getattr(b, "mtid", None) is not None:
+            # the overlap table never pairs a read whose mate maps to another reference (htslib sam.c overlap_push: mtid != tid)
+            other = (b.mtid >= 0) & (b.mtid != b.tid)
+            if other.any():
+                a = np.where(other, np.int32(-2), a).astype(np.int32)
+                keep.append(a)
         setattr(s, n, None if a is None else a.ctypes.data)
+    s._keep = keep
     return s
 
 

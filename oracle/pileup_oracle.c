@@ -17,10 +17,13 @@
  * resolve_cigar2 / bam_plp_set_maxcnt; pysam libcalignmentfile.pyx __advance_nofilter /
  * __advance_samtools; libcalignedsegment.pyx PileupColumn.get_query_sequences,
  * pileup_base_qual_skip, strand_mark_char.
- * NOT restated (documented deviation): the mate-overlap quality rewriting that
- * ignore_overlaps=True enables (htslib tweak_overlap_quality) — it cannot change BuildIndex
- * (min_base_quality=0) and only affects ExtractInserts on columns where both mates of a proper
- * pair overlap.
+ * Also restated: the mate-overlap quality rewriting that pysam's default ignore_overlaps=True enables
+ * (htslib sam.c overlap_push / overlap_remove / tweak_overlap_quality with cigar_iref2iseq_set / _next,
+ * as of htslib >= 1.13: which mate keeps its quality is drawn from a hash of the QNAME, and bases opposite
+ * a deletion in the mate are down-weighted too; oparams_t.reserved bits 8-9 select 1 = off
+ * (ignore_overlaps=False) or 2 = the rule of htslib <= 1.12).  It cannot change BuildIndex
+ * (min_base_quality=0) and is skipped there; it decides which entries of ExtractInserts' columns pass the
+ * min_base_quality=13 test wherever both mates of a proper pair cover the column.
  *
  * The engine below is deliberately the streaming, column-by-column one (a list of live reads,
  * one column emitted at a time, per-read CIGAR cursor) — slow and plain, nothing like the GPU
@@ -63,7 +66,162 @@ typedef struct {
     int64_t read;
     int32_t beg, end;       /* [beg, end) on the reference; end = beg + raw rlen */
     int32_t k, x, y;        /* CIGAR cursor: op index (-1 = untouched), ref coord of op start, query coord */
+    uint8_t* q;             /* base qualities rewritten by tweak_overlap_quality (NULL: the read's own) */
 } node_t;
+
+/* ---------------------------------------------------------------- mate overlaps (htslib sam.c) */
+enum { OLAP_HASH = 0, OLAP_OFF = 1, OLAP_FIRST = 2 };      /* oparams_t.reserved bits 8-9 */
+
+/* khash.h __ac_Wang_hash */
+static inline uint32_t wang_hash(uint32_t key) {
+    key += ~(key << 15); key ^= (key >> 10); key += (key << 3); key ^= (key >> 6); key += ~(key << 11); key ^= (key >> 16);
+    return key;
+}
+
+/* cigar_iref2iseq_set / cigar_iref2iseq_next: walk to the first / next M,=,X base */
+typedef struct { const uint32_t* cig; const uint32_t* end; int64_t icig, iseq, iref; } cwalk_t;
+
+static int iref2iseq_set(cwalk_t* w, int64_t pos) {
+    if (pos < 0) return -1;
+    w->icig = 0; w->iseq = 0; w->iref = 0;
+    while (w->cig < w->end) {
+        int cig = (int)(*w->cig & 15); int64_t ncig = (int64_t)(*w->cig >> 4);
+        if (cig == OP_S) { w->cig++; w->iseq += ncig; w->icig = 0; continue; }
+        if (cig == OP_H || cig == OP_P) { w->cig++; w->icig = 0; continue; }
+        if (cig == OP_M || cig == OP_EQ || cig == OP_X) {
+            pos -= ncig;
+            if (pos < 0) { w->icig = ncig + pos; w->iseq += w->icig; w->iref += w->icig; return OP_M; }
+            w->cig++; w->iseq += ncig; w->icig = 0; w->iref += ncig;
+            continue;
+        }
+        if (cig == OP_I) { w->cig++; w->iseq += ncig; w->icig = 0; continue; }
+        if (cig == OP_D || cig == OP_N) {
+            pos -= ncig;
+            if (pos < 0) pos = 0;
+            w->cig++; w->icig = 0; w->iref += ncig;
+            continue;
+        }
+        return -2;
+    }
+    w->iseq = -1;
+    return -1;
+}
+
+static int iref2iseq_next(cwalk_t* w) {
+    while (w->cig < w->end) {
+        int cig = (int)(*w->cig & 15); int64_t ncig = (int64_t)(*w->cig >> 4);
+        if (cig == OP_M || cig == OP_EQ || cig == OP_X) {
+            if (w->icig >= ncig - 1) { w->icig = -1; w->cig++; continue; }
+            w->iseq++; w->icig++; w->iref++;
+            return OP_M;
+        }
+        if (cig == OP_D || cig == OP_N) { w->cig++; w->iref += ncig; w->icig = -1; continue; }
+        if (cig == OP_I) { w->cig++; w->iseq += ncig; w->icig = -1; continue; }
+        if (cig == OP_S) { w->cig++; w->iseq += ncig; w->icig = -1; continue; }
+        if (cig == OP_H || cig == OP_P) { w->cig++; w->icig = -1; continue; }
+        return -2;
+    }
+    w->iseq = -1; w->iref = -1;
+    return -1;
+}
+
+/* tweak_overlap_quality(a, b): a arrived first.  aq / bq are the two reads' modifiable base qualities. */
+static void tweak_overlap_quality(const oreads_t* R, int64_t ra, uint8_t* aq, int64_t rb, uint8_t* bq, int mode) {
+    const uint32_t* a_first = R->cigar + R->cigar_off[ra]; const uint32_t* b_first = R->cigar + R->cigar_off[rb];
+    cwalk_t a = { a_first, R->cigar + R->cigar_off[ra + 1], 0, 0, 0 };
+    cwalk_t b = { b_first, R->cigar + R->cigar_off[rb + 1], 0, 0, 0 };
+    const int64_t apos = R->pos[ra], bpos = R->pos[rb];
+    const int64_t alq = R->l_seq[ra], blq = R->l_seq[rb];
+    int64_t iref = bpos;
+    a.iref = iref - apos; b.iref = iref - bpos;
+    int a_ret = iref2iseq_set(&a, a.iref);
+    if (a_ret < 0) return;
+    int b_ret = iref2iseq_set(&b, b.iref);
+    if (b_ret < 0) return;
+    /* which read keeps its qualities: a hash of the first-arrived read's name (htslib >= 1.13); always a before */
+    int amul = 1, bmul = 0;
+    if (mode == OLAP_HASH) { if (wang_hash((uint32_t)R->qname_hash[ra]) & 1u) { amul = 1; bmul = 0; } else { amul = 0; bmul = 1; } }
+    for (;;) {
+        while (a_ret >= 0 && a.iref >= 0 && a.iref < iref - apos) a_ret = iref2iseq_next(&a);
+        if (a_ret < 0) break;
+        if (iref < a.iref + apos) iref = a.iref + apos;
+        while (b_ret >= 0 && b.iref >= 0 && b.iref < iref - bpos) b_ret = iref2iseq_next(&b);
+        if (b_ret < 0) break;
+        if (iref < b.iref + bpos) iref = b.iref + bpos;
+        iref++;
+        if (a.iref + apos != b.iref + bpos) {
+            if (mode != OLAP_HASH) continue;            /* htslib <= 1.12: only positions both reads match */
+            /* a deletion in one read: the other catches up, its bases under the deletion are down-weighted */
+            if (a.iref + apos < b.iref + bpos && b.cig > b_first && (int)(*(b.cig - 1) & 15) == OP_D) {
+                int done = 0;
+                do {
+                    if (a.iseq < alq) aq[a.iseq] = amul ? (uint8_t)(aq[a.iseq] * 0.8) : 0;
+                    a_ret = iref2iseq_next(&a);
+                    if (a_ret < 0) { done = 1; break; }
+                } while (a.iref + apos < b.iref + bpos);
+                if (done) return;
+            } else if (a.cig > a_first && (int)(*(a.cig - 1) & 15) == OP_D) {
+                int done = 0;
+                do {
+                    if (b.iseq < blq) bq[b.iseq] = bmul ? (uint8_t)(bq[b.iseq] * 0.8) : 0;
+                    b_ret = iref2iseq_next(&b);
+                    if (b_ret < 0) { done = 1; break; }
+                } while (b.iref + bpos < a.iref + apos);
+                if (done) return;
+            } else continue;                            /* anything else, e.g. a reference skip */
+        }
+        if (a.iseq >= alq || b.iseq >= blq) return;     /* fell off the end of SEQ (upstream: > l_qseq is the error, == reads past it) */
+        if (seq_code(R, ra, (int)a.iseq) == seq_code(R, rb, (int)b.iseq)) {
+            int qual = aq[a.iseq] + bq[b.iseq];
+            if (qual > 200) qual = 200;
+            aq[a.iseq] = (uint8_t)(amul * qual);
+            bq[b.iseq] = (uint8_t)(bmul * qual);
+        } else if (mode == OLAP_HASH) {
+            if (aq[a.iseq] > bq[b.iseq]) { aq[a.iseq] = (uint8_t)(0.8 * aq[a.iseq]); bq[b.iseq] = 0; }
+            else if (aq[a.iseq] < bq[b.iseq]) { bq[b.iseq] = (uint8_t)(0.8 * bq[b.iseq]); aq[a.iseq] = 0; }
+            else { aq[a.iseq] = (uint8_t)(amul * 0.8 * aq[a.iseq]); bq[b.iseq] = (uint8_t)(bmul * 0.8 * bq[b.iseq]); }
+        } else {
+            if (aq[a.iseq] >= bq[b.iseq]) { aq[a.iseq] = (uint8_t)(0.8 * aq[a.iseq]); bq[b.iseq] = 0; }
+            else { bq[b.iseq] = (uint8_t)(0.8 * bq[b.iseq]); aq[a.iseq] = 0; }
+        }
+    }
+}
+
+/* khash olap_hash restated as a plain open-addressing map QNAME hash -> read index of the stored node */
+typedef struct { uint64_t* key; int64_t* val; uint8_t* used; int64_t cap, n; } omap_t;
+static void omap_init(omap_t* m) { m->cap = 1024; m->n = 0; m->key = malloc(m->cap * 8); m->val = malloc(m->cap * 8); m->used = calloc(m->cap, 1); }
+static void omap_free(omap_t* m) { free(m->key); free(m->val); free(m->used); }
+static int64_t omap_find(const omap_t* m, uint64_t k) {
+    int64_t h = (int64_t)((k * 0x9e3779b97f4a7c15ULL) >> 20) & (m->cap - 1);
+    while (m->used[h]) { if (m->key[h] == k) return h; h = (h + 1) & (m->cap - 1); }
+    return -1;
+}
+static void omap_put(omap_t* m, uint64_t k, int64_t v);
+static void omap_grow(omap_t* m) {
+    omap_t o = *m;
+    m->cap = o.cap * 2; m->n = 0; m->key = malloc(m->cap * 8); m->val = malloc(m->cap * 8); m->used = calloc(m->cap, 1);
+    for (int64_t i = 0; i < o.cap; ++i) if (o.used[i]) omap_put(m, o.key[i], o.val[i]);
+    omap_free(&o);
+}
+static void omap_put(omap_t* m, uint64_t k, int64_t v) {
+    if (2 * (m->n + 1) > m->cap) omap_grow(m);
+    int64_t h = (int64_t)((k * 0x9e3779b97f4a7c15ULL) >> 20) & (m->cap - 1);
+    while (m->used[h]) { if (m->key[h] == k) { m->val[h] = v; return; } h = (h + 1) & (m->cap - 1); }
+    m->used[h] = 1; m->key[h] = k; m->val[h] = v; m->n++;
+}
+static void omap_del(omap_t* m, uint64_t k) {
+    int64_t h = omap_find(m, k);
+    if (h < 0) return;
+    m->used[h] = 0; m->n--;
+    /* re-insert the cluster behind the hole */
+    int64_t j = (h + 1) & (m->cap - 1);
+    while (m->used[j]) {
+        uint64_t kk = m->key[j]; int64_t vv = m->val[j];
+        m->used[j] = 0; m->n--;
+        omap_put(m, kk, vv);
+        j = (j + 1) & (m->cap - 1);
+    }
+}
 
 /* what resolve_cigar2 reports for (read, column) */
 typedef struct { int is_del, is_refskip, indel, qpos; } entry_t;
@@ -143,10 +301,10 @@ static char strand_char(char c, int rev) {
 
 /* pysam PileupColumn.get_query_sequences(add_indels=True) for one entry; returns 0 if the entry
  * is skipped by the base-quality test (pileup_base_qual_skip) */
-static int entry_string(const oreads_t* R, int64_t rd, const entry_t* e, int min_bq, sbuf_t* b) {
+static int entry_string(const oreads_t* R, int64_t rd, const uint8_t* node_q, const entry_t* e, int min_bq, sbuf_t* b) {
     int lq = R->l_seq[rd];
     int rev = (R->flag[rd] & 16) != 0;
-    int q = (e->qpos < lq) ? R->qual[8ULL * R->seq_off[rd] + e->qpos] : 0;
+    int q = (e->qpos < lq) ? (node_q ? node_q[e->qpos] : R->qual[8ULL * R->seq_off[rd] + e->qpos]) : 0;
     if (q < min_bq) return 0;
     if (!e->is_del) {
         char c = (e->qpos < lq) ? NT16[seq_code(R, rd, e->qpos)] : 'N';
@@ -192,6 +350,11 @@ static int run_engine(const oreads_t* R, int64_t r0, int64_t r1, const oparams_t
                       int32_t region_start, int32_t region_end, column_cb cb, void* ud) {
     int64_t cap = 1024, nlive = 0;
     node_t* live = malloc(cap * sizeof(node_t));
+    /* pysam's ignore_overlaps=True (its default at both call sites); invisible without a base-quality filter */
+    const int olap_mode = (P->reserved >> 8) & 3;
+    const int olap = olap_mode != OLAP_OFF && P->min_base_quality > 0 && R->qname_hash && R->mpos && R->isize;
+    omap_t omap;
+    if (olap) omap_init(&omap);
     sbuf_t sb = {0, 0, 0};
     int32_t it_pos = 0, max_pos = -1;
     int64_t cnt = 1;            /* htslib mempool count: the tail sentinel */
@@ -206,12 +369,16 @@ static int run_engine(const oreads_t* R, int64_t r0, int64_t r1, const oparams_t
             int64_t w = 0;
             for (int64_t j = 0; j < nlive; ++j) {
                 node_t* nd = &live[j];
-                if (nd->end <= it_pos) { --cnt; continue; }     /* finished: drop (lazy free) */
+                if (nd->end <= it_pos) {                        /* finished: drop (lazy free; overlap_remove by name) */
+                    if (olap) omap_del(&omap, R->qname_hash[nd->read]);
+                    free(nd->q);
+                    --cnt; continue;
+                }
                 if (nd->beg <= it_pos) {
                     entry_t e;
                     resolve(R, nd, it_pos, &e);
                     size_t before = sb.l;
-                    if (entry_string(R, nd->read, &e, P->min_base_quality, &sb)) { sb_putc(&sb, ':'); ++n_plp; }
+                    if (entry_string(R, nd->read, nd->q, &e, P->min_base_quality, &sb)) { sb_putc(&sb, ':'); ++n_plp; }
                     else sb.l = before;
                 }
                 live[w++] = *nd;
@@ -249,8 +416,11 @@ static int run_engine(const oreads_t* R, int64_t r0, int64_t r1, const oparams_t
         }
         if (rd < 0) { eof = 1; continue; }
         /* bam_plp_push */
-        if (R->flag[rd] & 4) continue;                                          /* htslib always drops UNMAP */
-        if (it_pos == R->pos[rd] && cnt > P->max_depth) continue;               /* bam_plp_set_maxcnt */
+        if (R->flag[rd] & 4) { if (olap) omap_del(&omap, R->qname_hash[rd]); continue; }       /* htslib always drops UNMAP */
+        if (it_pos == R->pos[rd] && cnt > P->max_depth) {                       /* bam_plp_set_maxcnt */
+            if (olap) omap_del(&omap, R->qname_hash[rd]);                       /* overlap_remove: by name, whichever mate is stored */
+            continue;
+        }
         int32_t span = 0;
         for (uint32_t k = R->cigar_off[rd]; k < R->cigar_off[rd + 1]; ++k)
             if (consumes_ref((int)(R->cigar[k] & 15))) span += (int32_t)(R->cigar[k] >> 4);
@@ -258,10 +428,33 @@ static int run_engine(const oreads_t* R, int64_t r0, int64_t r1, const oparams_t
         max_pos = R->pos[rd];
         if (R->pos[rd] + span > it_pos) {
             if (nlive == cap) { cap *= 2; live = realloc(live, cap * sizeof(node_t)); }
-            node_t nd; nd.read = rd; nd.beg = R->pos[rd]; nd.end = R->pos[rd] + span; nd.k = -1; nd.x = nd.y = 0;
+            node_t nd; nd.read = rd; nd.beg = R->pos[rd]; nd.end = R->pos[rd] + span; nd.k = -1; nd.x = nd.y = 0; nd.q = NULL;
             live[nlive++] = nd; ++cnt;
+            /* overlap_push: proper pairs with a mapped mate on this reference that can overlap */
+            uint16_t fl = R->flag[rd];
+            int32_t mp = R->mpos[rd];               /* -1: unavailable, -2: the mate is on another reference */
+            int64_t isz = R->isize[rd]; if (isz < 0) isz = -isz;
+            if (olap && !(fl & 8) && (fl & 2) && mp != -2 && !(isz >= 2 * (int64_t)R->l_seq[rd] && mp >= nd.end)) {
+                int64_t h = omap_find(&omap, R->qname_hash[rd]);
+                if (h < 0) {
+                    if (mp >= R->pos[rd] || ((fl & 1) && mp == -1)) omap_put(&omap, R->qname_hash[rd], rd);    /* the mate is still to arrive */
+                } else {
+                    int64_t ra = omap.val[h];
+                    node_t* na = NULL;
+                    for (int64_t j = 0; j < nlive - 1; ++j) if (live[j].read == ra) { na = &live[j]; break; }
+                    if (na) {
+                        node_t* nb = &live[nlive - 1];
+                        if (!na->q) { int lq = R->l_seq[ra]; na->q = malloc(lq > 0 ? lq : 1); memcpy(na->q, R->qual + 8ULL * R->seq_off[ra], lq); }
+                        if (!nb->q) { int lq = R->l_seq[rd]; nb->q = malloc(lq > 0 ? lq : 1); memcpy(nb->q, R->qual + 8ULL * R->seq_off[rd], lq); }
+                        tweak_overlap_quality(R, ra, na->q, rd, nb->q, olap_mode);
+                    }
+                    omap_del(&omap, R->qname_hash[rd]);
+                }
+            }
         }
     }
+    for (int64_t j = 0; j < nlive; ++j) free(live[j].q);
+    if (olap) omap_free(&omap);
     free(live); free(sb.s);
     return rc;
 }

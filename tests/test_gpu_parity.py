@@ -876,3 +876,147 @@ def test_two_samples_in_flight(ctx, orc):
     for i in range(5):          # steady state: enqueue i + 1, finish i
         t = ctx.sample_enqueue(dev, L, w.mincov, True, bufs[i % 2][0], bufs[i % 2][2])
         assert ctx.sample_finish(t) == ref_ins
+
+
+# ---------------------------------------------------------------------------- mate overlaps (htslib tweak_overlap_quality)
+def _column_strings(g):
+    return g["string"], g["n_entries"], g["mode_count"]
+
+
+def _expected_call(pileup, call, b, pos1, **params):
+    kw = dict(pileup.EXTRACTINSERTS)
+    kw.update(params)
+    cols = pileup.pileup_columns(b, region=(pos1 - 1, pos1), **kw)
+    strings = cols[0][1] if cols else ""
+    up = [s.upper() for s in strings] if strings else []
+    if not up:
+        return None, 0, 0
+    cnt = Counter(up)
+    best = max(cnt.values())
+    first = next(s for s in up if cnt[s] == best)
+    return first, len(up), best
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_mate_overlap_rewrite_kat(ctx, orc, mode):
+    """The hand-derived cases of oracle/fixtures.overlap_kat_records through tc_extract_inserts: the column holds exactly the
+    entries htslib's mate-overlap quality rewriting leaves (count and mode), in all three modes of the rewrite, for host
+    arrays (ranges staged) and device-resident reads."""
+    from oracle import fixtures
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, call = orc
+    recs, exp = fixtures.overlap_kat_records()
+    b = ReadBatch.from_records(recs)
+    L = fixtures.OVERLAP_REF_LEN
+    pos1 = fixtures.OVERLAP_COL + 1
+    p = gpu.extractinserts_params()
+    p.reserved = mode << 8
+    want = _expected_call(pileup, call, b, pos1, reserved=mode << 8)
+    if mode == 0:
+        assert want[1] == len(exp)          # ... which the CPU suite has checked against the hand-derived list
+    for make in (lambda: b, lambda: ctx.upload(b)):
+        got = ctx.extract_inserts(make(), L, [pos1], p)[0]
+        assert (got["string"], got["n_entries"], got["mode_count"]) == want
+
+
+def _paired_fuzz_records(rng, n_pairs, L, col):
+    """Proper pairs (and a few triples: a supplementary alignment shares the QNAME) whose mates mostly both cover `col`, with
+    random indels / clips / reference skips around it, random qualities near the threshold of 13 and a good share of
+    disagreeing bases."""
+    recs = []
+
+    def alignment(pos, span_target):
+        ops, x, q = [], pos, 0
+        if rng.random() < 0.2:
+            l = int(rng.integers(1, 6)); ops.append(("S", l)); q += l
+        while x < pos + span_target:
+            l = int(rng.integers(1, 25)); ops.append(("M", l)); x += l; q += l
+            u = rng.random()
+            if u < 0.25:
+                l = int(rng.integers(1, 4)); ops.append(("I", l)); q += l
+            elif u < 0.5:
+                l = int(rng.integers(1, 6)); ops.append(("D", l)); x += l
+            elif u < 0.55:
+                l = int(rng.integers(1, 8)); ops.append(("N", l)); x += l
+            elif u < 0.6:
+                ops += [("D", 1), ("I", 1)]; x += 1; q += 1
+        if ops[-1][0] != "M":
+            ops.append(("M", 2)); x += 2; q += 2
+        return "".join(f"{l}{o}" for o, l in ops), q, x
+
+    for i in range(n_pairs):
+        pa = col - int(rng.integers(5, 60))
+        pb = pa + int(rng.integers(0, 40))
+        ca, qa, ea = alignment(pa, int(rng.integers(40, 90)))
+        cb, qb, eb = alignment(pb, int(rng.integers(40, 90)))
+        name = f"p{i}"
+        proper = rng.random() < 0.9
+        fa = 1 | (2 if proper else 0) | 0x40 | (0x20 if rng.random() < 0.5 else 0)
+        fb = 1 | (2 if proper else 0) | 0x80 | (0x10 if rng.random() < 0.5 else 0)
+        mk = lambda n: "".join("ACGT"[j] for j in rng.choice(4, n, p=[0.7, 0.1, 0.1, 0.1]))
+        mq = lambda n: [int(v) for v in rng.choice([2, 7, 8, 12, 13, 14, 16, 17, 20, 30, 40], n)]
+        isz = eb - pa
+        if rng.random() < 0.1:
+            isz = 1000                              # "no overlap possible, unless some wild cigar"
+        mpa, mpb = pb, pa
+        if rng.random() < 0.05:
+            mpa = -1
+        recs.append(dict(pos=pa, cigar=ca, seq=mk(qa), qual=mq(qa), flag=fa, qname=name, mpos=mpa, isize=isz))
+        recs.append(dict(pos=pb, cigar=cb, seq=mk(qb), qual=mq(qb), flag=fb, qname=name, mpos=mpb, isize=-isz))
+        if rng.random() < 0.08:                     # a supplementary alignment of mate a (same name, passes the stepper's filter)
+            pc = pa + int(rng.integers(0, 30))
+            cc, qc, _ = alignment(pc, 50)
+            recs.append(dict(pos=pc, cigar=cc, seq=mk(qc), qual=mq(qc), flag=fa | 0x800, qname=name, mpos=mpa, isize=isz))
+    recs.sort(key=lambda r: r["pos"])
+    return recs
+
+
+@pytest.mark.parametrize("seed,max_depth", [(1, 8000), (2, 8000), (3, 60), (4, 25)])
+def test_mate_overlap_rewrite_fuzz(ctx, orc, seed, max_depth):
+    """Random overlapping pairs around several columns, with the depth cap binding in two of the cases (a capped mate makes
+    htslib forget the stored one): tc_extract_inserts == the oracle's column (entries, modal string, its count) in every mode."""
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, call = orc
+    rng = np.random.default_rng(300 + seed)
+    L = 400
+    col = 200
+    b = ReadBatch.from_records(_paired_fuzz_records(rng, 150, L, col))
+    positions = [col - 3, col, col + 1, col + 2, col + 9, col + 17]
+    for mode in (0, 1, 2):
+        p = gpu.extractinserts_params()
+        p.reserved = mode << 8
+        p.max_depth = max_depth
+        got = ctx.extract_inserts(b, L, positions, p)
+        for g in got:
+            want = _expected_call(pileup, call, b, g["pos"], reserved=mode << 8, max_depth=max_depth)
+            assert (g["string"], g["n_entries"], g["mode_count"]) == want, (mode, g["pos"])
+        p.kernel = 2            # the sorted form counts the same keys
+        assert [(_column_strings(g)) for g in ctx.extract_inserts(b, L, positions, p)] == [(_column_strings(g)) for g in got]
+
+
+def test_config1_full_size_insertion_inside_mate_overlap(ctx, orc):
+    """BASELINE configs[0] at full size (25 k overlapping 2x150 pairs): count table == oracle, and every insertion candidate's
+    ExtractInserts call == the oracle's column under the mate-overlap rewrite — including an insertion placed where most
+    pairs overlap."""
+    from trueconsense_b200 import gpu, synth
+
+    pileup, call = orc
+    w = synth.config(0, scale=1.0)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    counts = ctx.pileup_counts(b, L)
+    assert np.array_equal(counts, pileup.pileup_counts(b, L, threads=8))
+    res = ctx.call(counts, L, w.mincov, True)
+    cands = ctx.list_insert_candidates(res.flags, L)
+    assert list(cands) == call.insert_candidates(counts.astype(np.int64), w.mincov) and len(cands) > 0
+    got = ctx.extract_inserts(b, L, cands)
+    n_diff = 0
+    for g in got:
+        want = _expected_call(pileup, call, b, g["pos"])
+        assert (g["string"], g["n_entries"], g["mode_count"]) == want, g["pos"]
+        n_diff += want[1] != _expected_call(pileup, call, b, g["pos"], reserved=1 << 8)[1]
+    assert n_diff > 0           # the rewrite does change these columns

@@ -172,3 +172,29 @@ def test_call_table_consistency():
             except KeyError:
                 assert t["flags"][p - 1] & call.CF_XRUN_OFF_END
             assert bool(t["flags"][p - 1] & call.CF_PRIMARY_X) == (call.get_nucleotide(counts, p, 1)[0] == "X")
+
+
+def test_mate_overlap_rewrite_kat():
+    """htslib's mate-overlap quality rewriting (pysam ignore_overlaps=True, the default of Events.py:66) on hand-derived
+    cases: the oracle's ExtractInserts column must hold exactly the strings htslib's rule leaves (oracle/fixtures.py)."""
+    from collections import Counter
+
+    from oracle import fixtures
+    from trueconsense_b200.reads import ReadBatch
+
+    recs, exp = fixtures.overlap_kat_records()
+    b = ReadBatch.from_records(recs)
+    c = fixtures.OVERLAP_COL
+    cols = pileup.pileup_columns(b, region=(c, c + 1), **pileup.EXTRACTINSERTS)
+    assert len(cols) == 1 and cols[0][0] == c
+    assert Counter(cols[0][1]) == Counter(exp)
+    # ignore_overlaps=False: every mate of a proper pair whose own quality passes is there
+    off = pileup.pileup_columns(b, region=(c, c + 1), reserved=1 << 8, **pileup.EXTRACTINSERTS)
+    assert len(off[0][1]) > len(exp)
+    # the rule of htslib <= 1.12: the first-arrived mate always keeps (agreement: the sum; disagreement: the better, a on ties)
+    old = Counter(pileup.pileup_columns(b, region=(c, c + 1), reserved=2 << 8, **pileup.EXTRACTINSERTS)[0][1])
+    # solo reads, mate_far, mate a of agree_low / agree_high / dis_a_better / dis_tie; mate b only where it is the better base
+    assert old["a+2tt"] == 0 and old["A+2TT"] == 12 + 1 + 4 and old["c+2tt"] == 1
+    # BuildIndex (min_base_quality = 0) cannot see any of it
+    full = pileup.pileup_counts(b, fixtures.OVERLAP_REF_LEN)
+    assert full[0, c] == len(recs) - 1          # every read but mate_far's second mate covers the column (orphans included: nofilter)

@@ -22,7 +22,14 @@
 //            key, so a hash collision is reported (TC_ERR_RANGE) and can never silently change a count.
 //            A column with more distinct strings than the table holds falls back to the sorted form:
 //            cub::DeviceSegmentedRadixSort (stable) + run-length encoding (ins_mode_kernel).
-// Not emulated (deviations): htslib's mate-overlap quality rewriting.
+//   pair     (ins_pair_kernel, one CTA per candidate, only with a base-quality filter) htslib's mate-overlap quality
+//            rewriting (pysam's default ignore_overlaps=True: sam.c overlap_push / overlap_remove /
+//            tweak_overlap_quality).  The reads pushed for this column and those the depth cap dropped are grouped by
+//            QNAME hash in a shared-memory table; per name a tiny automaton in file order replays htslib's hash table
+//            (store the first mate, pair it with the next alignment of that name, forget it when a capped read of that
+//            name goes by); for every pair one thread replays tweak_overlap_quality's walk over the two CIGARs and
+//            keeps what it does to the two base qualities this column tests.  Then the quality test, and the
+//            admitted entries are counted.
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "tc_common.cuh"
@@ -48,7 +55,11 @@ struct ins_args {
     int32_t* tile_sel;              // [n_tiles] selected reads in the tile
     int32_t* tile_last;             // [n_tiles] last selected read of the tile, -1 if none
     uint64_t* ent_key; int32_t* ent_indel; int32_t* ent_qpos; uint8_t* ent_head;
-    uint8_t* ent_sel;               // bit 0: selected (fetched and passed by the stepper), bit 1: yields an entry
+    uint8_t* ent_sel;               // bit 0: selected (fetched and passed by the stepper), bit 1: yields an entry (before the base-quality
+                                    // test when min_bq > 0: ins_pair_kernel applies it), bit 2: admitted by the depth cap
+    uint8_t* ent_q;                 // quality of the base the entry's quality test reads
+    uint8_t* pair_q; unsigned long long pair_cap; unsigned long long* pair_bump;   // scratch for the rewritten quality strings of paired reads
+    int olap_mode;                  // mate-overlap rewriting: 0 htslib >= 1.13, 1 off, 2 htslib <= 1.12 (tc_pileup_params_t.reserved bits 8-9)
     int32_t* seg_count;             // [n_cand] admitted entries
     int32_t* overflow;              // [1] some column had more distinct keys than INS_TBL holds
     const int32_t* layout;          // device-built layout (ins_layout_kernel): [0] tiles, [1] slots, [2] 1 = did not fit; NULL: host-built
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
         const uint32_t fl = a.r.flag[r];
         const bool pass = !(fl & (a.flag_filter | 4u)) && !(a.min_mapq > 0 && a.r.mapq && (int)a.r.mapq[r] < a.min_mapq) &&
                           !(a.ignore_orphans && (fl & 1u) && !(fl & 2u));
-        int indel = 0, qpos = 0; char head = 0; uint64_t key = KEY_NONE;
+        int indel = 0, qpos = 0, qv = 0; char head = 0; uint64_t key = KEY_NONE;
         if (pass) {
             // CIGAR walk up to the column.  BAI query: pos < c+1 && endpos > c, where a read without reference
             // span has endpos = pos + 1
@@ -215,8 +226,8 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
                     const bool match = op_is_match(op);
                     qpos = match ? y + (c - x) : y;
                     if (c == x + l - 1) indel = peek_indel(cig, n, k);
-                    const int qv = (qpos < lq) ? (int)a.r.qual[8ull * a.r.seq_off[r] + qpos] : 0;
-                    if (qv >= a.min_bq) {
+                    qv = (qpos < lq) ? (int)a.r.qual[8ull * a.r.seq_off[r] + qpos] : 0;
+                    if (qv >= a.min_bq || a.min_bq > 0) {      // with a filter: decided after the mate-overlap rewriting
                         emit = true;
                         if (match) head = (qpos < lq) ? base_char_upper(seq_code(a.r.seq4 + a.r.seq_off[r], qpos), rev) : 'N';
                         else head = (op == OP_N) ? (rev ? '<' : '>') : '*';
@@ -260,6 +271,7 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
         const int64_t slot = a.seg_off[ci] + (r - lo);
         a.ent_key[slot] = key; a.ent_indel[slot] = indel; a.ent_qpos[slot] = qpos; a.ent_head[slot] = (uint8_t)head;
         a.ent_sel[slot] = (uint8_t)((sel ? 1 : 0) | (emit ? 2 : 0));
+        a.ent_q[slot] = (uint8_t)qv;
     }
     const int nsel = __syncthreads_count(sel);
     int last = __reduce_max_sync(0xffffffffu, sel ? r : -1);
@@ -312,9 +324,245 @@ __global__ void __launch_bounds__(INS_TILE) ins_admit_kernel(ins_args a) {
         const bool first_at_start = prev < 0 || a.r.pos[prev] != a.r.pos[r];
         admitted = first_at_start || rank < a.max_depth;
     }
+    if (a.min_bq > 0) {         // the quality test (after the mate-overlap rewriting) and the count: ins_pair_kernel
+        if (r < hi && admitted) a.ent_sel[slot] = (uint8_t)(es | 4);
+        return;
+    }
     if (emit && !admitted) a.ent_key[slot] = KEY_NONE;
     const int n_adm = __syncthreads_count(emit && admitted);
     if (threadIdx.x == 0 && n_adm) atomicAdd(&a.seg_count[ci], n_adm);
+}
+
+// ---------------------------------------------------------------- mate overlaps (htslib sam.c)
+// khash.h __ac_Wang_hash: which mate keeps its qualities is drawn from it (htslib >= 1.13)
+__device__ __forceinline__ uint32_t wang_hash(uint32_t key) {
+    key += ~(key << 15); key ^= (key >> 10); key += (key << 3); key ^= (key >> 6); key += ~(key << 11); key ^= (key >> 16);
+    return key;
+}
+
+// cigar_iref2iseq_set / cigar_iref2iseq_next: walk to the first / next M,=,X base
+struct cwalk { const uint32_t* cig; const uint32_t* end; long long icig, iseq, iref; };
+
+__device__ int iref2iseq_set(cwalk& w, long long pos) {
+    if (pos < 0) return -1;
+    w.icig = 0; w.iseq = 0; w.iref = 0;
+    while (w.cig < w.end) {
+        const uint32_t cig = *w.cig & 15u; const long long ncig = (long long)(*w.cig >> 4);
+        if (cig == OP_S) { w.cig++; w.iseq += ncig; w.icig = 0; continue; }
+        if (cig == OP_H || cig == OP_P) { w.cig++; w.icig = 0; continue; }
+        if (cig == OP_M || cig == OP_EQ || cig == OP_X) {
+            pos -= ncig;
+            if (pos < 0) { w.icig = ncig + pos; w.iseq += w.icig; w.iref += w.icig; return 0; }
+            w.cig++; w.iseq += ncig; w.icig = 0; w.iref += ncig;
+            continue;
+        }
+        if (cig == OP_I) { w.cig++; w.iseq += ncig; w.icig = 0; continue; }
+        if (cig == OP_D || cig == OP_N) { pos -= ncig; if (pos < 0) pos = 0; w.cig++; w.icig = 0; w.iref += ncig; continue; }
+        return -2;
+    }
+    w.iseq = -1;
+    return -1;
+}
+
+__device__ int iref2iseq_next(cwalk& w) {
+    while (w.cig < w.end) {
+        const uint32_t cig = *w.cig & 15u; const long long ncig = (long long)(*w.cig >> 4);
+        if (cig == OP_M || cig == OP_EQ || cig == OP_X) {
+            if (w.icig >= ncig - 1) { w.icig = -1; w.cig++; continue; }
+            w.iseq++; w.icig++; w.iref++;
+            return 0;
+        }
+        if (cig == OP_D || cig == OP_N) { w.cig++; w.iref += ncig; w.icig = -1; continue; }
+        if (cig == OP_I || cig == OP_S) { w.cig++; w.iseq += ncig; w.icig = -1; continue; }
+        if (cig == OP_H || cig == OP_P) { w.cig++; w.icig = -1; continue; }
+        return -2;
+    }
+    w.iseq = -1; w.iref = -1;
+    return -1;
+}
+
+// tweak_overlap_quality(a, b), a the first-arrived read, replayed literally on scratch copies aq / bq of the two reads' base
+// qualities.  (Only two of the rewritten values matter to a column, but htslib's catch-up around deletions can visit a
+// base twice and then rewrites it from the already rewritten value opposite it — so the whole state is carried.)
+__device__ void tweak_pair(const ins_args& a, uint32_t ra, uint32_t rb, uint8_t* aq, uint8_t* bq, int mode) {
+    const uint32_t* a_first = a.r.cigar + a.r.cigar_off[ra]; const uint32_t* b_first = a.r.cigar + a.r.cigar_off[rb];
+    cwalk wa = {a_first, a.r.cigar + a.r.cigar_off[ra + 1], 0, 0, 0}, wb = {b_first, a.r.cigar + a.r.cigar_off[rb + 1], 0, 0, 0};
+    const long long apos = a.r.pos[ra], bpos = a.r.pos[rb], alq = a.r.l_seq[ra], blq = a.r.l_seq[rb];
+    long long iref = bpos;
+    int a_ret = iref2iseq_set(wa, iref - apos);
+    if (a_ret < 0) return;
+    int b_ret = iref2iseq_set(wb, iref - bpos);
+    if (b_ret < 0) return;
+    int amul = 1, bmul = 0;
+    if (mode == 0) { if (wang_hash((uint32_t)a.r.qname_hash[ra]) & 1u) { amul = 1; bmul = 0; } else { amul = 0; bmul = 1; } }
+    for (;;) {
+        while (a_ret >= 0 && wa.iref >= 0 && wa.iref < iref - apos) a_ret = iref2iseq_next(wa);
+        if (a_ret < 0) break;
+        if (iref < wa.iref + apos) iref = wa.iref + apos;
+        while (b_ret >= 0 && wb.iref >= 0 && wb.iref < iref - bpos) b_ret = iref2iseq_next(wb);
+        if (b_ret < 0) break;
+        if (iref < wb.iref + bpos) iref = wb.iref + bpos;
+        iref++;
+        if (wa.iref + apos != wb.iref + bpos) {
+            if (mode != 0) continue;            // htslib <= 1.12: only positions both reads match
+            if (wa.iref + apos < wb.iref + bpos && wb.cig > b_first && (*(wb.cig - 1) & 15u) == OP_D) {
+                bool done = false;
+                do {        // a deletion in b: a catches up, its bases under the deletion are down-weighted
+                    if (wa.iseq < alq) aq[wa.iseq] = amul ? (uint8_t)((int)aq[wa.iseq] * 4 / 5) : (uint8_t)0;
+                    a_ret = iref2iseq_next(wa);
+                    if (a_ret < 0) { done = true; break; }
+                } while (wa.iref + apos < wb.iref + bpos);
+                if (done) return;
+            } else if (wa.cig > a_first && (*(wa.cig - 1) & 15u) == OP_D) {
+                bool done = false;
+                do {
+                    if (wb.iseq < blq) bq[wb.iseq] = bmul ? (uint8_t)((int)bq[wb.iseq] * 4 / 5) : (uint8_t)0;
+                    b_ret = iref2iseq_next(wb);
+                    if (b_ret < 0) { done = true; break; }
+                } while (wb.iref + bpos < wa.iref + apos);
+                if (done) return;
+            } else continue;
+        }
+        if (wa.iseq >= alq || wb.iseq >= blq) return;
+        const int oa = aq[wa.iseq], ob = bq[wb.iseq];
+        int na, nb;
+        if (seq_code(a.r.seq4 + a.r.seq_off[ra], (int)wa.iseq) == seq_code(a.r.seq4 + a.r.seq_off[rb], (int)wb.iseq)) {
+            const int sum = min(oa + ob, 200);
+            na = amul * sum; nb = bmul * sum;
+        } else if (mode == 0) {
+            if (oa > ob) { na = oa * 4 / 5; nb = 0; }
+            else if (oa < ob) { nb = ob * 4 / 5; na = 0; }
+            else { na = amul * (oa * 4 / 5); nb = bmul * (ob * 4 / 5); }
+        } else {
+            if (oa >= ob) { na = oa * 4 / 5; nb = 0; } else { nb = ob * 4 / 5; na = 0; }
+        }
+        aq[wa.iseq] = (uint8_t)na; bq[wb.iseq] = (uint8_t)nb;
+    }
+}
+
+constexpr int PAIR_TBL = 16384;             // QNAME groups per candidate column (pushed reads <= max_depth + distinct starts)
+
+// overlap_push's conditions on a pushed read: a proper pair whose mate is mapped on this reference and can overlap
+__device__ bool olap_eligible(const ins_args& a, uint32_t r) {
+    const uint32_t fl = a.r.flag[r];
+    if ((fl & 8u) || !(fl & 2u)) return false;
+    const int mp = a.r.mpos[r];
+    if (mp == -2) return false;                         // the mate is on another reference
+    long long isz = a.r.isize[r]; if (isz < 0) isz = -isz;
+    if (isz >= 2ll * a.r.l_seq[r]) {                    // "no overlap possible, unless some wild cigar"
+        int end = a.r.pos[r];
+        for (uint32_t k = a.r.cigar_off[r]; k < a.r.cigar_off[r + 1]; ++k) { const uint32_t c = a.r.cigar[k]; if (op_consumes_ref(c & 15u)) end += (int)(c >> 4); }
+        if (mp >= end) return false;
+    }
+    return true;
+}
+
+// One CTA per candidate.  Events of the column in file order: a pushed read (selected and admitted, with a reference
+// span) or a read the depth cap dropped (htslib calls overlap_remove on it: whatever is stored under its name is
+// forgotten).  They are grouped by QNAME hash; per group the automaton of htslib's olap_hash.
+__global__ void __launch_bounds__(1024) ins_pair_kernel(ins_args a) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    unsigned int* tmin = reinterpret_cast<unsigned int*>(pair_smem);        // [PAIR_TBL] first event of the group + 1 (0: empty)
+    unsigned int* tmax = tmin + PAIR_TBL;                                   // [PAIR_TBL] last event + 1
+    unsigned short* tcnt = reinterpret_cast<unsigned short*>(tmax + PAIR_TBL);  // [PAIR_TBL] events
+    __shared__ int over_s, nadm_s;
+    const int ci = blockIdx.x;
+    if (ci >= ins_ncand(a)) return;
+    if (a.layout && a.layout[2]) return;
+    const int64_t off = a.seg_off[ci];
+    const int lo = a.range[2 * ci];
+    const int n = a.range[2 * ci + 1] - lo;
+    const bool pairing = a.olap_mode != 1 && a.r.qname_hash && a.r.mpos && a.r.isize;
+    if (threadIdx.x == 0) { over_s = 0; nadm_s = 0; }
+    if (pairing) {
+        for (int i = threadIdx.x; i < PAIR_TBL; i += blockDim.x) { tmin[i] = 0u; tmax[i] = 0u; tcnt[i] = 0; }
+        __syncthreads();
+        // an event: pushed (bits 0 and 2, a reference span: its entry bit or a later column) or capped (bit 0 without bit 2)
+        auto is_event = [&](int i, bool& push) -> bool {
+            const uint8_t es = a.ent_sel[off + i];
+            if (!(es & 1)) return false;
+            if (!(es & 4)) { push = false; return true; }
+            push = true;
+            return true;
+        };
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            bool push;
+            if (!is_event(i, push)) continue;
+            const uint32_t r = (uint32_t)(lo + i);
+            if (push && !(a.r.flag[r] & 2u)) continue;          // never in the table, never paired (cheap early out)
+            const unsigned long long k = a.r.qname_hash[r];
+            unsigned h = (unsigned)(k ^ (k >> 31)) & (PAIR_TBL - 1);
+            int probes = 0;
+            for (;;) {
+                const unsigned cur = atomicCAS(&tmin[h], 0u, (unsigned)i + 1u);
+                if (cur == 0u || a.r.qname_hash[lo + cur - 1] == k) {
+                    atomicMin(&tmin[h], (unsigned)i + 1u); atomicMax(&tmax[h], (unsigned)i + 1u);
+                    // (16-bit counter: two atomics on the containing word)
+                    atomicAdd(reinterpret_cast<unsigned int*>(tcnt) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                    break;
+                }
+                h = (h + 1) & (PAIR_TBL - 1);
+                if (++probes >= PAIR_TBL * 3 / 4) { over_s = 1; break; }
+            }
+        }
+        __syncthreads();
+        if (over_s) { if (threadIdx.x == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); return; }
+        for (int h = threadIdx.x; h < PAIR_TBL; h += blockDim.x) {
+            const int cnt = tcnt[h];
+            if (cnt < 2) continue;
+            const int first = (int)tmin[h] - 1, last = (int)tmax[h] - 1;
+            const unsigned long long k = a.r.qname_hash[lo + first];
+            int stored = -1;
+            int seen = 0;
+            for (int i = first; i <= last && seen < cnt; i = (cnt == 2 && i == first) ? last : i + 1) {
+                bool push;
+                if (!is_event(i, push)) continue;
+                const uint32_t r = (uint32_t)(lo + i);
+                if (a.r.qname_hash[r] != k || (push && !(a.r.flag[r] & 2u))) continue;
+                ++seen;
+                if (!push) { stored = -1; continue; }                       // overlap_remove by name
+                if (!olap_eligible(a, r)) continue;
+                // a read without reference span is never linked (sel without a span: no overlap_push)
+                bool has_span = false;
+                for (uint32_t q = a.r.cigar_off[r]; q < a.r.cigar_off[r + 1] && !has_span; ++q) { const uint32_t c = a.r.cigar[q]; has_span = op_consumes_ref(c & 15u) && (c >> 4) > 0; }
+                if (!has_span) continue;
+                if (stored < 0) {
+                    const int mp = a.r.mpos[r];
+                    if (mp >= a.r.pos[r] || ((a.r.flag[r] & 1u) && mp == -1)) stored = i;     // the mate is still to arrive
+                    continue;
+                }
+                // pair (stored, i): tweak_overlap_quality on scratch copies of the two quality strings, then the two values the
+                // column tests
+                const int64_t sa = off + stored, sb = off + i;
+                const uint32_t ra = (uint32_t)(lo + stored);
+                const int la = a.r.l_seq[ra], lb = a.r.l_seq[r];
+                const unsigned long long at = atomicAdd(a.pair_bump, (unsigned long long)(la + lb));
+                if (at + (unsigned long long)(la + lb) <= a.pair_cap) {
+                    uint8_t* aq = a.pair_q + at; uint8_t* bq = aq + la;
+                    const uint8_t* ga = a.r.qual + 8ull * a.r.seq_off[ra]; const uint8_t* gb = a.r.qual + 8ull * a.r.seq_off[r];
+                    for (int q = 0; q < la; ++q) aq[q] = ga[q];
+                    for (int q = 0; q < lb; ++q) bq[q] = gb[q];
+                    tweak_pair(a, ra, r, aq, bq, a.olap_mode);
+                    if ((a.ent_sel[sa] & 2) && a.ent_qpos[sa] < la) a.ent_q[sa] = aq[a.ent_qpos[sa]];
+                    if ((a.ent_sel[sb] & 2) && a.ent_qpos[sb] < lb) a.ent_q[sb] = bq[a.ent_qpos[sb]];
+                } else atomicOr(a.overflow, 2);         // the scratch is too small: the host sizes it from pair_bump and runs again
+                stored = -1;
+            }
+        }
+        __syncthreads();
+    }
+    // the quality test and the count of admitted entries
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint8_t es = a.ent_sel[off + i];
+        const bool ok = (es & 6) == 6 && (int)a.ent_q[off + i] >= a.min_bq;
+        if (!ok) a.ent_key[off + i] = KEY_NONE;
+        mine += ok ? 1 : 0;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&nadm_s, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) a.seg_count[ci] = nadm_s;
 }
 
 __device__ __forceinline__ bool same_entry(const ins_args& a, int lo, int64_t off, uint32_t e1, uint32_t e2) {
@@ -400,7 +648,7 @@ __global__ void __launch_bounds__(1024) ins_count_kernel(ins_args a, tc_insert_c
         }
     }
     __syncthreads();
-    if (over_s) { if (threadIdx.x == 0) atomicExch(a.overflow, 1); return; }
+    if (over_s) { if (threadIdx.x == 0) atomicOr(a.overflow, 1); return; }
     // hashed keys (insertions longer than 12): every entry against the first entry of its key
     if (hashed_s)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -469,6 +717,17 @@ __global__ void ins_bases_kernel(ins_args a, const tc_insert_call_t* __restrict_
     for (int j = threadIdx.x; j < c.indel; j += blockDim.x) bases[c.bases_off + j] = (uint8_t)ins_char(a, r, a.ent_qpos[e], j + 1, rev);
 }
 
+static int launch_pair(tc_ctx* ctx, const ins_args& a, int grid, cudaStream_t s) {
+    const size_t smem = (size_t)PAIR_TBL * 10;
+    if (!(ctx->ins_attr_set & 2)) {
+        TC_CUDA(cudaFuncSetAttribute(ins_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->ins_attr_set |= 2;
+    }
+    ins_pair_kernel<<<grid, 1024, smem, s>>>(a);
+    TC_LAUNCH_CHECK();
+    return TC_OK;
+}
+
 TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const int32_t* cand_pos, int32_t n_cand,
                               const tc_pileup_params_t* p, tc_insert_call_t* calls, uint8_t* bases, int64_t bases_cap, void* stream) {
     if (!ctx) return TC_ERR_ARG;
@@ -485,11 +744,15 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     // Host-resident SEQ / QUAL / CIGAR are staged range by range once the candidate ranges are known: this pass
     // reads them only for the reads over the candidate columns, and QUAL alone is 8x the packed bases.  (Without a
     // span bound the CIGARs of all reads are needed first, so they are staged in full.)
-    const bool bounded = reads->max_ref_span > 0;
-    const int stage = NEED_QUAL | DEFER_SEQ | DEFER_QUAL | (bounded ? DEFER_CIGAR : 0);
+    // the caller's span bound is only trusted when tc_pileup_counts has verified it for these very arrays; a bound that is too
+    // small would silently narrow the range of reads fetched for a column
+    const bool bounded = reads->max_ref_span > 0 && ctx->span_ok_bound == reads->max_ref_span && ctx->span_ok_cigar == reads->cigar &&
+                         ctx->span_ok_off == reads->cigar_off && ctx->span_ok_n == reads->n_reads && ctx->span_ok_ops == reads->n_cigar_ops;
+    const int stage = NEED_QUAL | NEED_MATE | DEFER_SEQ | DEFER_QUAL | DEFER_MATE | (bounded ? DEFER_CIGAR : 0);
     const bool host_seq = reads->seq4 && !tc_is_device_ptr(reads->seq4);
     const bool host_qual = reads->qual && !tc_is_device_ptr(reads->qual);
     const bool host_cig = bounded && reads->cigar && !tc_is_device_ptr(reads->cigar);
+    const bool host_mate = reads->qname_hash && reads->mpos && reads->isize && !tc_is_device_ptr(reads->qname_hash);
     int rc = tc_resolve_reads(ctx, reads, &a.r, stage, s);
     if (rc) return rc;
     const int64_t n = a.r.n;
@@ -497,7 +760,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     if (n == 0) return TC_OK;
     // results block: status, layout, overflow flag, admitted counts, the calls and their inserted characters — one
     // memset in front, one copy back
-    const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_SEG = 96;
+    const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_BUMP = 88, RB_SEG = 96;
     const size_t rb_calls = RB_SEG + ((4 * ((size_t)n_cand + 1) + 15) & ~(size_t)15);
     const size_t rb_fixed = rb_calls + sizeof(tc_insert_call_t) * (size_t)n_cand;
     const size_t rb_bytes = rb_fixed + (size_t)n_cand * INS_BASES_FIXED;
@@ -510,13 +773,14 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     TC_CUDA(cudaMemsetAsync(d_rb, 0, rb_calls, s));
     TC_CUDA(cudaMemcpyAsync(d_cand, cand_pos, 4 * (size_t)n_cand, cudaMemcpyHostToDevice, s));
     ctx->h2d_bytes += 4 * (int64_t)n_cand;
-    a.span_hint = reads->max_ref_span > 0 ? reads->max_ref_span : 0;
+    a.span_hint = bounded ? reads->max_ref_span : 0;
     if (a.span_hint == 0) {
         max_span_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.r, d_status);
         TC_LAUNCH_CHECK();
     }
     a.cand = d_cand; a.n_cand = n_cand; a.range = d_range; a.range_off = (uint32_t*)(d_range + 2 * (size_t)n_cand); a.status = d_status;
     a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality; a.ignore_orphans = p->ignore_orphans;
+    a.olap_mode = (p->reserved >> 8) & 3;
     a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
     cand_range_kernel<<<(n_cand + 3) / 4, 128, 0, s>>>(a);
     TC_LAUNCH_CHECK();
@@ -524,7 +788,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     // on the device into buffers sized from the last calls (no read-back of the ranges, one synchronisation per
     // call); otherwise — host arrays to stage range by range, the sorted form, or a layout that did not fit — on
     // the host from the ranges.
-    const bool spec = !(host_seq || host_qual || host_cig) && p->kernel != 2 && !(p->reserved & 1);
+    const bool spec = !(host_seq || host_qual || host_cig || host_mate) && p->kernel != 2 && !(p->reserved & 1);
     if (ctx->ins_slot_cap <= 0) ctx->ins_slot_cap = 1 << 16;     // grows to twice the largest layout seen
     int32_t* h_range = (int32_t*)malloc(24 * (size_t)n_cand);
     int64_t* h_off = (int64_t*)malloc(8 * ((size_t)n_cand + 1));
@@ -541,6 +805,23 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     INS_CUDA(cudaMemcpyAsync(h_range, d_range, 24 * (size_t)n_cand, cudaMemcpyDeviceToHost, s), "range readback");
     INS_CUDA(cudaStreamSynchronize(s), "range readback");
     ctx->d2h_bytes += 24 * (int64_t)n_cand;
+    if (host_mate) {
+        // QNAME hash, PNEXT, TLEN of the reads over the candidate columns (read index ranges; candidates ascend, so do their ranges)
+        int i = 0;
+        while (i < n_cand) {
+            int64_t b0 = h_range[2 * i], b1 = h_range[2 * i + 1];
+            int j = i + 1;
+            while (j < n_cand && h_range[2 * j] <= b1) { if (h_range[2 * j + 1] > b1) b1 = h_range[2 * j + 1]; ++j; }
+            const size_t len = (size_t)(b1 - b0);
+            if (len) {
+                INS_CUDA(cudaMemcpyAsync((uint64_t*)a.r.qname_hash + b0, reads->qname_hash + b0, 8 * len, cudaMemcpyHostToDevice, s), "QNAME hash range upload");
+                INS_CUDA(cudaMemcpyAsync((int32_t*)a.r.mpos + b0, reads->mpos + b0, 4 * len, cudaMemcpyHostToDevice, s), "PNEXT range upload");
+                INS_CUDA(cudaMemcpyAsync((int32_t*)a.r.isize + b0, reads->isize + b0, 4 * len, cudaMemcpyHostToDevice, s), "TLEN range upload");
+                ctx->h2d_bytes += 16 * (int64_t)len;
+            }
+            i = j;
+        }
+    }
     if (host_seq || host_qual || host_cig) {
         // candidates ascend, so do their ranges: merge the overlapping ones and copy every stretch once
         const uint32_t* ho = (const uint32_t*)(h_range + 2 * (size_t)n_cand);
@@ -579,7 +860,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     }
     const size_t T = (size_t)(total > 0 ? total : 1), NT = (size_t)(n_tiles > 0 ? n_tiles : 1);
     // one slab: keys, indel, qpos, head, sel per slot; tile tables; per-candidate offsets, counts
-    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + (size_t)n_cand * INS_BASES_FIXED + 256 + 16;
+    const size_t bytes = T * (8 + 4 + 4 + 1 + 1 + 1) + NT * 12 + ((size_t)n_cand + 1) * 16 + (size_t)n_cand * INS_BASES_FIXED + 256 + 16;
     uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
     tc_insert_call_t* d_calls = (tc_insert_call_t*)(d_rb + rb_calls);
     if (!slab) { INS_FREE(); return TC_ERR_NOMEM; }
@@ -589,8 +870,12 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + n_cand + 1; a.tile_last = a.tile_sel + NT;
     a.seg_count = (int32_t*)(d_rb + RB_SEG); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    if (ctx->pair_cap <= 0) ctx->pair_cap = 1 << 22;
+    a.pair_bump = (unsigned long long*)(d_rb + RB_BUMP); a.pair_cap = (unsigned long long)ctx->pair_cap;
+    a.pair_q = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_F, (size_t)ctx->pair_cap);
+    if (!a.pair_q) { INS_FREE(); return TC_ERR_NOMEM; }
     int32_t* d_layout = (int32_t*)(d_rb + RB_LAYOUT);         // [3], speculative layout only
-    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.bases_fixed = d_rb + rb_fixed;
+    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.ent_q = a.ent_sel + T; a.bases_fixed = d_rb + rb_fixed;
     a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst;
     if (spec) {
         a.layout = d_layout;
@@ -609,18 +894,23 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
         ins_admit_kernel<<<n_tiles, INS_TILE, 0, s>>>(a);
         ctx->launches++;
     }
+    if (a.min_bq > 0) {
+        rc = launch_pair(ctx, a, n_cand, s);
+        if (rc) { INS_FREE(); return rc; }
+    }
     bool sorted_form = p->kernel == 2;
     const size_t tbl_smem = (size_t)INS_TBL * 16;
     int32_t h_over = 0;
+    unsigned long long h_bump = 0;
     int32_t h_layout[3] = {0, 0, 0};
     // the results block comes back in one copy through pinned memory (copies into the caller's pageable buffers
     // would each wait for the stream)
     const size_t calls_bytes = sizeof(tc_insert_call_t) * (size_t)n_cand, fixed_bytes = (size_t)n_cand * INS_BASES_FIXED;
     const bool via_pinned = rb_bytes <= TC_HOST_SCRATCH;
     if (!sorted_form) {
-        if (!ctx->ins_attr_set) {
+        if (!(ctx->ins_attr_set & 1)) {
             INS_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem), "smem attribute");
-            ctx->ins_attr_set = 1;
+            ctx->ins_attr_set |= 1;
         }
         ins_count_kernel<<<n_cand, 1024, tbl_smem, s>>>(a, d_calls);
         ctx->launches++;
@@ -630,21 +920,27 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
         INS_CUDA(cudaMemcpyAsync(pin, d_rb, rb_bytes, cudaMemcpyDeviceToHost, s), "results readback");
         INS_CUDA(cudaStreamSynchronize(s), "results readback");
         memcpy(ctx->host_status, pin, sizeof(tc_status));
-        memcpy(h_layout, pin + RB_LAYOUT, 12); memcpy(&h_over, pin + RB_OVER, 4);
+        memcpy(h_layout, pin + RB_LAYOUT, 12); memcpy(&h_over, pin + RB_OVER, 4); memcpy(&h_bump, pin + RB_BUMP, 8);
         memcpy(calls, pin + rb_calls, calls_bytes); memcpy(h_fixed, pin + rb_fixed, fixed_bytes);
-        if (sorted_form) { h_over = 0; }
+        if (sorted_form) { h_over &= 2; }
         if (!spec) { h_layout[0] = h_layout[1] = h_layout[2] = 0; }
     } else {
-        if (!sorted_form) {
-            INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
-            if (spec) INS_CUDA(cudaMemcpyAsync(h_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
-        }
+        INS_CUDA(cudaMemcpyAsync(&h_over, a.overflow, 4, cudaMemcpyDeviceToHost, s), "overflow readback");
+        INS_CUDA(cudaMemcpyAsync(&h_bump, a.pair_bump, 8, cudaMemcpyDeviceToHost, s), "overflow readback");
+        if (!sorted_form && spec) INS_CUDA(cudaMemcpyAsync(h_layout, d_layout, 12, cudaMemcpyDeviceToHost, s), "layout readback");
         INS_CUDA(cudaMemcpyAsync(calls, d_calls, calls_bytes, cudaMemcpyDeviceToHost, s), "insert calls readback");
         INS_CUDA(cudaMemcpyAsync(h_fixed, a.bases_fixed, fixed_bytes, cudaMemcpyDeviceToHost, s), "inserted bases readback");
         INS_CUDA(cudaMemcpyAsync(ctx->host_status, d_status, sizeof(tc_status), cudaMemcpyDeviceToHost, s), "status readback");
         INS_CUDA(cudaStreamSynchronize(s), "insert calls readback");
     }
     ctx->d2h_bytes += (int64_t)(sizeof(tc_insert_call_t) + INS_BASES_FIXED) * n_cand + (int64_t)sizeof(tc_status) + 4;
+    if (!via_pinned && sorted_form) h_over &= 2;
+    if (h_over & 2) {
+        // the scratch for the rewritten quality strings of overlapping mates was too small: size it and run again
+        ctx->pair_cap = 2 * (int64_t)h_bump + 4096;
+        INS_FREE();
+        return tc_extract_inserts(ctx, reads, ref_len, cand_pos, n_cand, p, calls, bases, bases_cap, stream);
+    }
     if (spec) {
         if (h_layout[2] || h_over) {
             // the layout did not fit the speculative buffers (size them for next time), or a column needs the sorted
@@ -740,7 +1036,7 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
     ins_args a;
     memset(&a, 0, sizeof(a));
     memset(pend, 0, sizeof(*pend));
-    int rc = tc_resolve_reads(ctx, reads, &a.r, NEED_QUAL, s);       // every array is a device pointer already: nothing is copied
+    int rc = tc_resolve_reads(ctx, reads, &a.r, NEED_QUAL | NEED_MATE, s);       // every array is a device pointer already: nothing is copied
     if (rc) return rc;
     const int64_t n = a.r.n;
     const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_EXTRA = 128;      // extra: [0] n_cand, [16..32) pileup status, [32..32+cap) candidates
@@ -761,12 +1057,13 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
     }
     a.cand = d_cand; a.n_cand = cap; a.n_cand_dev = d_ncand; a.range = d_range; a.range_off = (uint32_t*)(d_range + 2 * (size_t)cap);
     a.flag_filter = p->flag_filter; a.min_mapq = p->min_mapq; a.min_bq = p->min_base_quality; a.ignore_orphans = p->ignore_orphans;
+    a.olap_mode = (p->reserved >> 8) & 3;
     a.max_depth = p->max_depth > 0 ? p->max_depth : (1ll << 62);
     cand_range_kernel<<<(cap + 3) / 4, 128, 0, s>>>(a);
     TC_LAUNCH_CHECK();
     if (ctx->ins_slot_cap <= 0) ctx->ins_slot_cap = 1 << 16;
     const size_t T = (size_t)ctx->ins_slot_cap, NT = T / INS_TILE + (size_t)cap + 1;
-    const size_t bytes = T * (8 + 4 + 4 + 1 + 1) + NT * 12 + ((size_t)cap + 1) * 16 + 256 + 16;
+    const size_t bytes = T * (8 + 4 + 4 + 1 + 1 + 1) + NT * 12 + ((size_t)cap + 1) * 16 + 256 + 16;
     uint8_t* slab = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_D, bytes);
     if (!slab) return TC_ERR_NOMEM;
     uint64_t* d_key = (uint64_t*)slab;
@@ -775,8 +1072,12 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + cap + 1; a.tile_last = a.tile_sel + NT;
     a.seg_count = (int32_t*)(d_rb + rb_seg); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    if (ctx->pair_cap <= 0) ctx->pair_cap = 1 << 22;
+    a.pair_bump = (unsigned long long*)(d_rb + 88); a.pair_cap = (unsigned long long)ctx->pair_cap;
+    a.pair_q = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_F, (size_t)ctx->pair_cap);
+    if (!a.pair_q) return TC_ERR_NOMEM;
     int32_t* d_layout = (int32_t*)(d_rb + RB_LAYOUT);
-    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.bases_fixed = d_rb + rb_fixed;
+    a.ent_head = (uint8_t*)(a.tile_last + NT); a.ent_sel = a.ent_head + T; a.ent_q = a.ent_sel + T; a.bases_fixed = d_rb + rb_fixed;
     a.ent_key = d_key; a.seg_off = d_off; a.tile_cand = d_tcand; a.tile_first = d_tfirst; a.layout = d_layout;
     ins_layout_kernel<<<1, 256, 0, s>>>(a, d_off, d_tfirst, d_tcand, d_layout, (int64_t)T, (int)NT, d_pileup_status, (int32_t*)(d_rb + RB_EXTRA));
     TC_LAUNCH_CHECK();
@@ -785,10 +1086,11 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
         TC_LAUNCH_CHECK();
         ins_admit_kernel<<<(unsigned)NT, INS_TILE, 0, s>>>(a);
         TC_LAUNCH_CHECK();
+        if (a.min_bq > 0) { rc = launch_pair(ctx, a, cap, s); if (rc) return rc; }
         const size_t tbl_smem = (size_t)INS_TBL * 16;
-        if (!ctx->ins_attr_set) {
+        if (!(ctx->ins_attr_set & 1)) {
             TC_CUDA(cudaFuncSetAttribute(ins_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl_smem));
-            ctx->ins_attr_set = 1;
+            ctx->ins_attr_set |= 1;
         }
         ins_count_kernel<<<cap, 1024, tbl_smem, s>>>(a, (tc_insert_call_t*)(d_rb + rb_calls));
         TC_LAUNCH_CHECK();
@@ -816,6 +1118,7 @@ int tc_inserts_finish_dev(tc_ctx* ctx, const tc_ins_pending* pend, const void* h
     if (n > pend->cap) { *fit = 0; return TC_OK; }
     memcpy(cands, extra + 32, 4 * (size_t)n);
     if (layout[2]) { ctx->ins_slot_cap = 2 * (int64_t)layout[1] + 4096; *fit = 0; return TC_OK; }
+    if (over & 2) { unsigned long long bump; memcpy(&bump, pin + 88, 8); ctx->pair_cap = 2 * (int64_t)bump + 4096; }
     if (over) { *fit = 0; return TC_OK; }
     if (st.err == TC_ERR_UNSORTED) return tc_fail(ctx, TC_ERR_UNSORTED, "Unsorted input. Pileup aborts");
     if (st.err) return tc_fail(ctx, st.err, "insertion key collision or device-side failure %d", st.err);

@@ -375,7 +375,13 @@ int tc_pileup_finish(tc_ctx* ctx, const tc_status& st_in, const tc_pileup_pendin
     }
     if (st.err == 0 && reads->max_ref_span > 0 && st.max_span > reads->max_ref_span)
         return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t.max_ref_span = %d but a read spans %d reference columns", reads->max_ref_span, st.max_span);
-    return status_to_rc(ctx, st, p);
+    const int rc = status_to_rc(ctx, st, p);
+    // a flag filter hides reads from this pass: the bound then only holds for the reads that passed, not for another pass's
+    if (rc == TC_OK && reads->max_ref_span > 0 && (p->flag_filter & ~4u) == 0 && p->min_mapq <= 0 && !p->ignore_orphans) {
+        ctx->span_ok_cigar = reads->cigar; ctx->span_ok_off = reads->cigar_off; ctx->span_ok_n = reads->n_reads;
+        ctx->span_ok_ops = reads->n_cigar_ops; ctx->span_ok_bound = reads->max_ref_span;
+    }
+    return rc;
 }
 
 TC_API int tc_pileup_counts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p,

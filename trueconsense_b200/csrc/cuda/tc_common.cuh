@@ -38,6 +38,10 @@ struct tc_ctx {
     int timing;             // bracket the pileup kernel with events
     cudaEvent_t ev0, ev1;
     int ev_valid;
+    // the span bound (tc_reads_t.max_ref_span) tc_pileup_counts verified last, and for which arrays: tc_extract_inserts
+    // trusts a bound only when it is this one — otherwise it finds the longest span itself
+    const void* span_ok_cigar; const void* span_ok_off; int64_t span_ok_n, span_ok_ops; int32_t span_ok_bound;
+    int64_t pair_cap;       // tc_extract_inserts: bytes of scratch for the rewritten quality strings of overlapping mates; grows on demand
     int64_t ins_slot_cap;   // tc_extract_inserts: entry slots its speculative (no read-back) layout may use; grows on demand
     struct tc_sample_slot* samples;     // [2] samples in flight (tc_sample_enqueue / tc_sample_finish), allocated on first use
     int sample_next;
@@ -97,6 +101,7 @@ struct dreads {
 #define DEFER_SEQ   4
 #define DEFER_CIGAR 8
 #define DEFER_QUAL  16
+#define DEFER_MATE  32
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s);
 
 // ---- pieces of the entry points that only ENQUEUE (tc_pileup_call_inserts chains them without a host round trip)

@@ -94,10 +94,10 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
     } else if (in->qual && tc_is_device_ptr(in->qual)) {
         out->qual = in->qual;
     }
-    if (need & NEED_MATE) {
-        if (in->qname_hash) { STAGE(qname_hash, SLOT_QHASH, uint64_t, n) }
-        if (in->mpos) { STAGE(mpos, SLOT_MPOS, int32_t, n) }
-        if (in->isize) { STAGE(isize, SLOT_ISIZE, int32_t, n) }
+    if ((need & NEED_MATE) && in->qname_hash && in->mpos && in->isize) {       // all three or none
+        STAGE_OR_DEFER(qname_hash, SLOT_QHASH, uint64_t, n, DEFER_MATE)
+        STAGE_OR_DEFER(mpos, SLOT_MPOS, int32_t, n, DEFER_MATE)
+        STAGE_OR_DEFER(isize, SLOT_ISIZE, int32_t, n, DEFER_MATE)
     }
 #undef STAGE_OR_DEFER
 #undef STAGE
@@ -193,7 +193,7 @@ TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* de
     if (!ctx || !host || !dev) return tc_fail(ctx, TC_ERR_ARG, "NULL argument");
     TC_CUDA(cudaSetDevice(ctx->device));
     dreads d;
-    int need = host->qual ? NEED_QUAL : 0;      // the mate arrays stay on the host: no kernel reads them
+    int need = (host->qual ? NEED_QUAL : 0) | NEED_MATE;        // (arrays that are NULL in *host are not copied)
     int rc = tc_resolve_reads(ctx, host, &d, need, (cudaStream_t)stream);
     if (rc) return rc;
     *dev = *host;

@@ -156,12 +156,16 @@ class DeviceReads:
         self.generation = generation
 
     def with_host_qual(self) -> "DeviceReads":
-        """The same device arrays plus the batch's HOST quality array: tc_extract_inserts then copies QUAL
-        only for the reads over its candidate columns."""
+        """The same device arrays plus the batch's HOST quality and mate arrays (QNAME hash, PNEXT, TLEN):
+        tc_extract_inserts then copies them only for the reads over its candidate columns."""
         st = TcReads()
         C.memmove(C.byref(st), C.byref(self.struct), C.sizeof(TcReads))
         if not st.qual and self.host.qual is not None:
             st.qual = self.host.qual.ctypes.data
+        if not st.qname_hash and self.host.qname_hash is not None and self.host.mpos is not None and self.host.isize is not None:
+            st.qname_hash = self.host.qname_hash.ctypes.data
+            st.mpos = self.host.mpos.ctypes.data
+            st.isize = self.host.isize.ctypes.data
         return DeviceReads(st, self.host, self.ctx, self.generation)
 
 
@@ -227,8 +231,9 @@ class Context:
         later call that is handed host arrays — so a DeviceReads is only valid until then (checked)."""
         dev = TcReads()
         host = batch.c_struct()
-        if not with_qual:
+        if not with_qual:       # what only tc_extract_inserts reads stays on the host (see DeviceReads.with_host_qual)
             host.qual = None
+            host.qname_hash = host.mpos = host.isize = None
         self._generation += 1
         self._check(self._lib.tc_reads_upload(self._h, C.byref(host), C.byref(dev), stream))
         return DeviceReads(dev, batch, self, self._generation)

@@ -109,9 +109,25 @@ class ReadBatch:
         s.n_cigar_ops = int(self.cigar.shape[0])
         for name in _ARRAYS:
             a = getattr(self, name)
+            if name == "mpos" and a is not None:
+                a = self._mpos_for_abi()
             setattr(s, name, None if a is None else a.ctypes.data)
         s.max_ref_span = max(int(self.max_ref_span), 0)      # 0 = unknown
         return s
+
+    def _mpos_for_abi(self) -> np.ndarray:
+        """tc_reads_t.mpos: PNEXT, -1 if unavailable, -2 when the mate maps to another reference (htslib's overlap
+        handling never pairs such reads).  The batch itself keeps the BAM's PNEXT."""
+        if self.tid is None or self.mtid is None:
+            return self.mpos
+        other = (self.mtid >= 0) & (self.mtid != self.tid)
+        if not other.any():
+            return self.mpos
+        cached = getattr(self, "_mpos_abi", None)
+        if cached is None or cached.shape != self.mpos.shape:
+            cached = np.where(other, np.int32(-2), self.mpos).astype(np.int32)
+            object.__setattr__(self, "_mpos_abi", cached)
+        return cached
 
     # ------------------------------------------------------------------ derived quantities
     def ref_spans(self) -> np.ndarray:
