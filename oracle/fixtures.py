@@ -268,3 +268,21 @@ def overlap_kat_records():
     exp.append("A+2TT")
     recs.sort(key=lambda r: r["pos"])
     return recs, exp
+
+
+def overlap_workload():
+    """A 200-bp reference where the insertion behind OVERLAP_COL reads "TT" in 9 unpaired reads and "CC" in both mates of
+    6 overlapping proper pairs: counted per entry "CC" wins 12 : 9, under htslib's mate-overlap rewriting (one entry per
+    pair) "TT" wins 9 : 6 — ListInserts and the consensus differ.  Returns (name, refseq, feats, mincov, ReadBatch)."""
+    rng = np.random.default_rng(77)
+    refseq = "".join("ACGT"[i] for i in rng.integers(0, 4, OVERLAP_REF_LEN))
+    recs = []
+    for i in range(9):
+        recs.append(dict(pos=70, cigar="31M2I19M", seq="G" * 30 + "A" + "TT" + "G" * 19, qual=30, qname=f"solo{i}"))
+    for i in range(6):
+        recs += overlap_pair(f"pair{i}", "A", 30, "A", 30, ins="CC")
+    recs.sort(key=lambda r: r["pos"])
+    b = ReadBatch.from_records(recs)
+    b.ref_names = ["ref"]; b.ref_lens = [OVERLAP_REF_LEN]
+    feats = [{"name": "o", "start": 10, "end": 189, "strand": "+"}]
+    return "mini_overlap", refseq, feats, 5, b

@@ -195,6 +195,8 @@ def main() -> None:
     for name in fixtures.MINI_NAMES:
         w, batch = fixtures.mini_workload(name)
         make_bam_fixture(ref, w.name, batch, w.ref, w.feats, w.mincov)
+    name, oref, ofeats, omincov, ob = fixtures.overlap_workload()
+    make_bam_fixture(ref, name, ob, oref, ofeats, omincov)
     print("golden vectors written to", GOLD)
 
 

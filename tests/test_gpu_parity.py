@@ -14,7 +14,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 
 pytestmark = pytest.mark.gpu
 
-MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
+MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long", "mini_overlap")
 KERNELS = [1, 3, 4]   # pileup kernel variants: 1 scatter (smem atomics), 3 bit-parallel warp streams, 4 pieces of long reads + 3
 
 
@@ -636,6 +636,16 @@ def test_span_bound_hint(ctx, orc):
     with pytest.raises(gpu.TcError) as ei:
         ctx.pileup_counts(small, len(ref))
     assert ei.value.code == -2
+    # tc_extract_inserts does not trust a bound tc_pileup_counts has not verified for these arrays: a bound that is too small
+    # would silently narrow the range of reads fetched for a column
+    ref, _, amp = _synth("amplicon_deep")
+    counts = ctx.pileup_counts(amp, len(ref))
+    cands = ctx.list_insert_candidates(ctx.call(counts, len(ref), 10, True).flags, len(ref))
+    assert len(cands) > 0
+    good = ctx.extract_inserts(amp, len(ref), cands)
+    lying = copy.copy(amp)
+    lying.max_ref_span = 20
+    assert ctx.extract_inserts(lying, len(ref), cands) == good
     # the checks the span pass used to make
     unsorted = ReadBatch.from_records([dict(pos=50, cigar="10M", seq="A" * 10), dict(pos=10, cigar="10M", seq="A" * 10)])
     unsorted.max_ref_span = 10

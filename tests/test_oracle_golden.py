@@ -11,7 +11,7 @@ from conftest import GOLD, load_golden_counts, load_golden_json
 from oracle import bam_py, call, pileup
 
 KAT = load_golden_json("kat.json")
-MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long")
+MINIS = ("quirk", "mini_illumina", "mini_ont", "mini_long", "mini_overlap")
 
 
 def _col_counts(c):
