@@ -124,6 +124,83 @@ def test_bam_reader_errors(tmp_path, host_libs):
         bamio.read_bam(str(tmp_path / "missing.bam"))
 
 
+def _bgzf_block(payload: bytes, isize=None, bsize_delta=0, xlen_extra=b"") -> bytes:
+    import struct
+    import zlib
+
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    data = comp.compress(payload) + comp.flush()
+    extra = b"BC" + struct.pack("<HH", 2, 0) + xlen_extra          # BSIZE patched below
+    bsize = 12 + len(extra) + len(data) + 8
+    extra = b"BC" + struct.pack("<HH", 2, bsize - 1 + bsize_delta) + xlen_extra
+    hdr = bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255]) + struct.pack("<H", len(extra)) + extra
+    return hdr + data + struct.pack("<Ii", zlib.crc32(payload) & 0xFFFFFFFF, len(payload) if isize is None else isize)
+
+
+def test_bam_reader_rejects_crafted_sizes(tmp_path, host_libs):
+    """Every size the reader takes from the file is checked before it is used: a crafted ISIZE pair that
+    under-allocated the inflate buffer, a BSIZE shorter than the block's own header, subfields past XLEN, negative
+    header lengths, records shorter than their fields, truncation and random corruption all end in an error, never in
+    a crash."""
+    import struct
+
+    from trueconsense_b200 import bamio
+
+    def header(n_ref=1, l_text=0, l_name=4):
+        return b"BAM\1" + struct.pack("<i", l_text) + struct.pack("<i", n_ref) + struct.pack("<i", l_name) + b"ref\0" + struct.pack("<i", 1000)
+
+    def record(l_seq=4, n_cig=1, bs_delta=0, l_name=3, name=b"r1\0"):
+        body = struct.pack("<iiBBHHHIiii", 0, 10, l_name, 60, 0, n_cig, 0, l_seq, -1, -1, 0) + name
+        body += struct.pack("<I", (4 << 4) | 0) * 1 + bytes((4 + 1) // 2) + bytes(4)
+        return struct.pack("<i", len(body) + bs_delta) + body
+
+    eof = _bgzf_block(b"")
+    cases = {
+        "isize_pair": _bgzf_block(b"x" * 65000, isize=65000) + _bgzf_block(b"y" * 1000, isize=-64000) + eof,
+        "isize_huge": _bgzf_block(header() + record(), isize=70000) + eof,
+        "bsize_short": _bgzf_block(header() + record(), bsize_delta=-40) + eof,
+        "subfield_past_xlen": _bgzf_block(header() + record())[:10] + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 200, 0) + eof,
+        "negative_l_text": _bgzf_block(header(l_text=-8) + record()) + eof,
+        "negative_n_ref": _bgzf_block(header(n_ref=-1) + record()) + eof,
+        "huge_n_ref": _bgzf_block(header(n_ref=1 << 28) + record()) + eof,
+        "negative_l_name": _bgzf_block(header(l_name=-4) + record()) + eof,
+        "record_l_seq": _bgzf_block(header() + record(l_seq=4000)) + eof,
+        "record_n_cig": _bgzf_block(header() + record(n_cig=60000)) + eof,
+        "record_block_size": _bgzf_block(header() + record(bs_delta=5000)) + eof,
+        "record_name_unterminated": _bgzf_block(header() + record(name=b"r1x")) + eof,
+    }
+    good = _bgzf_block(header() + record()) + eof
+    path = tmp_path / "good.bam"
+    path.write_bytes(good)
+    assert bamio.read_bam(str(path)).n_reads == 1
+    for name, blob in cases.items():
+        path = tmp_path / f"{name}.bam"
+        path.write_bytes(blob)
+        with pytest.raises((ValueError, RuntimeError, OSError)):
+            bamio.read_bam(str(path))
+    # truncations and byte flips of a real file
+    real = open(f"{GOLD}/mini_illumina.bam", "rb").read()
+    rng = np.random.default_rng(9)
+    for i in range(40):
+        blob = bytearray(real[: int(rng.integers(30, len(real)))]) if i % 2 else bytearray(real)
+        for _ in range(int(rng.integers(1, 6))):
+            blob[int(rng.integers(0, len(blob)))] = int(rng.integers(0, 256))
+        path = tmp_path / "fuzz.bam"
+        path.write_bytes(bytes(blob))
+        try:
+            bamio.read_bam(str(path))
+        except (ValueError, RuntimeError, OSError):
+            pass
+    # a CIGAR kept in the CG tag (placeholder <l_seq>S<span>N) is refused, not piled up as a reference skip
+    body = struct.pack("<iiBBHHHIiii", 0, 10, 3, 60, 0, 2, 0, 4, -1, -1, 0) + b"r1\0"
+    body += struct.pack("<II", (4 << 4) | 4, (100 << 4) | 3) + bytes(2) + bytes(4)
+    path = tmp_path / "cg.bam"
+    path.write_bytes(_bgzf_block(header() + struct.pack("<i", len(body)) + body) + eof)
+    with pytest.raises(OSError) as ei:
+        bamio.read_bam(str(path))
+    assert "CG tag" in str(ei.value)
+
+
 def test_readbatch_slice_and_records():
     from trueconsense_b200.reads import ReadBatch
 

@@ -122,6 +122,7 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     /* (1) index BGZF blocks */
     int64_t nblk = 0, cap = 1024;
     blk_t* blk = malloc(cap * sizeof(blk_t));
+    if (!blk) { munmap((void*)f, fsize); return fail(err, errlen, -5, "out of memory"); }
     int64_t off = 0, uoff = 0;
     int rc = 0;
     while (off < fsize) {
@@ -130,17 +131,28 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) {
             rc = fail(err, errlen, -2, "not a BGZF block at offset %lld", (long long)off); break;
         }
+        /* every size below comes from the file: nothing is used before it has been checked against the file and the format */
         int xlen = rd16(h + 10);
+        if (off + 12 + xlen > fsize) { rc = fail(err, errlen, -2, "truncated BGZF extra field at %lld", (long long)off); break; }
         int bsize = -1;
         for (int x = 0; x + 4 <= xlen;) {
             const uint8_t* e = h + 12 + x;
             int slen = rd16(e + 2);
+            if (x + 4 + slen > xlen) break;                      /* a subfield running past XLEN */
             if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = rd16(e + 4) + 1;
             x += 4 + slen;
         }
-        if (bsize < 0 || off + bsize > fsize) { rc = fail(err, errlen, -2, "bad BGZF BSIZE at %lld", (long long)off); break; }
-        int32_t usize = (int32_t)rd32(h + bsize - 4);
-        if (nblk == cap) { cap *= 2; blk = realloc(blk, cap * sizeof(blk_t)); }
+        /* header (12) + extra + at least an empty deflate stream (2) + CRC32 + ISIZE (8) */
+        if (bsize < 12 + xlen + 2 + 8 || off + bsize > fsize) { rc = fail(err, errlen, -2, "bad BGZF BSIZE at %lld", (long long)off); break; }
+        uint32_t isize = rd32(h + bsize - 4);
+        if (isize > 65536u) { rc = fail(err, errlen, -2, "bad BGZF ISIZE %u at %lld (a block inflates to at most 64 KiB)", isize, (long long)off); break; }
+        int32_t usize = (int32_t)isize;
+        if (nblk == cap) {
+            cap *= 2;
+            blk_t* nb = realloc(blk, cap * sizeof(blk_t));
+            if (!nb) { rc = fail(err, errlen, -5, "out of memory"); break; }
+            blk = nb;
+        }
         blk[nblk].coff = off + 12 + xlen;
         blk[nblk].csize = bsize - 12 - xlen - 8;
         blk[nblk].uoff = uoff; blk[nblk].usize = usize;
@@ -153,21 +165,22 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
 
     /* (2) inflate in parallel */
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads) reduction(|:bad)
     for (int64_t b = 0; b < nblk; ++b) {
         if (blk[b].usize == 0) continue;
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
-        zs.next_in = (Bytef*)(f + blk[b].coff); zs.avail_in = blk[b].csize;
-        zs.next_out = u + blk[b].uoff; zs.avail_out = blk[b].usize;
+        if (inflateInit2(&zs, -15) != Z_OK) { bad |= 1; continue; }
+        zs.next_in = (Bytef*)(f + blk[b].coff); zs.avail_in = (uInt)blk[b].csize;
+        zs.next_out = u + blk[b].uoff; zs.avail_out = (uInt)blk[b].usize;       /* inflate never writes more than ISIZE bytes */
         int r = inflate(&zs, Z_FINISH);
-        if (r != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+        int ok = (r == Z_STREAM_END && zs.avail_out == 0);
         inflateEnd(&zs);
-        if (!bad) {
+        if (ok) {
             uint32_t crc = crc32(crc32(0L, Z_NULL, 0), u + blk[b].uoff, blk[b].usize);
-            if (crc != rd32(f + blk[b].coff + blk[b].csize)) bad = 1;
+            if (crc != rd32(f + blk[b].coff + blk[b].csize)) ok = 0;
         }
+        if (!ok) bad |= 1;
     }
     free(blk);
     munmap((void*)f, fsize);
@@ -178,18 +191,26 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     /* header */
     if (utotal < 12 || memcmp(u, "BAM\1", 4) != 0) { free(u); return fail(err, errlen, -2, "%s: missing BAM magic", path); }
     int64_t p = 4;
-    int32_t l_text = (int32_t)rd32(u + p); p += 4 + l_text;
-    if (p + 4 > utotal) { free(u); return fail(err, errlen, -2, "truncated BAM header"); }
+    int32_t l_text = (int32_t)rd32(u + p);
+    if (l_text < 0 || p + 4 + (int64_t)l_text + 4 > utotal) { free(u); return fail(err, errlen, -2, "truncated BAM header"); }
+    p += 4 + l_text;
     int32_t n_ref = (int32_t)rd32(u + p); p += 4;
+    if (n_ref < 0 || (int64_t)n_ref * 8 > utotal - p) { free(u); return fail(err, errlen, -2, "bad BAM reference count %d", n_ref); }
     out->n_ref = n_ref;
     out->ref_len = malloc(sizeof(int32_t) * (n_ref > 0 ? n_ref : 1));
     int64_t names_cap = 64, names_len = 0;
     out->ref_names = malloc(names_cap);
+    if (!out->ref_len || !out->ref_names) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
     for (int i = 0; i < n_ref; ++i) {
         if (p + 4 > utotal) { free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "truncated BAM reference list"); }
         int32_t l_name = (int32_t)rd32(u + p); p += 4;
-        if (p + l_name + 4 > utotal) { free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "truncated BAM reference list"); }
-        while (names_len + l_name + 1 > names_cap) { names_cap *= 2; out->ref_names = realloc(out->ref_names, names_cap); }
+        if (l_name < 0 || p + (int64_t)l_name + 4 > utotal) { free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "truncated BAM reference list"); }
+        while (names_len + l_name + 1 > names_cap) {
+            names_cap *= 2;
+            char* nn = realloc(out->ref_names, names_cap);
+            if (!nn) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
+            out->ref_names = nn;
+        }
         memcpy(out->ref_names + names_len, u + p, l_name);
         names_len += l_name;
         if (l_name == 0 || out->ref_names[names_len - 1] != 0) out->ref_names[names_len++] = 0;
@@ -201,14 +222,42 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     /* (3) hop over records */
     int64_t rcap = 1 << 16, nrec = 0, nkept = 0;
     int64_t* recoff = malloc(rcap * sizeof(int64_t));
+    if (!recoff) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
     int64_t q = p;
     while (q + 4 <= utotal) {
         int32_t bs = (int32_t)rd32(u + q);
         if (bs < 32 || q + 4 + bs > utotal) { rc = fail(err, errlen, -2, "corrupt BAM record at payload offset %lld", (long long)q); break; }
         ++nrec;
         int32_t refid = (int32_t)rd32(u + q + 4);
+        {
+            /* the record's own sizes against its block_size, before anything is sized from them */
+            const uint8_t* r = u + q + 4;
+            int32_t l_name = r[8];
+            uint32_t n_cig = rd16(r + 12);
+            uint32_t l_seq = rd32(r + 16);
+            int64_t need = 32 + (int64_t)l_name + 4LL * n_cig + ((int64_t)l_seq + 1) / 2 + (int64_t)l_seq;
+            if (l_seq > 0x7fffffffu || need > bs || l_name < 1 || r[32 + l_name - 1] != 0) {
+                rc = fail(err, errlen, -2, "%s: BAM record %lld shorter than its fields (or an unterminated read name)", path, (long long)(nrec - 1));
+                break;
+            }
+            /* more than 65535 CIGAR ops: the real CIGAR sits in the CG:B,I tag behind a <l_seq>S<span>N placeholder, which
+             * htslib expands transparently.  Not expanded here: refuse, rather than pile the read up as a reference skip */
+            if (refid >= 0 && n_cig == 2) {
+                const uint8_t* cg = r + 32 + l_name;
+                uint32_t c0 = rd32(cg), c1 = rd32(cg + 4);
+                if ((c0 & 15) == 4 && (c0 >> 4) == l_seq && (c1 & 15) == 3 && l_seq > 0) {
+                    rc = fail(err, errlen, -2, "%s: record %lld keeps its CIGAR in a CG tag (more than 65535 operations): not supported", path, (long long)(nrec - 1));
+                    break;
+                }
+            }
+        }
         if (refid >= 0) {
-            if (nkept == rcap) { rcap *= 2; recoff = realloc(recoff, rcap * sizeof(int64_t)); }
+            if (nkept == rcap) {
+                rcap *= 2;
+                int64_t* nr2 = realloc(recoff, rcap * sizeof(int64_t));
+                if (!nr2) { rc = fail(err, errlen, -5, "out of memory"); break; }
+                recoff = nr2;
+            }
             recoff[nkept++] = q + 4;
         }
         q += 4 + bs;
@@ -220,6 +269,7 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     /* sizes -> offsets (sequential prefix sum, cheap) */
     uint32_t* soff = malloc((nkept + 1) * 4);
     uint32_t* coff = malloc((nkept + 1) * 4);
+    if (!soff || !coff) { free(soff); free(coff); free(recoff); free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
     uint64_t sw = 0, co = 0;
     for (int64_t i = 0; i < nkept; ++i) {
         const uint8_t* r = u + recoff[i];

@@ -284,24 +284,26 @@ class Context:
         p = CallParams(int(mincov), int(bool(include_ambig)), maxdist, minority_del_pct, insert_pct)
         self._check(self._lib.tc_call(self._h, _ptr(counts), int(ref_len), C.byref(p), C.byref(table), stream))
 
-    def is_ambiguous(self, letters: np.ndarray, cnts: np.ndarray, cov: np.ndarray, maxdist: float = 10.0) -> np.ndarray:
+    def is_ambiguous(self, letters: np.ndarray, cnts: np.ndarray, cov: np.ndarray, maxdist: float = 10.0, stream: int = 0) -> np.ndarray:
         letters = np.ascontiguousarray(letters, dtype=np.uint8)
         cnts = np.ascontiguousarray(cnts, dtype=np.int32)
         cov = np.ascontiguousarray(cov, dtype=np.int32)
         n = cov.shape[0]
         out = np.zeros(n, np.uint8)
-        self._check(self._lib.tc_is_ambiguous(self._h, _ptr(letters), _ptr(cnts), _ptr(cov), n, maxdist, _ptr(out), 0))
+        self._check(self._lib.tc_is_ambiguous(self._h, _ptr(letters), _ptr(cnts), _ptr(cov), n, maxdist, _ptr(out), stream))
         return out
 
     # ------------------------------------------------------------------ (2) insertions
-    def list_insert_candidates(self, flags, ref_len: int, cap: int | None = None) -> np.ndarray:
+    def list_insert_candidates(self, flags, ref_len: int, cap: int | None = None, stream: int = 0) -> np.ndarray:
+        """1-based positions with TC_CF_INS_CANDIDATE.  ``stream`` must be the stream the producer of a device ``flags`` array
+        (``call_device``) was enqueued on — or that work must have been synchronised."""
         cap = int(ref_len) if cap is None else cap
         out = np.empty(max(cap, 1), np.int32)
         n = C.c_int32(0)
-        self._check(self._lib.tc_list_insert_candidates(self._h, _ptr(flags), int(ref_len), _ptr(out), cap, C.byref(n), 0))
+        self._check(self._lib.tc_list_insert_candidates(self._h, _ptr(flags), int(ref_len), _ptr(out), cap, C.byref(n), stream))
         return out[: n.value].copy()
 
-    def extract_inserts(self, reads, ref_len: int, positions, params: PileupParams | None = None):
+    def extract_inserts(self, reads, ref_len: int, positions, params: PileupParams | None = None, stream: int = 0):
         """ExtractInserts for the given 1-based positions.  Returns a list of dicts with the modal
         upper-cased string of each column (``None`` when pysam would have returned ``""``).
 
@@ -312,7 +314,7 @@ class Context:
         pos = np.ascontiguousarray(positions, dtype=np.int32)
         if pos.shape[0] == 0:
             return []
-        return self._extract_inserts_raw(reads, ref_len, pos, params)
+        return self._extract_inserts_raw(reads, ref_len, pos, params, stream)
 
     @staticmethod
     def _insert_dicts(calls, n: int, bases: np.ndarray):
@@ -381,7 +383,7 @@ class Context:
         self._check(self._lib.tc_sample_finish(self._h, int(ticket), calls, cap, C.byref(n), _ptr(bases), bases.shape[0]))
         return self._insert_dicts(calls, n.value, bases)
 
-    def _extract_inserts_raw(self, reads, ref_len: int, pos: np.ndarray, params: PileupParams):
+    def _extract_inserts_raw(self, reads, ref_len: int, pos: np.ndarray, params: PileupParams, stream: int = 0):
         n = int(pos.shape[0])
         calls = (InsertCall * n)()
         cap = 1 << 16
@@ -389,7 +391,7 @@ class Context:
         while True:
             bases = np.zeros(cap, np.uint8)
             rc = self._lib.tc_extract_inserts(self._h, C.byref(rs), int(ref_len), _ptr(pos), n, C.byref(params), calls,
-                                              _ptr(bases), cap, 0)
+                                              _ptr(bases), cap, stream)
             if rc == -8 and cap < (1 << 30):
                 cap *= 16
                 continue
