@@ -5,13 +5,18 @@
 
 One *step* is one pass of the hot path over one synthetic sample of BASELINE.json configs[1]
 (29,903-bp genome, 2 M ONT-like 400-bp amplicon reads, ~25,000x):
-    tc_pileup_counts (pileup kernel + coverage scan)  ->  tc_call (call kernel + X-run scan)
-    ->  tc_list_insert_candidates  ->  tc_extract_inserts (select/emit, segmented radix sort, mode)
+    pileup kernel + coverage scan -> call kernel + X-run scan -> insertion candidates -> ExtractInserts
+    (select, depth cap, mate-overlap rewrite, count), chained on the device by tc_sample_enqueue / tc_sample_finish:
+    one enqueue and one synchronisation per sample, step i + 1 enqueued before step i is finished.
 `value`  : aligned bases/s with the reads already resident in HBM, CUDA-event timed.
 `e2e`    : the same pass through the C-ABI with HOST (pinned) buffers: the H2D copy of every read
            array and the D2H copy of the count and call tables are inside the timed region.
 N > 1    : one process per GPU (torchrun), each rank piles up its own sample (the 96-sample plate
            of configs[2] sharded by sample): no data-path collective, weak scaling.
+`read_range` (every N): configs[3], ONE ultra-deep sample sharded by read range, the per-rank tables summed
+           with tc_allreduce_counts (NCCL) inside the timed region — strong scaling, checked bit for bit
+           against the single-GPU table.  `configs` (N = 1): tc_pileup_counts on the other configs.
+           `parity_checked`: the GPU table over the cpu_baseline prefix equals the oracle's.
 `--impl reference` times the CPU oracle port of the reference path (oracle/, all host threads) on a
 bounded sample of the same workload; the reference itself is pure Python on pysam, which is not
 installable here, so oracle/_ref does not exist.
@@ -164,6 +169,7 @@ def cpu_port(batch, L, mincov, threads, max_reads):
         cols = pileup.pileup_columns(sub, region=(p - 1, p), **pileup.EXTRACTINSERTS)
         call.extract_insert(cols[0][1] if cols else "")
     t2 = time.perf_counter()
+    cpu_port.last = (sub, counts, cands)        # the oracle's table over the prefix: bench.py's parity check of the GPU path
     return bases, t2 - t0, f"first {sub.n_reads} start-sorted reads of the sample ({bases} aligned bases); pileup {t1 - t0:.2f}s + call/inserts {t2 - t1:.2f}s"
 
 
@@ -187,6 +193,167 @@ def host_decode_rate(batch, L, max_reads=200_000):
     return {"reads": int(back.n_reads), "bam_bytes": int(size), "seconds": dt, "aligned_bases_per_s": bases / dt,
             "threads": os.cpu_count() or 1, "t_inflate_s": float(back.info.get("t_inflate_s", 0.0)),
             "t_parse_s": float(back.info.get("t_parse_s", 0.0))}
+
+
+
+def time_pileup(ctx, dev, L, params, out, steps, warmup, torch):
+    """Mean CUDA-event ms of tc_pileup_counts (device-resident reads, device output) and of its pileup kernel alone."""
+    for _ in range(warmup):
+        ctx.pileup_counts(dev, L, params, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = []
+    e0.record()
+    for _ in range(steps):
+        ctx.pileup_counts(dev, L, params, out=out)
+        k.append(ctx.last_pileup_kernel_ms())
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, statistics.mean(k)
+
+
+def configs_block(ctx, gpu, torch, peak, steps, deep_scale):
+    """The other BASELINE configs on one GPU, device-resident, with a clock record of their own (the driver-run line carries
+    them): tc_pileup_counts per sample — config 1 at full size, one sample of config 3's plate, config 4 at `deep_scale` of
+    its 50 M reads, config 5 at half its reads (the long-read path: span pass, split into pieces, sort, pileup)."""
+    from trueconsense_b200 import synth
+
+    out = {}
+    for idx, scale in ((0, 1.0), (2, 1.0), (3, deep_scale), (4, 0.5)):
+        w = synth.config(idx, scale=scale)
+        b = synth.generate_reads(w.params, w.ref)
+        L = len(w.ref)
+        dev = ctx.upload(b, with_qual=False)
+        table = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")
+        bases = b.count_aligned_bases(0x4)
+        alg = b.algorithmic_bytes(L)
+        ms, k_ms = time_pileup(ctx, dev, L, gpu.buildindex_params(), table, steps, 3, torch)
+        out[w.name] = {"scale": scale, "reads": int(b.n_reads), "ref_len": L, "aligned_bases": int(bases), "algorithmic_bytes": int(alg),
+                       "pileup_counts_ms": ms, "pileup_kernel_ms": k_ms, "aligned_bases_per_s": bases / (ms * 1e-3),
+                       "roofline_frac_kernel": alg / (k_ms * 1e-3) / 1e9 / peak, "roofline_frac_call": alg / (ms * 1e-3) / 1e9 / peak}
+        del dev, table, b
+    return out
+
+
+def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, deep_scale, peak):
+    """BASELINE configs[3]: ONE ultra-deep sample sharded by read range — every rank piles up a contiguous slice of the
+    start-sorted reads into a full-length table, the tables are summed with tc_allreduce_counts (NCCL int32 sum over NVLink)
+    inside the timed region.  Strong scaling: the sample is fixed, the ranks share it.  Rank 0 also piles up the whole sample
+    alone: the summed table must equal that table bit for bit, and its time is the 1-GPU reference of the efficiency."""
+    from trueconsense_b200 import sharding, synth
+
+    w = synth.config(3, scale=deep_scale)
+    n_reads = int(w.params.n_reads)
+    L = len(w.ref)
+    lo, hi = sharding.read_range(n_reads, rank, world)
+    shard = synth.generate_reads(w.params, w.ref, read_range=(lo, hi))
+    dev = ctx.upload(shard, with_qual=False)
+    out = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")
+    p = gpu.buildindex_params()
+    p.max_depth = 0                 # the depth cap is a property of the SUMMED coverage (checked below), not of a shard
+    comm = sharding.NcclComm(rank, world, local) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def one_pass():
+        ctx.pileup_counts(dev, L, p, out=out, stream=stream)
+        if comm is not None:
+            ctx.allreduce_counts(out, comm, stream=stream)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        one_pass()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1) / steps
+    ar_ms = 0.0
+    if comm is not None:            # the collective alone (the table is summed in place over and over: timing only)
+        scratch = out.clone()
+        for _ in range(3):
+            ctx.allreduce_counts(scratch, comm, stream=stream)
+        sync()
+        e0.record()
+        for _ in range(steps):
+            ctx.allreduce_counts(scratch, comm, stream=stream)
+        e1.record()
+        sync()
+        ar_ms = e0.elapsed_time(e1) / steps
+        one_pass()                  # `out` again holds the sum of the shards' tables
+    t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0]), float(t[1])
+    # ---- the single-GPU table and time (rank 0), and the comparison on every rank
+    single = torch.empty_like(out)
+    single_ms = ms
+    if world > 1:
+        if rank == 0:
+            whole = synth.generate_reads(w.params, w.ref)
+            ctx2 = gpu.Context(local)
+            dev2 = ctx2.upload(whole, with_qual=False)
+            single_ms, _ = time_pileup(ctx2, dev2, L, gpu.buildindex_params(), single, steps, 3, torch)
+            bases = whole.count_aligned_bases(0x4)
+            alg = whole.algorithmic_bytes(L)
+            meta = torch.tensor([single_ms, float(bases), float(alg)], dtype=torch.float64, device="cuda")
+            del dev2, ctx2, whole
+        else:
+            meta = torch.zeros(3, dtype=torch.float64, device="cuda")
+        dist.broadcast(single, src=0)
+        dist.broadcast(meta, src=0)
+        single_ms, bases, alg = float(meta[0]), float(meta[1]), float(meta[2])
+        equal = torch.tensor([int(torch.equal(out, single))], device="cuda")
+        dist.all_reduce(equal, op=dist.ReduceOp.MIN)
+        equal = bool(equal.item())
+    else:
+        bases = float(shard.count_aligned_bases(0x4))
+        alg = float(shard.algorithmic_bytes(L))
+        ctx.pileup_counts(dev, L, gpu.buildindex_params(), out=single)      # with the depth cap proven non-binding
+        equal = bool(torch.equal(out, single))
+    sharding.check_depth_cap(int(out[0].max().item()), 0, 10_000_000)
+    if comm is not None:
+        comm.close()
+    block = {
+        "workload": w.name, "sharding": "by read range, tc_allreduce_counts (ncclAllReduce int32 sum) inside the timed region",
+        "scaling": "strong", "n_gpus": world, "reads": n_reads, "reads_per_rank": int(hi - lo), "aligned_bases": bases,
+        "ms_per_pass": ms, "aligned_bases_per_s": bases / (ms * 1e-3), "allreduce_ms": ar_ms, "allreduce_bytes": int(out.numel() * 4),
+        "single_gpu_ms_per_pass": single_ms, "strong_scaling_efficiency": single_ms / (world * ms),
+        "roofline_frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "table_equals_single_gpu": equal,
+        "limiter": ("pileup of the shard (%.3f ms) + allreduce of %.2f MB (%.3f ms: latency-bound on NVLink)" %
+                    (ms - ar_ms, out.numel() * 4 / 1e6, ar_ms)) if world > 1 else "one GPU: no collective",
+    }
+    del dev, out, single
+    return block
+
+
+def h2d_ceiling(torch, dist, world, nbytes, steps=5):
+    """What the box gives all ranks at once for pinned host -> device copies of one sample's size: the end-to-end number is
+    PCIe / host-memory bound, and the ranks share the host's memory path."""
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    devb = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        devb.copy_(host, non_blocking=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        devb.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"bytes_per_rank": int(nbytes), "ms": float(ms[0]), "gb_per_s_per_rank": nbytes / (float(ms[0]) * 1e-3) / 1e9,
+            "gb_per_s_all_ranks": world * nbytes / (float(ms[0]) * 1e-3) / 1e9}
 
 
 def run_reference(args):
@@ -343,8 +510,16 @@ def run_ours(args):
         total_bases, launches = float(tsum[2]), int(tsum[3])
     else:
         total_bases = float(bases)
+    peak, peak_src = peaks()
+    ceiling = h2d_ceiling(torch, dist, world, int(h2d)) if world > 1 or args.h2d_ceiling else None
+    rr = None
+    if not args.no_read_range:
+        rr = read_range_block(ctx, gpu, torch, dist, rank, world, local, args.steps, args.warmup, args.deep_scale, peak)
+    cfgs = None
+    if world == 1 and not args.no_configs:
+        cfgs = configs_block(ctx, gpu, torch, peak, args.steps, args.deep_scale)
+    parity = None
     if rank == 0:
-        peak, peak_src = peaks()
         k_ms = statistics.mean(kernel_ms)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         value = total_bases * args.steps / (ms_total * 1e-3)
@@ -356,6 +531,15 @@ def run_ours(args):
             opile.build()
             cb, ct, desc = cpu_port(batch, L, w.mincov, 1, int(args.cpu_reads))
             cpu = {"value": cb / ct, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+            # parity at benchmark size, outside every timed region: the GPU's table, call flags and insertion candidates over
+            # the same prefix of the benchmarked sample must equal the oracle's
+            sub, o_counts, o_cands = cpu_port.last
+            g_counts = ctx.pileup_counts(sub, L, params)
+            g_res = ctx.call(g_counts, L, w.mincov, True)
+            g_cands = ctx.list_insert_candidates(g_res.flags, L)
+            parity = bool(np.array_equal(g_counts, o_counts)) and list(g_cands) == list(o_cands)
+            if not parity:
+                raise SystemExit("bench.py: the GPU count table / candidates differ from the oracle's on the benchmarked sample")
         try:
             decode = host_decode_rate(batch, L)
         except Exception as e:      # reporting aid only
@@ -367,7 +551,9 @@ def run_ours(args):
             "config": {"workload": w.name, "ref_len": L, "reads_per_sample": batch.n_reads, "samples": world,
                        "aligned_bases_per_sample": bases, "mincov": w.mincov, "sharding": "by sample, no collective",
                        "l2": f"inputs {alg_bytes / 1e6:.0f} MB per pass exceed the 126 MB L2 (no flush needed)",
-                       "insert_candidates": len(calls)},
+                       "insert_candidates": len(calls),
+                       "step": "tc_sample_enqueue + tc_sample_finish (chained, step i + 1 enqueued before step i is finished)"
+                               if not args.unchained else "four separate calls, three synchronisations"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "pileup kernel (tc_pileup_counts)", "kernel_ms": k_ms,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
@@ -377,7 +563,13 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "host_decode": decode,
+            "parity_checked": parity,
+            "read_range": rr,
+            "configs": cfgs,
         }
+        if ceiling is not None:
+            line["e2e"]["h2d_ceiling"] = ceiling
+            line["e2e"]["h2d_frac_of_ceiling"] = (h2d / (e2e_ms / args.steps * 1e-3) / 1e9) / ceiling["gb_per_s_per_rank"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -393,6 +585,10 @@ def main():
     ap.add_argument("--unchained", action="store_true", help="the four separate calls per step (three synchronisations) instead of tc_sample_enqueue / tc_sample_finish")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 2 M reads of configs[1] (tests only)")
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed passes before the warm-up steps (clock / driver spin-up of a cold GPU)")
+    ap.add_argument("--deep-scale", type=float, default=0.2, help="fraction of configs[3]'s 50 M reads in the read-range block and the configs block (0.2 = 10 M reads)")
+    ap.add_argument("--no-read-range", action="store_true", help="skip the read-range sharded block (configs[3])")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (N = 1 only)")
+    ap.add_argument("--h2d-ceiling", action="store_true", help="also measure the concurrent pinned H2D ceiling at N = 1")
     ap.add_argument("--cpu-reads", type=float, default=1_000_000, help="reads in the cpu_baseline sample (1 M reads = 400 M aligned bases, 10-15 s on one core)")
     ap.add_argument("--ref-reads", type=float, default=400_000, help="reads per step of the --impl reference arm")
     args = ap.parse_args()

@@ -98,6 +98,9 @@ typedef struct tc_synth_params {
 /* ref_codes: ref_len 4-bit base codes (1,2,4,8), one per byte. */
 int  tc_synth_reads(const tc_synth_params_t* p, const uint8_t* ref_codes, int n_threads,
                     tc_hostreads_t* out, char* err, int errlen);
+/* reads [r0, r1) of that start-sorted set only (r1 < 0: to the end) */
+int  tc_synth_reads_range(const tc_synth_params_t* p, const uint8_t* ref_codes, int n_threads, int64_t r0, int64_t r1,
+                          tc_hostreads_t* out, char* err, int errlen);
 
 #ifdef __cplusplus
 }

@@ -1030,3 +1030,30 @@ def test_config1_full_size_insertion_inside_mate_overlap(ctx, orc):
         assert (g["string"], g["n_entries"], g["mode_count"]) == want, g["pos"]
         n_diff += want[1] != _expected_call(pileup, call, b, g["pos"], reserved=1 << 8)[1]
     assert n_diff > 0           # the rewrite does change these columns
+
+
+# ---------------------------------------------------------------------------- benchmark sizes
+@pytest.mark.parametrize("idx,scale", [(1, 1.0), (3, 0.1), (4, 1.0)])
+def test_full_size_configs_vs_oracle(ctx, orc, idx, scale):
+    """BASELINE configs[1] (2 M ONT-like reads: the benchmarked sample), configs[3] at 5 M reads and configs[4] (98.5 k reads
+    of 10 kb) at FULL size: the count table equals the multi-threaded oracle's bit for bit; for configs[1] also the chained
+    sample call — every insertion candidate (depth 25,000: the 8000-read cap drops two thirds of each column) against the
+    oracle's column."""
+    import os
+
+    from trueconsense_b200 import synth
+
+    pileup, call = orc
+    w = synth.config(idx, scale=scale)
+    b = synth.generate_reads(w.params, w.ref)
+    L = len(w.ref)
+    exp = pileup.pileup_counts(b, L, threads=os.cpu_count() or 8)
+    if idx != 1:
+        assert np.array_equal(ctx.pileup_counts(b, L), exp)
+        return
+    counts, flags, _, _, ins = _chained(ctx, b, L, w.mincov, ctx.upload(b))
+    assert np.array_equal(counts, exp)
+    cands = call.insert_candidates(exp.astype(np.int64), w.mincov)
+    assert [g["pos"] for g in ins] == cands and len(cands) >= 3
+    for g in ins:
+        assert (g["string"], g["n_entries"], g["mode_count"]) == _expected_call(pileup, call, b, g["pos"]), g["pos"]

@@ -61,6 +61,7 @@ struct ins_args {
     uint8_t* pair_q; unsigned long long pair_cap; unsigned long long* pair_bump;   // scratch for the rewritten quality strings of paired reads
     int olap_mode;                  // mate-overlap rewriting: 0 htslib >= 1.13, 1 off, 2 htslib <= 1.12 (tc_pileup_params_t.reserved bits 8-9)
     int32_t* seg_count;             // [n_cand] admitted entries
+    int32_t* pair_any;              // [n_cand] some selected read of the column is one of a proper pair (else ins_pair_kernel has nothing to pair)
     int32_t* overflow;              // [1] some column had more distinct keys than INS_TBL holds
     const int32_t* layout;          // device-built layout (ins_layout_kernel): [0] tiles, [1] slots, [2] 1 = did not fit; NULL: host-built
     uint8_t* bases_fixed;           // [n_cand][INS_BASES_FIXED] inserted characters of each winner (longer ones: ins_bases_kernel)
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
     const int c = a.cand[ci] - 1;
     const int lo = a.range[2 * ci], hi = a.range[2 * ci + 1];
     const int r = lo + (tile - a.tile_first[ci]) * INS_TILE + threadIdx.x;
-    bool sel = false, emit = false;
+    bool sel = false, emit = false, proper = false;
     if (r < hi) {
         const int pos = a.r.pos[r];
         if (r > 0 && pos < a.r.pos[r - 1]) atomicCAS(&a.status->err, 0, TC_ERR_UNSORTED);
@@ -272,7 +273,9 @@ __global__ void __launch_bounds__(INS_TILE) ins_select_kernel(ins_args a) {
         a.ent_key[slot] = key; a.ent_indel[slot] = indel; a.ent_qpos[slot] = qpos; a.ent_head[slot] = (uint8_t)head;
         a.ent_sel[slot] = (uint8_t)((sel ? 1 : 0) | (emit ? 2 : 0));
         a.ent_q[slot] = (uint8_t)qv;
+        proper = sel && (fl & 2u);
     }
+    if (__syncthreads_or(proper) && threadIdx.x == 0) a.pair_any[ci] = 1;
     const int nsel = __syncthreads_count(sel);
     int last = __reduce_max_sync(0xffffffffu, sel ? r : -1);
     if ((threadIdx.x & 31) == 0) wlast[threadIdx.x >> 5] = last;
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(1024) ins_pair_kernel(ins_args a) {
     const int64_t off = a.seg_off[ci];
     const int lo = a.range[2 * ci];
     const int n = a.range[2 * ci + 1] - lo;
-    const bool pairing = a.olap_mode != 1 && a.r.qname_hash && a.r.mpos && a.r.isize;
+    const bool pairing = a.olap_mode != 1 && a.r.qname_hash && a.r.mpos && a.r.isize && a.pair_any[ci];
     if (threadIdx.x == 0) { over_s = 0; nadm_s = 0; }
     if (pairing) {
         for (int i = threadIdx.x; i < PAIR_TBL; i += blockDim.x) { tmin[i] = 0u; tmax[i] = 0u; tcnt[i] = 0; }
@@ -485,25 +488,32 @@ __global__ void __launch_bounds__(1024) ins_pair_kernel(ins_args a) {
             push = true;
             return true;
         };
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            bool push;
-            if (!is_event(i, push)) continue;
-            const uint32_t r = (uint32_t)(lo + i);
-            if (push && !(a.r.flag[r] & 2u)) continue;          // never in the table, never paired (cheap early out)
-            const unsigned long long k = a.r.qname_hash[r];
-            unsigned h = (unsigned)(k ^ (k >> 31)) & (PAIR_TBL - 1);
-            int probes = 0;
-            for (;;) {
-                const unsigned cur = atomicCAS(&tmin[h], 0u, (unsigned)i + 1u);
-                if (cur == 0u || a.r.qname_hash[lo + cur - 1] == k) {
-                    atomicMin(&tmin[h], (unsigned)i + 1u); atomicMax(&tmax[h], (unsigned)i + 1u);
-                    // (16-bit counter: two atomics on the containing word)
-                    atomicAdd(reinterpret_cast<unsigned int*>(tcnt) + (h >> 1), (h & 1) ? 0x10000u : 1u);
-                    break;
+        // pass 1: the pushed reads of proper pairs open the groups (at most max_depth + a few of them); pass 2: the reads the
+        // depth cap dropped only JOIN the group of their name, if there is one (a deep unpaired sample drops tens of thousands
+        // of reads per column: none of them may take a table slot)
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                bool push;
+                if (!is_event(i, push) || push != (pass == 0)) continue;
+                const uint32_t r = (uint32_t)(lo + i);
+                if (push && !(a.r.flag[r] & 2u)) continue;          // never in the table, never paired
+                const unsigned long long k = a.r.qname_hash[r];
+                unsigned h = (unsigned)(k ^ (k >> 31)) & (PAIR_TBL - 1);
+                int probes = 0;
+                for (;;) {
+                    const unsigned cur = push ? atomicCAS(&tmin[h], 0u, (unsigned)i + 1u) : tmin[h];
+                    if (cur == 0u && !push) break;                  // no pushed read of that name
+                    if (cur == 0u || a.r.qname_hash[lo + cur - 1] == k) {
+                        atomicMin(&tmin[h], (unsigned)i + 1u); atomicMax(&tmax[h], (unsigned)i + 1u);
+                        // (16-bit counter: an atomic on the containing word)
+                        atomicAdd(reinterpret_cast<unsigned int*>(tcnt) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                        break;
+                    }
+                    h = (h + 1) & (PAIR_TBL - 1);
+                    if (++probes >= PAIR_TBL * 3 / 4) { over_s = 1; break; }
                 }
-                h = (h + 1) & (PAIR_TBL - 1);
-                if (++probes >= PAIR_TBL * 3 / 4) { over_s = 1; break; }
             }
+            __syncthreads();
         }
         __syncthreads();
         if (over_s) { if (threadIdx.x == 0) atomicCAS(&a.status->err, 0, TC_ERR_CAPACITY); return; }
@@ -761,7 +771,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     // results block: status, layout, overflow flag, admitted counts, the calls and their inserted characters — one
     // memset in front, one copy back
     const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_BUMP = 88, RB_SEG = 96;
-    const size_t rb_calls = RB_SEG + ((4 * ((size_t)n_cand + 1) + 15) & ~(size_t)15);
+    const size_t rb_calls = RB_SEG + ((4 * (2 * (size_t)n_cand + 2) + 15) & ~(size_t)15);     // seg_count, then pair_any
     const size_t rb_fixed = rb_calls + sizeof(tc_insert_call_t) * (size_t)n_cand;
     const size_t rb_bytes = rb_fixed + (size_t)n_cand * INS_BASES_FIXED;
     static_assert(sizeof(tc_status) <= 64, "tc_status outgrew its place in the results block");
@@ -869,7 +879,7 @@ TC_API int tc_extract_inserts(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t re
     a.ent_indel = (int32_t*)(d_off + n_cand + 1); a.ent_qpos = a.ent_indel + T;
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + n_cand + 1; a.tile_last = a.tile_sel + NT;
-    a.seg_count = (int32_t*)(d_rb + RB_SEG); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    a.seg_count = (int32_t*)(d_rb + RB_SEG); a.pair_any = a.seg_count + n_cand + 1; a.overflow = (int32_t*)(d_rb + RB_OVER);
     if (ctx->pair_cap <= 0) ctx->pair_cap = 1 << 22;
     a.pair_bump = (unsigned long long*)(d_rb + RB_BUMP); a.pair_cap = (unsigned long long)ctx->pair_cap;
     a.pair_q = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_F, (size_t)ctx->pair_cap);
@@ -1041,7 +1051,7 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
     const int64_t n = a.r.n;
     const size_t RB_LAYOUT = 64, RB_OVER = 80, RB_EXTRA = 128;      // extra: [0] n_cand, [16..32) pileup status, [32..32+cap) candidates
     const size_t rb_seg = RB_EXTRA + 4 * (32 + (size_t)cap);
-    const size_t rb_calls = rb_seg + ((4 * ((size_t)cap + 1) + 15) & ~(size_t)15);
+    const size_t rb_calls = rb_seg + ((4 * (2 * (size_t)cap + 2) + 15) & ~(size_t)15);         // seg_count, then pair_any
     const size_t rb_fixed = rb_calls + sizeof(tc_insert_call_t) * (size_t)cap;
     const size_t rb_bytes = rb_fixed + (size_t)cap * INS_BASES_FIXED;
     if (rb_bytes > TC_HOST_SCRATCH) return tc_fail(ctx, TC_ERR_ARG, "candidate capacity %d too large for the pinned results block", cap);
@@ -1071,7 +1081,7 @@ int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* 
     a.ent_indel = (int32_t*)(d_off + cap + 1); a.ent_qpos = a.ent_indel + T;
     int32_t* d_tcand = a.ent_qpos + T; int32_t* d_tfirst = d_tcand + NT;
     a.tile_sel = d_tfirst + cap + 1; a.tile_last = a.tile_sel + NT;
-    a.seg_count = (int32_t*)(d_rb + rb_seg); a.overflow = (int32_t*)(d_rb + RB_OVER);
+    a.seg_count = (int32_t*)(d_rb + rb_seg); a.pair_any = a.seg_count + cap + 1; a.overflow = (int32_t*)(d_rb + RB_OVER);
     if (ctx->pair_cap <= 0) ctx->pair_cap = 1 << 22;
     a.pair_bump = (unsigned long long*)(d_rb + 88); a.pair_cap = (unsigned long long)ctx->pair_cap;
     a.pair_q = (uint8_t*)tc_dev_buf(ctx, SLOT_INS_F, (size_t)ctx->pair_cap);

@@ -202,6 +202,13 @@ static void gen_read(const tc_synth_params_t* P, const uint8_t* ref, const place
 
 int tc_synth_reads(const tc_synth_params_t* P, const uint8_t* ref, int n_threads, tc_hostreads_t* out,
                    char* err, int errlen) {
+    return tc_synth_reads_range(P, ref, n_threads, 0, -1, out, err, errlen);
+}
+
+/* Reads [r0, r1) of the start-sorted set tc_synth_reads would produce (r1 < 0: to the end): every read draws from its own
+ * stream, so a shard is generated without the others — what a rank of a read-range sharded run needs. */
+int tc_synth_reads_range(const tc_synth_params_t* P, const uint8_t* ref, int n_threads, int64_t r0, int64_t r1,
+                         tc_hostreads_t* out, char* err, int errlen) {
     memset(out, 0, sizeof(*out));
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_num_procs();
@@ -261,11 +268,18 @@ int tc_synth_reads(const tc_synth_params_t* P, const uint8_t* ref, int n_threads
     for (int i = 0; i < L; ++i) bucket[i + 1] += bucket[i];
     for (int64_t i = 0; i < n; ++i) sorted[bucket[pl[i].start]++] = pl[i];
     free(bucket); free(pl);
+    /* the shard: from here on `sorted` / `n` are its reads only */
+    place_t* sorted_all = sorted;
+    if (r1 < 0 || r1 > n) r1 = n;
+    if (r0 < 0) r0 = 0;
+    if (r0 > r1) r0 = r1;
+    sorted = sorted_all + r0;
+    n = r1 - r0;
 
     /* (2) sizes */
     uint32_t* nops = malloc(4 * (size_t)(n + 1));
     uint32_t* lseq = malloc(4 * (size_t)(n + 1));
-    if (!nops || !lseq) { free(sorted); free(nops); free(lseq); return sfail(err, errlen, -5, "out of memory"); }
+    if (!nops || !lseq) { free(sorted_all); free(nops); free(lseq); return sfail(err, errlen, -5, "out of memory"); }
 #pragma omp parallel for schedule(static) num_threads(n_threads)
     for (int64_t i = 0; i < n; ++i) {
         gen_t g; memset(&g, 0, sizeof(g));
@@ -276,11 +290,11 @@ int tc_synth_reads(const tc_synth_params_t* P, const uint8_t* ref, int n_threads
     uint64_t sw = 0, co = 0;
     for (int64_t i = 0; i < n; ++i) { sw += (lseq[i] + 7) / 8; co += nops[i]; }
     if (sw > 0xffffffffULL || co > 0xffffffffULL) {
-        free(sorted); free(nops); free(lseq);
+        free(sorted_all); free(nops); free(lseq);
         return sfail(err, errlen, -7, "synthetic batch too large for 32-bit offsets; generate per shard");
     }
     if (tc_hostreads_alloc_(out, n, (int64_t)sw, (int64_t)co) != 0) {
-        free(sorted); free(nops); free(lseq); tc_hostreads_free(out);
+        free(sorted_all); free(nops); free(lseq); tc_hostreads_free(out);
         return sfail(err, errlen, -5, "out of memory");
     }
     sw = 0; co = 0;
@@ -326,7 +340,7 @@ int tc_synth_reads(const tc_synth_params_t* P, const uint8_t* ref, int n_threads
         }
         free(sq); free(ql);
     }
-    free(sorted); free(nops); free(lseq);
+    free(sorted_all); free(nops); free(lseq);
     out->aligned_bases = aligned; out->max_ref_span = maxspan; out->sorted = 1;
     out->n_records = n; out->n_ref = 1;
     out->ref_len = malloc(sizeof(int32_t)); out->ref_len[0] = L;

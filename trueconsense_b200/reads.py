@@ -120,14 +120,13 @@ class ReadBatch:
         handling never pairs such reads).  The batch itself keeps the BAM's PNEXT."""
         if self.tid is None or self.mtid is None:
             return self.mpos
-        other = (self.mtid >= 0) & (self.mtid != self.tid)
-        if not other.any():
-            return self.mpos
-        cached = getattr(self, "_mpos_abi", None)
-        if cached is None or cached.shape != self.mpos.shape:
-            cached = np.where(other, np.int32(-2), self.mpos).astype(np.int32)
+        cached = getattr(self, "_mpos_abi", None)           # (computed once per batch: c_struct() is on the per-sample path)
+        if cached is None or cached[0] is not self.mpos:
+            other = (self.mtid >= 0) & (self.mtid != self.tid)
+            arr = np.where(other, np.int32(-2), self.mpos).astype(np.int32) if other.any() else self.mpos
+            cached = (self.mpos, arr)
             object.__setattr__(self, "_mpos_abi", cached)
-        return cached
+        return cached[1]
 
     # ------------------------------------------------------------------ derived quantities
     def ref_spans(self) -> np.ndarray:

@@ -88,12 +88,14 @@ def encode_ref(ref: str) -> np.ndarray:
     return lut[np.frombuffer(ref.encode(), dtype=np.uint8)]
 
 
-def generate_reads(p: SynthParams, ref: str | np.ndarray, threads: int = 0) -> ReadBatch:
+def generate_reads(p: SynthParams, ref: str | np.ndarray, threads: int = 0, read_range: tuple[int, int] | None = None) -> ReadBatch:
+    """The start-sorted synthetic read set — or, with ``read_range`` = (r0, r1), only its reads [r0, r1) (every read draws from
+    its own stream: a shard equals the slice of the whole)."""
     lib = bamio.host_lib()
     if not hasattr(lib, "_synth_ready"):
-        lib.tc_synth_reads.argtypes = [C.POINTER(_SynthParams), C.c_void_p, C.c_int, C.POINTER(bamio.TcHostReads),
-                                       C.c_char_p, C.c_int]
-        lib.tc_synth_reads.restype = C.c_int
+        lib.tc_synth_reads_range.argtypes = [C.POINTER(_SynthParams), C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                             C.POINTER(bamio.TcHostReads), C.c_char_p, C.c_int]
+        lib.tc_synth_reads_range.restype = C.c_int
         lib._synth_ready = True
     codes = encode_ref(ref) if isinstance(ref, str) else np.ascontiguousarray(ref, dtype=np.uint8)
     vs = sorted(p.variants, key=lambda v: v.pos)
@@ -111,7 +113,8 @@ def generate_reads(p: SynthParams, ref: str | np.ndarray, threads: int = 0) -> R
     )
     hr = bamio.TcHostReads()
     err = C.create_string_buffer(512)
-    rc = lib.tc_synth_reads(C.byref(sp), codes.ctypes.data, threads, C.byref(hr), err, len(err))
+    r0, r1 = (0, -1) if read_range is None else (int(read_range[0]), int(read_range[1]))
+    rc = lib.tc_synth_reads_range(C.byref(sp), codes.ctypes.data, threads, r0, r1, C.byref(hr), err, len(err))
     if rc != 0:
         raise RuntimeError(f"tc_synth_reads failed ({rc}): {err.value.decode(errors='replace')}")
     b = bamio.batch_from_hostreads(hr, lib)
