@@ -212,14 +212,19 @@ def time_pileup(ctx, dev, L, params, out, steps, warmup, torch):
     return e0.elapsed_time(e1) / steps, statistics.mean(k)
 
 
-def configs_block(ctx, gpu, torch, peak, steps, deep_scale):
+def configs_block(ctx, gpu, torch, peak, steps, deep):
     """The other BASELINE configs on one GPU, device-resident, with a clock record of their own (the driver-run line carries
     them): tc_pileup_counts per sample — config 1 at full size, one sample of config 3's plate, config 4 at `deep_scale` of
-    its 50 M reads, config 5 at half its reads (the long-read path: span pass, split into pieces, sort, pileup)."""
+    its 50 M reads (the read_range block's single-GPU pass: `deep`), config 5 at half its reads (the long-read path: span
+    pass, split into pieces, sort, pileup)."""
     from trueconsense_b200 import synth
 
     out = {}
-    for idx, scale in ((0, 1.0), (2, 1.0), (3, deep_scale), (4, 0.5)):
+    if deep is not None:
+        out[deep["workload"]] = {"reads": deep["reads"], "aligned_bases": deep["aligned_bases"], "pileup_counts_ms": deep["single_gpu_ms_per_pass"],
+                                 "aligned_bases_per_s": deep["aligned_bases"] / (deep["single_gpu_ms_per_pass"] * 1e-3),
+                                 "roofline_frac_call": deep["roofline_frac"], "note": "the read_range block's pass on one GPU"}
+    for idx, scale in ((0, 1.0), (2, 1.0), (4, 0.5)):
         w = synth.config(idx, scale=scale)
         b = synth.generate_reads(w.params, w.ref)
         L = len(w.ref)
@@ -329,7 +334,10 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
         "limiter": ("pileup of the shard (%.3f ms) + allreduce of %.2f MB (%.3f ms: latency-bound on NVLink)" %
                     (ms - ar_ms, out.numel() * 4 / 1e6, ar_ms)) if world > 1 else "one GPU: no collective",
     }
-    del dev, out, single
+    del dev, out, single, shard
+    import gc
+
+    gc.collect()
     return block
 
 
@@ -389,6 +397,7 @@ def run_reference(args):
 
 
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line and nothing else
     import torch
     import torch.distributed as dist
 
@@ -517,7 +526,7 @@ def run_ours(args):
         rr = read_range_block(ctx, gpu, torch, dist, rank, world, local, args.steps, args.warmup, args.deep_scale, peak)
     cfgs = None
     if world == 1 and not args.no_configs:
-        cfgs = configs_block(ctx, gpu, torch, peak, args.steps, args.deep_scale)
+        cfgs = configs_block(ctx, gpu, torch, peak, args.steps, rr)
     parity = None
     if rank == 0:
         k_ms = statistics.mean(kernel_ms)
@@ -585,7 +594,7 @@ def main():
     ap.add_argument("--unchained", action="store_true", help="the four separate calls per step (three synchronisations) instead of tc_sample_enqueue / tc_sample_finish")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 2 M reads of configs[1] (tests only)")
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed passes before the warm-up steps (clock / driver spin-up of a cold GPU)")
-    ap.add_argument("--deep-scale", type=float, default=0.2, help="fraction of configs[3]'s 50 M reads in the read-range block and the configs block (0.2 = 10 M reads)")
+    ap.add_argument("--deep-scale", type=float, default=1.0, help="fraction of configs[3]'s 50 M reads in the read-range block (1.0: the whole sample, 4.8 GB of read arrays on one GPU)")
     ap.add_argument("--no-read-range", action="store_true", help="skip the read-range sharded block (configs[3])")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (N = 1 only)")
     ap.add_argument("--h2d-ceiling", action="store_true", help="also measure the concurrent pinned H2D ceiling at N = 1")
