@@ -303,7 +303,7 @@ int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, con
     const bool direct = variant == 3;
     pend->span_hint = a.span_hint;
     if (a.r.n > 0) {
-        if (ctx->timing) TC_CUDA(cudaEventRecord(ctx->ev0, s));
+        if (ctx->timing) TC_CUDA(cudaEventRecordWithFlags(ctx->ev0, s, ctx->in_capture ? cudaEventRecordExternal : cudaEventRecordDefault));
         if (variant != 1) {
             // coverage ends, span statistics and the sortedness / range checks: one thread per read — unless the
             // caller bounded the longest span, then variant 3 does all of that while it walks the CIGARs anyway
@@ -333,7 +333,7 @@ int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, con
             }
             TC_LAUNCH_CHECK();
         }
-        if (ctx->timing) { TC_CUDA(cudaEventRecord(ctx->ev1, s)); ctx->ev_valid = 1; }
+        if (ctx->timing) { TC_CUDA(cudaEventRecordWithFlags(ctx->ev1, s, ctx->in_capture ? cudaEventRecordExternal : cudaEventRecordDefault)); ctx->ev_valid = 1; }
     }
     if (!per_entry) {
         rc = coverage_scan(ctx, d_diff, d_counts, L, d_status, variant != 1 ? a.xi : nullptr, s);

@@ -57,9 +57,39 @@ void tc_sample_slots_free(tc_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->samples[i].host_block) cudaFreeHost(ctx->samples[i].host_block);
         if (ctx->samples[i].done) { cudaEventDestroy(ctx->samples[i].done); cudaEventDestroy(ctx->samples[i].t0); cudaEventDestroy(ctx->samples[i].t1); }
+        if (ctx->samples[i].exec) cudaGraphExecDestroy(ctx->samples[i].exec);
     }
     free(ctx->samples);
     ctx->samples = nullptr;
+    if (ctx->cap_stream) { cudaStreamDestroy(ctx->cap_stream); ctx->cap_stream = nullptr; }
+}
+
+// everything the enqueued work depends on: the same key means the same kernels with the same arguments
+static int sample_key(const tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* pp, const tc_call_params_t* cp,
+                      const tc_pileup_params_t* ip, const int32_t* counts, const tc_call_table_t* table, unsigned char* key) {
+    int n = 0;
+    auto put = [&](const void* p, size_t bytes) { memcpy(key + n, p, bytes); n += (int)bytes; };
+    put(reads, sizeof(*reads)); put(&ref_len, 4); put(pp, sizeof(*pp)); put(cp, sizeof(*cp)); put(ip, sizeof(*ip));
+    put(&counts, sizeof(counts)); put(table, sizeof(*table));
+    put(&ctx->buf_epoch, 8); put(&ctx->ins_slot_cap, 8); put(&ctx->pair_cap, 8); put(&ctx->timing, 4);
+    return n;
+}
+static_assert(sizeof(tc_reads_t) + 4 + 2 * sizeof(tc_pileup_params_t) + sizeof(tc_call_params_t) + 8 + sizeof(tc_call_table_t) + 28 <= 512, "sample key");
+
+static int sample_enqueue_chain(tc_ctx* ctx, tc_sample_slot& sl, cudaStream_t s) {
+    // timing on: the events around the pileup kernel are this sample's own (two samples may be in flight)
+    const cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    sl.timed = ctx->timing;
+    if (ctx->timing) { ctx->ev0 = sl.t0; ctx->ev1 = sl.t1; }
+    int rc = tc_pileup_enqueue(ctx, &sl.reads, sl.ref_len, &sl.pp, sl.counts, s, &sl.pend);
+    ctx->ev0 = e0; ctx->ev1 = e1;
+    if (rc) return rc;
+    rc = tc_call(ctx, sl.counts, sl.ref_len, &sl.cp, &sl.table, (void*)s);       // device outputs only: enqueues and returns
+    if (rc) return rc;
+    int32_t *d_ncand, *d_cand;
+    rc = tc_candidates_enqueue(ctx, sl.table.flags, sl.ref_len, TC_SAMPLE_MAX_CAND, &d_ncand, &d_cand, s);
+    if (rc) return rc;
+    return tc_inserts_enqueue_dev(ctx, &sl.reads, d_cand, d_ncand, TC_SAMPLE_MAX_CAND, &sl.ip, sl.pend.d_status, sl.host_block, s, &sl.ipend);
 }
 
 TC_API int tc_sample_enqueue(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* pp,
@@ -84,20 +114,48 @@ TC_API int tc_sample_enqueue(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref
     if (!all_device(reads) || !table_dev || pp->min_base_quality > 0) {
         sl.state = 2;           // inputs the chained form does not take: the separate calls, at finish time
     } else {
-        // timing on: the events around the pileup kernel are this sample's own (two samples may be in flight)
-        const cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
-        sl.timed = ctx->timing;
-        if (ctx->timing) { ctx->ev0 = sl.t0; ctx->ev1 = sl.t1; }
-        rc = tc_pileup_enqueue(ctx, reads, ref_len, pp, counts, s, &sl.pend);
-        ctx->ev0 = e0; ctx->ev1 = e1;
-        if (rc) return rc;
-        rc = tc_call(ctx, counts, ref_len, cp, table, stream);       // device outputs only: enqueues and returns
-        if (rc) return rc;
-        int32_t *d_ncand, *d_cand;
-        rc = tc_candidates_enqueue(ctx, t.flags, ref_len, TC_SAMPLE_MAX_CAND, &d_ncand, &d_cand, s);
-        if (rc) return rc;
-        rc = tc_inserts_enqueue_dev(ctx, reads, d_cand, d_ncand, TC_SAMPLE_MAX_CAND, ip, sl.pend.d_status, sl.host_block, s, &sl.ipend);
-        if (rc) return rc;
+        unsigned char key[512];
+        const int key_len = sample_key(ctx, reads, ref_len, pp, cp, ip, counts, table, key);
+        const bool same = sl.key_len == key_len && memcmp(sl.key, key, (size_t)key_len) == 0;
+        if (!same) {
+            if (sl.exec) { cudaGraphExecDestroy(sl.exec); sl.exec = nullptr; }
+            memcpy(sl.key, key, (size_t)key_len); sl.key_len = key_len; sl.key_seen = 0;
+        }
+        if (same && sl.exec) {
+            // the same sample shape with the same buffers again: replay
+            TC_CUDA(cudaGraphLaunch(sl.exec, s));
+            ctx->launches += sl.g_launches; ctx->d2h_bytes += sl.g_d2h;
+        } else if (same && sl.key_seen >= 1 && !getenv("TC_NO_GRAPH")) {
+            // second time: every buffer exists (the eager run allocated them) — capture the chain and launch it as a graph
+            if (!ctx->cap_stream) TC_CUDA(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+            const int64_t l0 = ctx->launches, d0 = ctx->d2h_bytes, epoch0 = ctx->buf_epoch;
+            TC_CUDA(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeRelaxed));
+            ctx->in_capture = 1;
+            rc = sample_enqueue_chain(ctx, sl, ctx->cap_stream);
+            ctx->in_capture = 0;
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+            if (rc == TC_OK && ce == cudaSuccess && graph && ctx->buf_epoch == epoch0) {
+                const cudaError_t ie = cudaGraphInstantiate(&sl.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) { sl.exec = nullptr; return tc_cuda_fail(ctx, ie, "cudaGraphInstantiate"); }
+                sl.g_launches = ctx->launches - l0; sl.g_d2h = ctx->d2h_bytes - d0;
+                TC_CUDA(cudaGraphLaunch(sl.exec, s));
+            } else {
+                // something in the chain could not be captured (or a buffer grew): run it eagerly, try again next time
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                ctx->launches = l0; ctx->d2h_bytes = d0;
+                if (rc && rc != TC_ERR_CUDA) return rc;
+                sl.key_len = 0;
+                rc = sample_enqueue_chain(ctx, sl, s);
+                if (rc) return rc;
+            }
+        } else {
+            rc = sample_enqueue_chain(ctx, sl, s);
+            if (rc) return rc;
+            sl.key_seen++;
+        }
         TC_CUDA(cudaEventRecord(sl.done, s));
         sl.state = 1;
     }

@@ -45,6 +45,9 @@ struct tc_ctx {
     int64_t ins_slot_cap;   // tc_extract_inserts: entry slots its speculative (no read-back) layout may use; grows on demand
     struct tc_sample_slot* samples;     // [2] samples in flight (tc_sample_enqueue / tc_sample_finish), allocated on first use
     int sample_next;
+    int64_t buf_epoch;      // bumped whenever a context buffer is (re)allocated: captured graphs hold the old addresses
+    cudaStream_t cap_stream;    // the stream sample graphs are captured on (a user's legacy default stream cannot be captured)
+    int in_capture;         // timing events inside a capture are recorded as external event nodes
     float finished_ms;      // timing on: pileup-kernel duration of the sample tc_sample_finish returned last (< 0: none)
 };
 
@@ -126,6 +129,10 @@ struct tc_sample_slot {
     int timed;
     tc_reads_t reads; int32_t ref_len; tc_pileup_params_t pp, ip; tc_call_params_t cp; int32_t* counts; tc_call_table_t table; void* stream;
     tc_pileup_pending pend; tc_ins_pending ipend;
+    // the sample's enqueue as a CUDA graph: the first enqueue with a key runs eagerly (and allocates), the second is captured,
+    // later ones replay — one launch per sample instead of ~25 (kernels, memsets, the results copy)
+    unsigned char key[512]; int key_len; int key_seen;
+    cudaGraphExec_t exec; int64_t g_launches, g_d2h;
 };
 
 // ---------------------------------------------------------------- device helpers

@@ -35,6 +35,7 @@ void* tc_dev_buf(tc_ctx* ctx, int slot, size_t bytes) {
         return NULL;
     }
     b->p = p; b->cap = cap;
+    ctx->buf_epoch++;
     return p;
 }
 
