@@ -75,60 +75,67 @@ def WriteGFF(gffheader, gffdict, output_gff, name):
             out.write(_gff_line(feature))
 
 
+VCF_HEADER = ("##fileformat=VCFv4.3\n"
+              "##fileDate={today}\n"
+              "##source='TrueConsense {argv}'\n"
+              "##reference='{ref}'\n"
+              "##contig=<ID={contig}>\n"
+              '##INFO=<ID=DP,Number=1,Type=Integer,Description="Read Depth">\n'
+              '##INFO=<ID=INDEL,Number=0,Type=Flag,Description="Indicates that the variant is an INDEL.">\n'
+              "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+
+
+def _vcf_records(contig, reference, called, index, mincov, inserts):
+    """The reference's variant records (Outputs.py:131-180), one text line at a time and in its order, from the reference
+    residues, the upper-cased consensus without insertions and ListInserts' result.  Its coordinate quirks are part of the
+    format and kept: a deletion is reported on the 0-based index of its first column with the
+    base before it; a substitution on index + 1 with the depth of position max(index, 1) + 1; an insertion where the 0-based
+    index equals the 1-based insertion position, i.e. one column late."""
+    has_inserts, by_position = inserts
+    covered_by_deletion = set()
+    for i, ref_base in enumerate(reference):
+        if i in covered_by_deletion:
+            continue
+        base = called[i]
+        if base != ref_base:
+            if base == "-":
+                j = i
+                deleted = []
+                while called[j] == "-":         # (runs off the end like the reference: IndexError on a trailing deletion)
+                    deleted.append(reference[j])
+                    covered_by_deletion.add(j)
+                    j += 1
+                yield (f"{contig}\t{i}\t.\t{reference[i - 1] + ''.join(deleted)}\t{called[i - 1]}\t.\tPASS\t"
+                       f"DP={GetCoverage(index, i + 1)};INDEL\n")
+            else:
+                depth_at = (1 if i < 2 else i) + 1
+                yield f"{contig}\t{i + 1}\t.\t{ref_base}\t{base}\t.\tPASS\tDP={GetCoverage(index, depth_at)}\n"
+        if has_inserts is True and i in by_position:
+            depth = GetCoverage(index, i + 1)
+            if depth > mincov:
+                for inserted in by_position[i].values():
+                    yield f"{contig}\t{i}\t.\t{ref_base}\t{called[i]}{inserted}\t.\tPASS\tDP={depth};INDEL\n"
+
+
 def WriteOutputs(mincov, iDict, uGffDict, inputbam, IncludeAmbig, output_vcf, name, ref, output_gff, gffheader,
                  output_consensus):
-    """Outputs.py:74-183."""
-    today = date.today().strftime("%Y%m%d")
+    """Outputs.py:74-183: corrected GFF, variant list, consensus FASTA — in that order, each file written as soon as its
+    content exists, so a failure part-way leaves what the reference leaves."""
     bam = Readbam(inputbam)
-    consensus, newgff = BuildConsensus(mincov, iDict, uGffDict, IncludeAmbig, bam, True)
-    consensus_noinsert = BuildConsensus(mincov, iDict, uGffDict, IncludeAmbig, bam, False)[0]
+    with_inserts, corrected_gff = BuildConsensus(mincov, iDict, uGffDict, IncludeAmbig, bam, True)
+    without_inserts = BuildConsensus(mincov, iDict, uGffDict, IncludeAmbig, bam, False)[0]    # same call table, second walk
 
     if output_gff is not None:
-        WriteGFF(gffheader, newgff, output_gff, name)
+        WriteGFF(gffheader, corrected_gff, output_gff, name)
 
     if output_vcf is not None:
         inserts = ListInserts(iDict, mincov, bam)
-        refID, reflist = _first_fasta_record(ref)
-        seqlist = list(consensus_noinsert.upper())
+        contig, reference = _first_fasta_record(ref)
         with open(output_vcf, "w") as out:
-            out.write("##fileformat=VCFv4.3\n"
-                      f"##fileDate={today}\n"
-                      f"##source='TrueConsense {' '.join(sys.argv[1:])}'\n"
-                      f"##reference='{ref}'\n"
-                      f"##contig=<ID={refID}>\n"
-                      '##INFO=<ID=DP,Number=1,Type=Integer,Description="Read Depth">\n'
-                      '##INFO=<ID=INDEL,Number=0,Type=Flag,Description="Indicates that the variant is an INDEL.">\n'
-                      "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
-            # records are streamed, so a failure part-way leaves the same partial file the reference leaves
-            hasinserts, insertpositions = inserts
-            in_deletion = set()
-            for i in range(len(reflist)):
-                if i in in_deletion:
-                    continue
-                if reflist[i] != seqlist[i]:
-                    if seqlist[i] == "-":
-                        b = i
-                        gap = []
-                        while seqlist[b] == "-":
-                            gap.append(reflist[b])
-                            in_deletion.add(b)
-                            b += 1
-                        refallele = str(reflist[i - 1] + "".join(gap))
-                        depth = GetCoverage(iDict, i + 1)
-                        out.write(f"{refID}\t{i}\t.\t{refallele}\t{seqlist[i - 1]}\t.\tPASS\tDP={depth};INDEL\n")
-                    else:
-                        p = 1 if i < 2 else i
-                        depth = GetCoverage(iDict, p + 1)
-                        out.write(f"{refID}\t{i + 1}\t.\t{reflist[i]}\t{seqlist[i]}\t.\tPASS\tDP={depth}\n")
-                if hasinserts is True:
-                    for lposition in insertpositions:
-                        if i != lposition:
-                            continue
-                        depth = GetCoverage(iDict, i + 1)
-                        if depth > mincov:
-                            for size in insertpositions.get(lposition):
-                                alt = seqlist[i] + str(insertpositions.get(lposition).get(size))
-                                out.write(f"{refID}\t{i}\t.\t{reflist[i]}\t{alt}\t.\tPASS\tDP={depth};INDEL\n")
+            out.write(VCF_HEADER.format(today=date.today().strftime("%Y%m%d"), argv=" ".join(sys.argv[1:]), ref=ref, contig=contig))
+            for line in _vcf_records(contig, reference, list(without_inserts.upper()), iDict, mincov, inserts):
+                out.write(line)         # streamed: records up to a failure stay in the file
 
     with open(output_consensus, "w") as out:
-        out.write(f">{name} mincov={mincov}\n{consensus}\n")
+        out.write(f">{name} mincov={mincov}\n{with_inserts}\n")
+    return None, None

@@ -130,16 +130,30 @@ def BuildConsensus(mincov, iDict, GFFdict, IncludeAmbig, bam, includeINS):
     return consensus_from_inserts(mincov, _counts_from_index(p_index), GFFdict, IncludeAmbig, inserts, includeINS)
 
 
+_last_call: tuple | None = None      # (key, columns): WriteOutputs walks the same table twice (Outputs.py:95-98), with and without insertions
+
+
+def _call_table(counts: np.ndarray, L: int, mincov: int, include_ambig: bool):
+    """The call kernel's columns for this count table as Python lists; the table of the previous call is kept, so the second
+    BuildConsensus of a run (same index, same thresholds) costs no second tc_call and no second conversion."""
+    global _last_call
+    import hashlib
+
+    key = (L, int(mincov), include_ambig, hashlib.blake2b(counts.tobytes(), digest_size=16).digest())
+    if _last_call is not None and _last_call[0] == key:
+        return _last_call[1]
+    table = gpu.default_context().call(counts, L, mincov, include_ambig)
+    cols = (counts[0].tolist(), table.flags.tolist(), table.xrun.tolist(), table.call_char.tobytes().decode("ascii"))
+    _last_call = (key, cols)
+    return cols
+
+
 def consensus_from_inserts(mincov, counts, GFFdict, IncludeAmbig, inserts, includeINS):
     """The walk of Sequences.py:175-322 over a count table [8][L] given ListInserts' result."""
     hasinserts, insertpositions = inserts
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     L = counts.shape[1]
-    table = gpu.default_context().call(counts, L, mincov, bool(IncludeAmbig is True))
-    cov_l = counts[0].tolist()
-    flags = table.flags.tolist()
-    xrun = table.xrun.tolist()
-    chars = table.call_char.tobytes().decode("ascii")
+    cov_l, flags, xrun, chars = _call_table(counts, L, mincov, bool(IncludeAmbig is True))
 
     LOWCOV, PRIMX, MDEL, OFFEND, ZEROCOV = gpu.CF_LOWCOV, gpu.CF_PRIMARY_X, gpu.CF_MINORITY_DEL, gpu.CF_XRUN_OFF_END, gpu.CF_ZERO_COV
 

@@ -87,41 +87,36 @@ def GetArgs(givenargs):
     return parser.parse_args(givenargs)
 
 
+def _index_and_features(opts, bam):
+    """The count table and the GFF, read side by side like TrueConsense.py:225-230 (BuildIndex runs on a pool thread: the
+    C-ABI sets its device per call), then the optional override of single positions (:232-235)."""
+    with cf.ThreadPoolExecutor(max_workers=opts.threads) as pool:
+        jobs = (pool.submit(BuildIndex, bam, opts.reference), pool.submit(Gffindex, opts.features))
+        frame, gff = (j.result() for j in jobs)
+    if opts.index_override:
+        frame = Override_index_positions(frame, read_override_index(opts.index_override))
+    return frame, gff
+
+
 def main(args: list[str] | None = None):
-    """TrueConsense.py:212-264."""
-    if not args:
-        args = sys.argv[1:]
-    if len(args) < 1:
+    """The reference's command line (TrueConsense.py:212-264): same flags, same files."""
+    argv = args or sys.argv[1:]
+    if not argv:
         print("TrueConsense was called but no arguments were given, please try again.\n"
               "Use 'TrueConsense -h' to see the help document")
         sys.exit(1)
-    parsed = GetArgs(args)
-
-    bam = Readbam(parsed.input)      # one decoded copy of the BAM serves the index and the insertion columns
-
-    with cf.ThreadPoolExecutor(max_workers=parsed.threads) as pool:
-        index_job = pool.submit(BuildIndex, bam, parsed.reference)
-        gff_job = pool.submit(Gffindex, parsed.features)
-        IndexDF = index_job.result()
-        IndexGff = gff_job.result()
-
-    if parsed.index_override:
-        IndexDF = Override_index_positions(IndexDF, read_override_index(parsed.index_override))
-
-    indexDict = IndexDF.to_dict("index")
-    GffHeader = IndexGff.header
-    GffDF = IndexGff.df
-    GffDF["seqid"] = parsed.samplename
-    GffDict = GffDF.to_dict("index")
-
-    with cf.ThreadPoolExecutor(max_workers=parsed.threads) as pool:
-        if parsed.depth_of_coverage is not None:
-            pool.submit(BuildCoverage, indexDict, parsed.depth_of_coverage)   # result never checked (:243-245)
-
-    IncludeAmbig = parsed.noambiguity is False
-
-    WriteOutputs(parsed.coverage_level, indexDict, GffDict, bam, IncludeAmbig, parsed.variants, parsed.samplename,
-                 parsed.reference, parsed.output_gff, GffHeader, parsed.output)
+    opts = GetArgs(argv)
+    bam = Readbam(opts.input)        # one decoded copy of the BAM serves the index and the insertion columns
+    frame, gff = _index_and_features(opts, bam)
+    index = frame.to_dict("index")
+    features = gff.df
+    features["seqid"] = opts.samplename
+    if opts.depth_of_coverage is not None:
+        # fire and forget on a pool thread, its outcome never looked at (:243-245)
+        with cf.ThreadPoolExecutor(max_workers=opts.threads) as pool:
+            pool.submit(BuildCoverage, index, opts.depth_of_coverage)
+    WriteOutputs(opts.coverage_level, index, features.to_dict("index"), bam, opts.noambiguity is False, opts.variants,
+                 opts.samplename, opts.reference, opts.output_gff, gff.header, opts.output)
 
 
 if __name__ == "__main__":
