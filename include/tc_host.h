@@ -54,6 +54,23 @@ typedef struct tc_hostreads {
 int  tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err, int errlen);
 void tc_hostreads_free(tc_hostreads_t* r);
 
+/* The file's uncompressed payload and where its placed records start: the host half of the decode when the records are
+ * parsed on the GPU (trueconsense_b200.h: tc_bam_records_to_reads). */
+typedef struct tc_bampayload {
+    uint8_t* payload;       /* the BGZF blocks' concatenated payload (malloc-owned) */
+    int64_t  n_bytes;
+    int64_t* rec_off;       /* [n_reads] offset of every placed record's refID field (its block_size sits 4 bytes in front) */
+    int64_t  n_reads;       /* placed records (refID >= 0), file order */
+    int64_t  n_records, n_dropped_unplaced;
+    int32_t  n_ref;
+    int32_t* ref_len;
+    char*    ref_names;
+    int64_t  ref_names_len;
+    double   t_inflate_s, t_index_s;
+} tc_bampayload_t;
+int  tc_bam_payload(const char* path, int n_threads, tc_bampayload_t* out, char* err, int errlen);
+void tc_bampayload_free(tc_bampayload_t* p);
+
 /* Write flat arrays as a coordinate-sorted single-contig BAM (names are "q<hash hex>"). */
 int  tc_bam_write(const char* path, const tc_hostreads_t* reads, const char* ref_name,
                   int32_t ref_len, int level, char* err, int errlen);

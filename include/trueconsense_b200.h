@@ -176,6 +176,28 @@ float tc_last_pileup_kernel_ms(tc_ctx_t* ctx);
  * Arrays that are NULL in *host stay NULL.  Already-device pointers are passed through. */
 int  tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* dev, void* stream);
 
+/* Copy `bytes` from device memory (e.g. an array of a device-resident tc_reads_t) to the host; synchronises the stream. */
+int  tc_download(tc_ctx_t* ctx, void* dst_host, const void* src_dev, int64_t bytes, void* stream);
+
+/* ---- BAM records -> read arrays on the device: the reader half of pysam.AlignmentFile at indexing.py:96 ----
+ * payload: the BAM's uncompressed stream (the concatenated payload of its BGZF blocks), host or device memory;
+ * rec_off[n_reads]: for every record to keep, in file order, the offset of its refID field (block_size sits 4 bytes in
+ * front) — what the host's one sequential hop over the records yields (libtchost.so: tc_bam_payload inflates on all cores and
+ * hops).  The device parses the fixed fields, hashes the names, walks the CIGARs and packs SEQ / QUAL / CIGAR into
+ * context-owned buffers; *dev receives device pointers (valid until the next tc_reads_upload / tc_bam_records_to_reads on this
+ * context), exactly the arrays a host-side decode + tc_reads_upload would give.  The caller has validated the records'
+ * sizes (tc_bam_payload does).  Synchronises the stream once. */
+typedef struct tc_bam_stats {
+    unsigned long long aligned_bases;   /* sum over the kept reads of M,=,X,D,N lengths */
+    int32_t max_ref_span;
+    int32_t unsorted;                   /* some record sorts before its predecessor by (refID, pos) */
+    int32_t multi_contig;               /* records of more than one reference */
+    int32_t sorted;                     /* !unsorted */
+    int64_t n_seq_words, n_cigar_ops;
+} tc_bam_stats_t;
+int  tc_bam_records_to_reads(tc_ctx_t* ctx, const uint8_t* payload, int64_t n_bytes, const int64_t* rec_off, int64_t n_reads,
+                             tc_reads_t* dev, tc_bam_stats_t* stats, void* stream);
+
 /* ---- (1) pileup: replaces pysam pileup + parse_query_sequences, indexing.py:100-143 ----
  * counts: int32[TC_NROWS][ref_len] (host or device), fully overwritten, zero rows for uncovered
  * positions (indexing.py:147-151).  Reads starting at or beyond ref_len are an error (TC_ERR_RANGE). */

@@ -1057,3 +1057,29 @@ def test_full_size_configs_vs_oracle(ctx, orc, idx, scale):
     assert [g["pos"] for g in ins] == cands and len(cands) >= 3
     for g in ins:
         assert (g["string"], g["n_entries"], g["mode_count"]) == _expected_call(pileup, call, b, g["pos"]), g["pos"]
+
+
+# ---------------------------------------------------------------------------- BAM records parsed on the device
+@pytest.mark.parametrize("name", MINIS)
+def test_bam_records_parsed_on_device_equal_host_decode(ctx, name):
+    """tc_bam_records_to_reads (inflate + record hop on the host, everything else on the GPU) fills exactly the arrays
+    csrc/host/bamio.c's reader fills: every array byte for byte, the statistics, and the count table / insertion calls on top."""
+    from trueconsense_b200 import bamio
+
+    path = f"{GOLD}/{name}.bam"
+    host = bamio.read_bam(path)
+    payload = bamio.read_bam_payload(path)
+    assert payload.n_reads == host.n_reads and payload.ref_lens == host.ref_lens and payload.ref_names == host.ref_names
+    dev = ctx.bam_to_device(payload)
+    st = dev.stats
+    assert (st.n_seq_words, st.n_cigar_ops) == (host.seq4.shape[0], host.cigar.shape[0])
+    assert st.max_ref_span == host.max_ref_span and bool(st.sorted) == host.sorted and not st.multi_contig
+    assert st.aligned_bases == host.count_aligned_bases(0)
+    s = dev.struct
+    for field, arr in (("pos", host.pos), ("flag", host.flag), ("mapq", host.mapq), ("l_seq", host.l_seq), ("seq_off", host.seq_off),
+                       ("cigar_off", host.cigar_off), ("seq4", host.seq4), ("qual", host.qual), ("cigar", host.cigar),
+                       ("qname_hash", host.qname_hash), ("mpos", host._mpos_for_abi()), ("isize", host.isize)):
+        got = ctx.download(getattr(s, field), arr.size, arr.dtype)
+        assert np.array_equal(got, arr.reshape(-1)), field
+    L = host.ref_lens[0]
+    assert np.array_equal(ctx.pileup_counts(dev, L), ctx.pileup_counts(host, L))

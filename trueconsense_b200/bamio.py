@@ -33,6 +33,54 @@ class TcHostReads(C.Structure):
     ]
 
 
+class TcBamPayload(C.Structure):
+    """ctypes mirror of ``tc_bampayload_t`` (include/tc_host.h)."""
+
+    _fields_ = [
+        ("payload", C.POINTER(C.c_uint8)), ("n_bytes", C.c_int64), ("rec_off", C.POINTER(C.c_int64)), ("n_reads", C.c_int64),
+        ("n_records", C.c_int64), ("n_dropped_unplaced", C.c_int64), ("n_ref", C.c_int32), ("ref_len", C.POINTER(C.c_int32)),
+        ("ref_names", C.POINTER(C.c_char)), ("ref_names_len", C.c_int64), ("t_inflate_s", C.c_double), ("t_index_s", C.c_double),
+    ]
+
+
+class BamPayload:
+    """A BAM's uncompressed payload and the offsets of its placed records (host memory, freed with the object): the host half
+    of the decode when the records are parsed on the GPU (``gpu.Context.bam_to_device``)."""
+
+    def __init__(self, st: TcBamPayload, lib: C.CDLL):
+        self._st, self._lib = st, lib
+        self.n_reads = int(st.n_reads)
+        self.n_bytes = int(st.n_bytes)
+        names = []
+        if st.n_ref > 0 and st.ref_names_len > 0:
+            names = [x.decode() for x in C.string_at(st.ref_names, st.ref_names_len).split(b"\0")[: st.n_ref]]
+        self.ref_names = names
+        self.ref_lens = [int(st.ref_len[i]) for i in range(st.n_ref)] if st.n_ref > 0 else []
+        self.info = {"n_records": int(st.n_records), "n_dropped_unplaced": int(st.n_dropped_unplaced),
+                     "t_inflate_s": float(st.t_inflate_s), "t_index_s": float(st.t_index_s)}
+
+    @property
+    def payload_ptr(self) -> int:
+        return C.cast(self._st.payload, C.c_void_p).value or 0
+
+    @property
+    def rec_off_ptr(self) -> int:
+        return C.cast(self._st.rec_off, C.c_void_p).value or 0
+
+    def release(self) -> None:
+        """Free the payload and the offsets (the header fields read in __init__ stay)."""
+        if self._st is not None:
+            self._lib.tc_bampayload_free(C.byref(self._st))
+            self._st = None
+            self.n_bytes = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 _lib = None
 
 
@@ -51,6 +99,10 @@ def host_lib() -> C.CDLL:
         lib.tc_bam_write.argtypes = [C.c_char_p, C.POINTER(TcHostReads), C.c_char_p, C.c_int32, C.c_int,
                                      C.c_char_p, C.c_int]
         lib.tc_bam_write.restype = C.c_int
+        lib.tc_bam_payload.argtypes = [C.c_char_p, C.c_int, C.POINTER(TcBamPayload), C.c_char_p, C.c_int]
+        lib.tc_bam_payload.restype = C.c_int
+        lib.tc_bampayload_free.argtypes = [C.POINTER(TcBamPayload)]
+        lib.tc_bampayload_free.restype = None
         _lib = lib
     return _lib
 
@@ -121,6 +173,18 @@ def read_bam(path: str, threads: int = 0) -> ReadBatch:
     if rc != 0:
         raise OSError(f"tc_bam_read({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
     return batch_from_hostreads(hr, lib)
+
+
+def read_bam_payload(path: str, threads: int = 0) -> BamPayload:
+    """Inflate a BAM on the host's cores and index its placed records; the records themselves are parsed on the device
+    (``gpu.Context.bam_to_device``)."""
+    lib = host_lib()
+    st = TcBamPayload()
+    err = C.create_string_buffer(512)
+    rc = lib.tc_bam_payload(os.fsencode(path), threads, C.byref(st), err, len(err))
+    if rc != 0:
+        raise OSError(f"tc_bam_payload({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
+    return BamPayload(st, lib)
 
 
 def hostreads_struct(batch: ReadBatch) -> TcHostReads:

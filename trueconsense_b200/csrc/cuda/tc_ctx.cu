@@ -203,3 +203,13 @@ TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* de
     dev->qname_hash = d.qname_hash; dev->mpos = d.mpos; dev->isize = d.isize;
     return TC_OK;
 }
+
+TC_API int tc_download(tc_ctx_t* ctx, void* dst_host, const void* src_dev, int64_t bytes, void* stream) {
+    if (!ctx) return TC_ERR_ARG;
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return tc_fail(ctx, TC_ERR_ARG, "bad argument");
+    if (bytes == 0) return TC_OK;
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_D2H(dst_host, src_dev, (size_t)bytes, (cudaStream_t)stream);
+    TC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return TC_OK;
+}

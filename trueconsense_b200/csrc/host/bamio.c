@@ -101,7 +101,124 @@ int tc_hostreads_alloc_(tc_hostreads_t* o, int64_t n, int64_t n_words, int64_t n
 
 typedef struct { int64_t coff; int32_t csize; int64_t uoff; int32_t usize; } blk_t;
 
-int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err, int errlen) {
+/* header + record hop over the payload while it is still being inflated */
+typedef struct {
+    const uint8_t* u; int64_t utotal; const blk_t* blk; int64_t nblk; const uint8_t* done; const int* bad;
+    int64_t next_b, ready;          /* blocks [0, next_b) are known complete: payload bytes [0, ready) may be read */
+    const char* path; char* err; int errlen; tc_hostreads_t* out;
+    int64_t* recoff; int64_t nkept; int rc;
+} scan_t;
+
+/* payload bytes [0, upto) complete?  Spins behind the inflating threads; 0 when an inflate failed. */
+static int scan_wait(scan_t* s, int64_t upto) {
+    if (upto > s->utotal) upto = s->utotal;
+    while (s->ready < upto) {
+        if (s->next_b >= s->nblk) { s->ready = s->utotal; break; }
+        if (__atomic_load_n(&s->done[s->next_b], __ATOMIC_ACQUIRE)) {
+            s->ready = s->blk[s->next_b].uoff + s->blk[s->next_b].usize;
+            s->next_b++;
+        } else if (__atomic_load_n(s->bad, __ATOMIC_ACQUIRE)) return 0;
+        else {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    return 1;
+}
+#define SCAN_NEED(upto) do { if ((upto) > s->ready && !scan_wait(s, (upto))) return -2; } while (0)
+
+static int scan_payload(scan_t* s) {
+    const uint8_t* u = s->u; const int64_t utotal = s->utotal; tc_hostreads_t* out = s->out;
+    char* err = s->err; const int errlen = s->errlen; const char* path = s->path;
+    SCAN_NEED(12);
+    if (utotal < 12 || memcmp(u, "BAM\1", 4) != 0) return fail(err, errlen, -2, "%s: missing BAM magic", path);
+    int64_t p = 4;
+    int32_t l_text = (int32_t)rd32(u + p);
+    if (l_text < 0 || p + 4 + (int64_t)l_text + 4 > utotal) return fail(err, errlen, -2, "truncated BAM header");
+    p += 4 + l_text;
+    SCAN_NEED(p + 4);
+    int32_t n_ref = (int32_t)rd32(u + p); p += 4;
+    if (n_ref < 0 || (int64_t)n_ref * 8 > utotal - p) return fail(err, errlen, -2, "bad BAM reference count %d", n_ref);
+    out->n_ref = n_ref;
+    out->ref_len = malloc(sizeof(int32_t) * (n_ref > 0 ? n_ref : 1));
+    int64_t names_cap = 64, names_len = 0;
+    out->ref_names = malloc(names_cap);
+    if (!out->ref_len || !out->ref_names) return fail(err, errlen, -5, "out of memory");
+    for (int i = 0; i < n_ref; ++i) {
+        if (p + 4 > utotal) return fail(err, errlen, -2, "truncated BAM reference list");
+        SCAN_NEED(p + 4);
+        int32_t l_name = (int32_t)rd32(u + p); p += 4;
+        if (l_name < 0 || p + (int64_t)l_name + 4 > utotal) return fail(err, errlen, -2, "truncated BAM reference list");
+        SCAN_NEED(p + l_name + 4);
+        while (names_len + l_name + 1 > names_cap) {
+            names_cap *= 2;
+            char* nn = realloc(out->ref_names, names_cap);
+            if (!nn) return fail(err, errlen, -5, "out of memory");
+            out->ref_names = nn;
+        }
+        memcpy(out->ref_names + names_len, u + p, l_name);
+        names_len += l_name;
+        if (l_name == 0 || out->ref_names[names_len - 1] != 0) out->ref_names[names_len++] = 0;
+        p += l_name;
+        out->ref_len[i] = (int32_t)rd32(u + p); p += 4;
+    }
+    out->ref_names_len = names_len;
+
+    int64_t rcap = 1 << 16, nrec = 0, nkept = 0;
+    s->recoff = malloc(rcap * sizeof(int64_t));
+    if (!s->recoff) return fail(err, errlen, -5, "out of memory");
+    int64_t q = p;
+    while (q + 4 <= utotal) {
+        SCAN_NEED(q + 4);
+        int32_t bs = (int32_t)rd32(u + q);
+        if (bs < 32 || q + 4 + bs > utotal) return fail(err, errlen, -2, "corrupt BAM record at payload offset %lld", (long long)q);
+        ++nrec;
+        SCAN_NEED(q + 4 + 36);
+        int32_t refid = (int32_t)rd32(u + q + 4);
+        {
+            /* the record's own sizes against its block_size, before anything is sized from them */
+            const uint8_t* r = u + q + 4;
+            int32_t l_name = r[8];
+            uint32_t n_cig = rd16(r + 12);
+            uint32_t l_seq = rd32(r + 16);
+            int64_t need = 32 + (int64_t)l_name + 4LL * n_cig + ((int64_t)l_seq + 1) / 2 + (int64_t)l_seq;
+            if (l_seq > 0x7fffffffu || need > bs || l_name < 1)
+                return fail(err, errlen, -2, "%s: BAM record %lld shorter than its fields", path, (long long)(nrec - 1));
+            SCAN_NEED(q + 4 + 32 + l_name + 8);
+            if (r[32 + l_name - 1] != 0)
+                return fail(err, errlen, -2, "%s: BAM record %lld shorter than its fields (or an unterminated read name)", path, (long long)(nrec - 1));
+            /* more than 65535 CIGAR ops: the real CIGAR sits in the CG:B,I tag behind a <l_seq>S<span>N placeholder, which
+             * htslib expands transparently.  Not expanded here: refuse, rather than pile the read up as a reference skip */
+            if (refid >= 0 && n_cig == 2) {
+                const uint8_t* cg = r + 32 + l_name;
+                uint32_t c0 = rd32(cg), c1 = rd32(cg + 4);
+                if ((c0 & 15) == 4 && (c0 >> 4) == l_seq && (c1 & 15) == 3 && l_seq > 0)
+                    return fail(err, errlen, -2, "%s: record %lld keeps its CIGAR in a CG tag (more than 65535 operations): not supported", path, (long long)(nrec - 1));
+            }
+        }
+        if (refid >= 0) {
+            if (nkept == rcap) {
+                rcap *= 2;
+                int64_t* nr2 = realloc(s->recoff, rcap * sizeof(int64_t));
+                if (!nr2) return fail(err, errlen, -5, "out of memory");
+                s->recoff = nr2;
+            }
+            s->recoff[nkept++] = q + 4;
+        }
+        q += 4 + bs;
+    }
+    out->n_records = nrec;
+    out->n_dropped_unplaced = nrec - nkept;
+    s->nkept = nkept;
+    return 0;
+}
+
+
+/* Stages (1)-(3): the file's uncompressed payload, its header in *out, and the offsets of the placed records (of their
+ * refID field, i.e. behind block_size).  The caller owns *u_out and *recoff_out (free). */
+static int bam_payload_stage(const char* path, int n_threads, tc_hostreads_t* out, uint8_t** u_out, int64_t* utotal_out,
+                             int64_t** recoff_out, int64_t* nkept_out, char* err, int errlen) {
     memset(out, 0, sizeof(*out));
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_num_procs();
@@ -163,108 +280,74 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     uint8_t* u = malloc((size_t)(utotal > 0 ? utotal : 1));
     if (!u) { free(blk); munmap((void*)f, fsize); return fail(err, errlen, -5, "out of memory (%lld bytes)", (long long)utotal); }
 
-    /* (2) inflate in parallel */
+    /* (2) inflate in parallel and, behind the inflating threads, (3) header + one hop over the records.  The hop is sequential
+     * by nature (every record says how long it is) and latency-bound (one cache miss per record): run by one thread as the
+     * blocks in front of it complete, it costs no wall time of its own. */
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads) reduction(|:bad)
-    for (int64_t b = 0; b < nblk; ++b) {
-        if (blk[b].usize == 0) continue;
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { bad |= 1; continue; }
-        zs.next_in = (Bytef*)(f + blk[b].coff); zs.avail_in = (uInt)blk[b].csize;
-        zs.next_out = u + blk[b].uoff; zs.avail_out = (uInt)blk[b].usize;       /* inflate never writes more than ISIZE bytes */
-        int r = inflate(&zs, Z_FINISH);
-        int ok = (r == Z_STREAM_END && zs.avail_out == 0);
-        inflateEnd(&zs);
-        if (ok) {
-            uint32_t crc = crc32(crc32(0L, Z_NULL, 0), u + blk[b].uoff, blk[b].usize);
-            if (crc != rd32(f + blk[b].coff + blk[b].csize)) ok = 0;
-        }
-        if (!ok) bad |= 1;
-    }
-    free(blk);
-    munmap((void*)f, fsize);
-    if (bad) { free(u); return fail(err, errlen, -2, "%s: BGZF inflate / CRC failure", path); }
-    out->t_inflate_s = now_s() - t0;
-    t0 = now_s();
-
-    /* header */
-    if (utotal < 12 || memcmp(u, "BAM\1", 4) != 0) { free(u); return fail(err, errlen, -2, "%s: missing BAM magic", path); }
-    int64_t p = 4;
-    int32_t l_text = (int32_t)rd32(u + p);
-    if (l_text < 0 || p + 4 + (int64_t)l_text + 4 > utotal) { free(u); return fail(err, errlen, -2, "truncated BAM header"); }
-    p += 4 + l_text;
-    int32_t n_ref = (int32_t)rd32(u + p); p += 4;
-    if (n_ref < 0 || (int64_t)n_ref * 8 > utotal - p) { free(u); return fail(err, errlen, -2, "bad BAM reference count %d", n_ref); }
-    out->n_ref = n_ref;
-    out->ref_len = malloc(sizeof(int32_t) * (n_ref > 0 ? n_ref : 1));
-    int64_t names_cap = 64, names_len = 0;
-    out->ref_names = malloc(names_cap);
-    if (!out->ref_len || !out->ref_names) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
-    for (int i = 0; i < n_ref; ++i) {
-        if (p + 4 > utotal) { free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "truncated BAM reference list"); }
-        int32_t l_name = (int32_t)rd32(u + p); p += 4;
-        if (l_name < 0 || p + (int64_t)l_name + 4 > utotal) { free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "truncated BAM reference list"); }
-        while (names_len + l_name + 1 > names_cap) {
-            names_cap *= 2;
-            char* nn = realloc(out->ref_names, names_cap);
-            if (!nn) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
-            out->ref_names = nn;
-        }
-        memcpy(out->ref_names + names_len, u + p, l_name);
-        names_len += l_name;
-        if (l_name == 0 || out->ref_names[names_len - 1] != 0) out->ref_names[names_len++] = 0;
-        p += l_name;
-        out->ref_len[i] = (int32_t)rd32(u + p); p += 4;
-    }
-    out->ref_names_len = names_len;
-
-    /* (3) hop over records */
-    int64_t rcap = 1 << 16, nrec = 0, nkept = 0;
-    int64_t* recoff = malloc(rcap * sizeof(int64_t));
-    if (!recoff) { free(u); tc_hostreads_free(out); return fail(err, errlen, -5, "out of memory"); }
-    int64_t q = p;
-    while (q + 4 <= utotal) {
-        int32_t bs = (int32_t)rd32(u + q);
-        if (bs < 32 || q + 4 + bs > utotal) { rc = fail(err, errlen, -2, "corrupt BAM record at payload offset %lld", (long long)q); break; }
-        ++nrec;
-        int32_t refid = (int32_t)rd32(u + q + 4);
-        {
-            /* the record's own sizes against its block_size, before anything is sized from them */
-            const uint8_t* r = u + q + 4;
-            int32_t l_name = r[8];
-            uint32_t n_cig = rd16(r + 12);
-            uint32_t l_seq = rd32(r + 16);
-            int64_t need = 32 + (int64_t)l_name + 4LL * n_cig + ((int64_t)l_seq + 1) / 2 + (int64_t)l_seq;
-            if (l_seq > 0x7fffffffu || need > bs || l_name < 1 || r[32 + l_name - 1] != 0) {
-                rc = fail(err, errlen, -2, "%s: BAM record %lld shorter than its fields (or an unterminated read name)", path, (long long)(nrec - 1));
-                break;
-            }
-            /* more than 65535 CIGAR ops: the real CIGAR sits in the CG:B,I tag behind a <l_seq>S<span>N placeholder, which
-             * htslib expands transparently.  Not expanded here: refuse, rather than pile the read up as a reference skip */
-            if (refid >= 0 && n_cig == 2) {
-                const uint8_t* cg = r + 32 + l_name;
-                uint32_t c0 = rd32(cg), c1 = rd32(cg + 4);
-                if ((c0 & 15) == 4 && (c0 >> 4) == l_seq && (c1 & 15) == 3 && l_seq > 0) {
-                    rc = fail(err, errlen, -2, "%s: record %lld keeps its CIGAR in a CG tag (more than 65535 operations): not supported", path, (long long)(nrec - 1));
-                    break;
+    int64_t next_block = 0;
+    uint8_t* done = calloc((size_t)(nblk > 0 ? nblk : 1), 1);
+    scan_t sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.u = u; sc.utotal = utotal; sc.blk = blk; sc.nblk = nblk; sc.done = done; sc.bad = &bad; sc.path = path; sc.err = err; sc.errlen = errlen; sc.out = out;
+    if (!done) { free(blk); free(u); munmap((void*)f, fsize); return fail(err, errlen, -5, "out of memory"); }
+    double t_inflate_end = t0;
+#pragma omp parallel num_threads(n_threads)
+    {
+        int tid = 0, nth = 1;
+#ifdef _OPENMP
+        tid = omp_get_thread_num(); nth = omp_get_num_threads();
+#endif
+        if (tid == 0 && nth > 1) sc.rc = scan_payload(&sc);            /* waits for the blocks it needs */
+        for (;;) {
+            int64_t b = __atomic_fetch_add(&next_block, 1, __ATOMIC_RELAXED);
+            if (b >= nblk) break;
+            int ok = 1;
+            if (blk[b].usize != 0) {
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) != Z_OK) ok = 0;
+                else {
+                    zs.next_in = (Bytef*)(f + blk[b].coff); zs.avail_in = (uInt)blk[b].csize;
+                    zs.next_out = u + blk[b].uoff; zs.avail_out = (uInt)blk[b].usize;       /* inflate never writes more than ISIZE bytes */
+                    int r = inflate(&zs, Z_FINISH);
+                    ok = (r == Z_STREAM_END && zs.avail_out == 0);
+                    inflateEnd(&zs);
+                    if (ok) {
+                        uint32_t crc = crc32(crc32(0L, Z_NULL, 0), u + blk[b].uoff, blk[b].usize);
+                        if (crc != rd32(f + blk[b].coff + blk[b].csize)) ok = 0;
+                    }
                 }
             }
+            if (!ok) __atomic_store_n(&bad, 1, __ATOMIC_RELEASE);
+            __atomic_store_n(&done[b], 1, __ATOMIC_RELEASE);
         }
-        if (refid >= 0) {
-            if (nkept == rcap) {
-                rcap *= 2;
-                int64_t* nr2 = realloc(recoff, rcap * sizeof(int64_t));
-                if (!nr2) { rc = fail(err, errlen, -5, "out of memory"); break; }
-                recoff = nr2;
-            }
-            recoff[nkept++] = q + 4;
+#pragma omp barrier
+#pragma omp master
+        {
+            t_inflate_end = now_s();
+            if (nth == 1 && !bad) sc.rc = scan_payload(&sc);           /* a single thread: one after the other */
         }
-        q += 4 + bs;
     }
-    if (rc) { free(recoff); free(u); tc_hostreads_free(out); return rc; }
-    out->n_records = nrec;
-    out->n_dropped_unplaced = nrec - nkept;
+    free(blk); free(done);
+    munmap((void*)f, fsize);
+    if (bad) { free(sc.recoff); free(u); tc_hostreads_free(out); return fail(err, errlen, -2, "%s: BGZF inflate / CRC failure", path); }
+    if (sc.rc) { free(sc.recoff); free(u); tc_hostreads_free(out); return sc.rc; }
+    out->t_inflate_s = t_inflate_end - t0;
+    int64_t* recoff = sc.recoff; int64_t nkept = sc.nkept;
+    *u_out = u; *utotal_out = utotal; *recoff_out = recoff; *nkept_out = nkept;
+    return 0;
+}
+
+int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err, int errlen) {
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_num_procs();
+#else
+    n_threads = 1;
+#endif
+    uint8_t* u; int64_t utotal; int64_t* recoff; int64_t nkept;
+    int rc = bam_payload_stage(path, n_threads, out, &u, &utotal, &recoff, &nkept, err, errlen);
+    if (rc) return rc;
+    double t0 = now_s();
 
     /* sizes -> offsets (sequential prefix sum, cheap) */
     uint32_t* soff = malloc((nkept + 1) * 4);
@@ -345,6 +428,35 @@ int tc_bam_read(const char* path, int n_threads, tc_hostreads_t* out, char* err,
     out->sorted = sorted;
     out->t_parse_s = now_s() - t0;
     return 0;
+}
+
+/* The decode split for GPU-side record parsing (trueconsense_b200.h tc_bam_records_to_reads): inflate on the host's cores,
+ * hop over the records once (sequential by nature: every record says how long it is), and hand the raw payload plus the
+ * record offsets to the device — which parses the fixed fields, hashes the names, walks the CIGARs and repacks SEQ / QUAL /
+ * CIGAR into the flat arrays. */
+int tc_bam_payload(const char* path, int n_threads, tc_bampayload_t* out, char* err, int errlen) {
+    memset(out, 0, sizeof(*out));
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_num_procs();
+#else
+    n_threads = 1;
+#endif
+    tc_hostreads_t hdr;
+    uint8_t* u; int64_t utotal; int64_t* recoff; int64_t nkept;
+    double t0 = now_s();
+    int rc = bam_payload_stage(path, n_threads, &hdr, &u, &utotal, &recoff, &nkept, err, errlen);
+    if (rc) return rc;
+    out->payload = u; out->n_bytes = utotal; out->rec_off = recoff; out->n_reads = nkept;
+    out->n_records = hdr.n_records; out->n_dropped_unplaced = hdr.n_dropped_unplaced;
+    out->n_ref = hdr.n_ref; out->ref_len = hdr.ref_len; out->ref_names = hdr.ref_names; out->ref_names_len = hdr.ref_names_len;
+    out->t_inflate_s = hdr.t_inflate_s; out->t_index_s = now_s() - t0 - hdr.t_inflate_s;
+    return 0;
+}
+
+void tc_bampayload_free(tc_bampayload_t* p) {
+    if (!p) return;
+    free(p->payload); free(p->rec_off); free(p->ref_len); free(p->ref_names);
+    memset(p, 0, sizeof(*p));
 }
 
 /* ------------------------------------------------------------------ writer */

@@ -37,6 +37,11 @@ class PileupParams(C.Structure):
                 ("ignore_orphans", C.c_int32), ("max_depth", C.c_int64), ("kernel", C.c_int32), ("reserved", C.c_int32)]
 
 
+class BamStats(C.Structure):
+    _fields_ = [("aligned_bases", C.c_uint64), ("max_ref_span", C.c_int32), ("unsorted", C.c_int32), ("multi_contig", C.c_int32),
+                ("sorted", C.c_int32), ("n_seq_words", C.c_int64), ("n_cigar_ops", C.c_int64)]
+
+
 class CallParams(C.Structure):
     _fields_ = [("mincov", C.c_int32), ("include_ambig", C.c_int32), ("ambig_maxdist", C.c_double),
                 ("minority_del_pct", C.c_double), ("insert_pct", C.c_double)]
@@ -107,6 +112,10 @@ def lib() -> C.CDLL:
             l.tc_pileup_call_inserts.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
                                                  C.POINTER(PileupParams), vp, C.POINTER(CallTable), C.POINTER(InsertCall), i32,
                                                  C.POINTER(i32), vp, i64, vp]
+            l.tc_bam_records_to_reads.argtypes = [vp, vp, i64, vp, i64, C.POINTER(TcReads), C.POINTER(BamStats), vp]
+            l.tc_bam_records_to_reads.restype = C.c_int
+            l.tc_download.argtypes = [vp, vp, vp, i64, vp]
+            l.tc_download.restype = C.c_int
             l.tc_sample_enqueue.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
                                             C.POINTER(PileupParams), vp, C.POINTER(CallTable), vp, C.POINTER(i32)]
             l.tc_sample_finish.argtypes = [vp, i32, C.POINTER(InsertCall), i32, C.POINTER(i32), vp, i64]
@@ -148,16 +157,19 @@ class CallResult:
 class DeviceReads:
     """A read batch resident in context-owned device memory (see tc_reads_upload)."""
 
-    def __init__(self, struct: TcReads, batch: ReadBatch, ctx=None, generation: int = 0):
+    def __init__(self, struct: TcReads, batch: ReadBatch | None, ctx=None, generation: int = 0):
         self.struct = struct
-        self.n_reads = batch.n_reads
-        self.host = batch
+        self.n_reads = int(struct.n_reads) if batch is None else batch.n_reads
+        self.host = batch           # None: parsed on the device (bam_to_device), every array lives there
         self.ctx = ctx
         self.generation = generation
+        self.stats = None
 
     def with_host_qual(self) -> "DeviceReads":
         """The same device arrays plus the batch's HOST quality and mate arrays (QNAME hash, PNEXT, TLEN):
         tc_extract_inserts then copies them only for the reads over its candidate columns."""
+        if self.host is None:
+            return self
         st = TcReads()
         C.memmove(C.byref(st), C.byref(self.struct), C.sizeof(TcReads))
         if not st.qual and self.host.qual is not None:
@@ -237,6 +249,25 @@ class Context:
         self._generation += 1
         self._check(self._lib.tc_reads_upload(self._h, C.byref(host), C.byref(dev), stream))
         return DeviceReads(dev, batch, self, self._generation)
+
+    def download(self, dev_ptr: int, count: int, dtype, stream: int = 0) -> np.ndarray:
+        """``count`` elements of ``dtype`` from device memory (e.g. a field of ``DeviceReads.struct``) as a numpy array."""
+        out = np.empty(int(count), dtype=dtype)
+        self._check(self._lib.tc_download(self._h, _ptr(out), dev_ptr, out.nbytes, stream))
+        return out
+
+    def bam_to_device(self, payload, stream: int = 0) -> DeviceReads:
+        """GPU-side record parsing (tc_bam_records_to_reads): a ``bamio.BamPayload`` (the BAM inflated on the host, its records
+        indexed) becomes the flat read arrays in the context's device buffers — the CPU never touches a record's body.
+        ``.stats`` of the result: aligned bases, longest span, sortedness, whether more than one reference occurs."""
+        dev = TcReads()
+        st = BamStats()
+        self._generation += 1
+        self._check(self._lib.tc_bam_records_to_reads(self._h, payload.payload_ptr, payload.n_bytes, payload.rec_off_ptr,
+                                                      payload.n_reads, C.byref(dev), C.byref(st), stream))
+        d = DeviceReads(dev, None, self, self._generation)
+        d.stats = st
+        return d
 
     # ------------------------------------------------------------------ (1) pileup
     def pileup_counts(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):

@@ -3,8 +3,8 @@
 ``BuildIndex(bamfile, ref)`` returns the same DataFrame (seven int64 columns
 ``coverage,A,T,C,G,X,I``, int64 index 1..len(ref[0]), ``index.name is None``) the reference
 builds from a pysam pileup plus a per-string Python classifier (indexing.py:75-154).  Here the
-BAM is decoded into flat arrays on the host (csrc/host/bamio.c) and the whole pileup is one pass
-of the CUDA kernels behind ``tc_pileup_counts``.
+BAM is inflated on the host (csrc/host/bamio.c), its records are parsed on the GPU into flat arrays
+(``tc_bam_records_to_reads``) and the whole pileup is one pass of the CUDA kernels behind ``tc_pileup_counts``.
 """
 from __future__ import annotations
 
@@ -20,12 +20,15 @@ COLUMNS = ["coverage", "A", "T", "C", "G", "X", "I"]
 
 
 class BamHandle:
-    """What ``Readbam`` returns: the decoded reads of a BAM plus the attributes of
-    ``pysam.AlignmentFile`` the reference touches (``references``; Events.py:63)."""
+    """What ``Readbam`` returns: a BAM on its way to the device plus the attributes of ``pysam.AlignmentFile`` the reference
+    touches (``references``; Events.py:63).  The file is inflated on the host's cores, its records are parsed on the GPU
+    (``tc_bam_records_to_reads``) straight into the context's read buffers; ``reads`` (a host-side decode into numpy arrays) is
+    only made when somebody asks for it."""
 
     def __init__(self, filename: str, reads: ReadBatch | None = None):
         self.filename = filename
         self._reads = reads
+        self._payload = None
         self._dev = None
         self._lock = threading.Lock()
         self._insert_cache: dict = {}
@@ -37,20 +40,29 @@ class BamHandle:
                 self._reads = bamio.read_bam(self.filename)
             return self._reads
 
+    def _header(self):
+        """(reference names, reference lengths) from whichever decode exists."""
+        with self._lock:
+            if self._reads is not None:
+                return self._reads.ref_names, self._reads.ref_lens
+            if self._payload is None:
+                self._payload = bamio.read_bam_payload(self.filename)
+            return self._payload.ref_names, self._payload.ref_lens
+
     @property
     def references(self):
-        return tuple(self.reads.ref_names)
+        return tuple(self._header()[0])
 
     @property
     def lengths(self):
-        return tuple(self.reads.ref_lens)
+        return tuple(self._header()[1])
 
     @property
     def ref_len(self) -> int:
-        return int(self.reads.ref_lens[0])
+        return int(self._header()[1][0])
 
     def contig0(self) -> ReadBatch:
-        """Reads placed on the first reference (the only one the reference implementation is
+        """Host-side reads placed on the first reference (the only one the reference implementation is
         meaningful for: indexing.py:98,139 and Events.py:63 use lengths[0] / references[0])."""
         b = self.reads
         if b.tid is not None and b.n_reads and np.any(b.tid != 0):
@@ -59,23 +71,33 @@ class BamHandle:
         return b
 
     def device_reads(self, with_host_qual: bool = False):
-        """The reads of the first reference in device memory: uploaded (without QUAL) once per handle and
-        reused by later passes while the context has not staged anything else; ExtractInserts adds the
-        host QUAL array, of which only the stretches over candidate columns are ever copied."""
+        """The reads in device memory, made once per handle and reused by later passes while the context has not staged
+        anything else.  From a file: inflated on the host, parsed on the GPU (QUAL and the mate fields included).  From a
+        host batch handed to the constructor: uploaded without QUAL / mate fields, which ExtractInserts then stages for the
+        reads over its candidate columns only."""
         ctx = gpu.default_context()
         with self._lock:
             d = self._dev
             if d is None or d.ctx is not ctx or d.generation != ctx._generation:
-                d = self._dev = ctx.upload(self.contig0_nolock(), with_qual=False)
+                if self._reads is not None:
+                    b = self._reads
+                    if b.tid is not None and b.n_reads and np.any(b.tid != 0):
+                        raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference")
+                    if not b.sorted:
+                        raise ValueError("Unsorted input. Pileup aborts")
+                    d = ctx.upload(b, with_qual=False)
+                else:
+                    if self._payload is None or self._payload.n_bytes == 0:        # (released after an earlier parse)
+                        self._payload = bamio.read_bam_payload(self.filename)
+                    d = ctx.bam_to_device(self._payload)
+                    self._payload.release()         # the device holds the arrays now; the header stays
+                    if d.stats.multi_contig:
+                        raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference "
+                                         "(its DataFrame index would hold duplicate positions)")
+                    if d.stats.unsorted:
+                        raise ValueError("Unsorted input. Pileup aborts")
+                self._dev = d
             return d.with_host_qual() if with_host_qual else d
-
-    def contig0_nolock(self) -> ReadBatch:
-        if self._reads is None:
-            self._reads = bamio.read_bam(self.filename)
-        b = self._reads
-        if b.tid is not None and b.n_reads and np.any(b.tid != 0):
-            raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference")
-        return b
 
     def pileup(self, *args, **kwargs):
         raise NotImplementedError("column iteration is not part of this implementation; "
@@ -157,8 +179,5 @@ def BuildIndex(bamfile, ref):
     if not lens:
         raise ValueError(f"no sequences in {ref}")
     ref_length = int(lens[0])
-    reads = handle.contig0()
-    if not reads.sorted:
-        raise ValueError("Unsorted input. Pileup aborts")
     counts = gpu.default_context().pileup_counts(handle.device_reads(), ref_length)
     return frame_from_counts(counts)
