@@ -10,11 +10,12 @@ One *step* is one pass of the hot path over one synthetic sample of BASELINE.jso
     one enqueue and one synchronisation per sample, step i + 1 enqueued before step i is finished.
 `value`  : aligned bases/s with the reads already resident in HBM, CUDA-event timed.
 `e2e`    : the same pass through the C-ABI with HOST (pinned) buffers: the H2D copy of every read
-           array and the D2H copy of the count and call tables are inside the timed region.
+           array and the D2H copy of the count and call tables are inside the timed region.  Two samples travel at a
+           time (two host threads, a context and a stream each): one's upload overlaps the other's kernels.
 N > 1    : one process per GPU (torchrun), each rank piles up its own sample (the 96-sample plate
            of configs[2] sharded by sample): no data-path collective, weak scaling.
 `read_range` (every N): configs[3], ONE ultra-deep sample sharded by read range, the per-rank tables summed
-           with tc_allreduce_counts (NCCL) inside the timed region — strong scaling, checked bit for bit
+           with the pileup in one enqueue (tc_pileup_counts_allreduce, NCCL) inside the timed region — strong scaling, checked bit for bit
            against the single-GPU table.  `configs` (N = 1): tc_pileup_counts on the other configs.
            `parity_checked`: the GPU table over the cpu_baseline prefix equals the oracle's.
 `--impl reference` times the CPU oracle port of the reference path (oracle/, all host threads) on a
@@ -283,9 +284,10 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     stream = torch.cuda.current_stream().cuda_stream
 
     def one_pass():
-        ctx.pileup_counts(dev, L, p, out=out, stream=stream)
         if comm is not None:
-            ctx.allreduce_counts(out, comm, stream=stream)
+            ctx.pileup_counts_allreduce(dev, L, p, out, comm, stream=stream)       # one enqueue, one synchronisation, a graph
+        else:
+            ctx.pileup_counts(dev, L, p, out=out, stream=stream)
 
     def sync():
         if world > 1:
@@ -349,7 +351,7 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     if comm is not None:
         comm.close()
     block = {
-        "workload": w.name, "sharding": "by read range, tc_allreduce_counts (ncclAllReduce int32 sum) inside the timed region",
+        "workload": w.name, "sharding": "by read range, tc_pileup_counts_allreduce per pass (shard pileup + ncclAllReduce int32 sum in one enqueue, replayed as a CUDA graph)",
         "scaling": "strong", "n_gpus": world, "reads": n_reads, "reads_per_rank": int(hi - lo), "aligned_bases": bases,
         "ms_per_pass": ms, "aligned_bases_per_s": bases / (ms * 1e-3), "allreduce_ms": ar_ms, "allreduce_bytes": int(out.numel() * 4),
         "single_gpu_ms_per_pass": single_ms, "strong_scaling_efficiency": single_ms / (world * ms),
@@ -503,36 +505,64 @@ def run_ours(args):
     launches = ctx.launches - launches0
     ms_total = ev0.elapsed_time(ev1)
     # ---------------- end to end through the C-ABI with host buffers: `e2e`
-    h_counts = np.empty((gpu.TC_NROWS, L), dtype=np.int32)
+    # Two samples travel at a time: two host threads, each with a context, a stream and output buffers of its own, so one
+    # sample's upload overlaps the other's kernels and read-backs (every call below blocks its own thread only; the C-ABI
+    # releases the interpreter lock).  The copies share the one PCIe link: the step time is the upload time.
+    import threading
 
-    def e2e_step():
-        d = ctx.upload(pinned, stream, with_qual=False)      # H2D of every read array the pileup needs (pinned memory)
-        ctx.pileup_counts(d, L, params, out=counts_dev, stream=stream)
-        res = ctx.call(counts_dev, L, w.mincov, True, stream=stream)     # D2H of the call table
-        cands = ctx.list_insert_candidates(res.flags, L)
-        ins = ctx.extract_inserts(d.with_host_qual(), L, cands)          # H2D of QUAL over the candidate columns only
-        torch.cuda.current_stream().synchronize()
-        h = counts_dev.cpu().numpy()                         # D2H of the count table
+    n_lanes = max(1, min(2, args.e2e_lanes))
+    lanes = [(ctx, torch.cuda.Stream(), counts_dev)]
+    if n_lanes == 2:
+        lanes.append((gpu.Context(local), torch.cuda.Stream(), counts_dev2))
+
+    def e2e_step(lane):
+        c, ts, cdev = lanes[lane]
+        st = ts.cuda_stream
+        d = c.upload(pinned, st, with_qual=False)            # H2D of every read array the pileup needs (pinned memory)
+        c.pileup_counts(d, L, params, out=cdev, stream=st)
+        res = c.call(cdev, L, w.mincov, True, stream=st)     # D2H of the call table
+        cands = c.list_insert_candidates(res.flags, L, stream=st)
+        ins = c.extract_inserts(d.with_host_qual(), L, cands, stream=st)     # H2D of QUAL over the candidate columns only
+        h = c.download(cdev.data_ptr(), cdev.numel(), np.int32, stream=st)   # D2H of the count table
         return h, res, ins
 
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
+    def e2e_run(n_steps):
+        last, errs = [None] * n_lanes, []
+
+        def lane_loop(lane, n):
+            try:
+                torch.cuda.set_device(local)
+                for _ in range(n):
+                    last[lane] = e2e_step(lane)
+            except BaseException as e:      # noqa: BLE001 — re-raised on the main thread
+                errs.append(e)
+
+        ths = [threading.Thread(target=lane_loop, args=(k, (n_steps + n_lanes - 1 - k) // n_lanes)) for k in range(n_lanes)]
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        if errs:
+            raise errs[0]
+        return last[0]
+
+    e2e_run(n_lanes * min(args.warmup, 2))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    xfer0 = ctx.transfer_bytes()
+    xfer0 = [c.transfer_bytes() for c, _, _ in lanes]
     sampler.open_window()
     e0.record()
-    for _ in range(args.steps):
-        h, res, ins = e2e_step()
+    h, res, ins = e2e_run(args.steps)
+    torch.cuda.synchronize()        # both lanes' streams: e1 is stamped behind everything
     e1.record()
     barrier()
     sampler.close_window()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()          # sampled over both timed regions (device-resident steps, then end-to-end steps)
-    h2d, d2h_lib = (b - a_ for a_, b in zip(xfer0, ctx.transfer_bytes()))
-    h2d //= args.steps
-    d2h = d2h_lib // args.steps + int(h.nbytes)
-
+    h2d = sum(c.transfer_bytes()[0] - x[0] for (c, _, _), x in zip(lanes, xfer0)) // args.steps
+    d2h = sum(c.transfer_bytes()[1] - x[1] for (c, _, _), x in zip(lanes, xfer0)) // args.steps
+    for c, _, _ in lanes[1:]:
+        c.close()
     # ---------------- max over ranks
     t = torch.tensor([ms_total, e2e_ms, float(bases), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -620,6 +650,7 @@ def main():
     ap.add_argument("--deep-scale", type=float, default=1.0, help="fraction of configs[3]'s 50 M reads in the read-range block (1.0: the whole sample, 4.8 GB of read arrays on one GPU)")
     ap.add_argument("--no-read-range", action="store_true", help="skip the read-range sharded block (configs[3])")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (N = 1 only)")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="samples travelling at a time in the end-to-end loop (1 or 2)")
     ap.add_argument("--h2d-ceiling", action="store_true", help="also measure the concurrent pinned H2D ceiling at N = 1")
     ap.add_argument("--cpu-reads", type=float, default=1_000_000, help="reads in the cpu_baseline sample (1 M reads = 400 M aligned bases, 10-15 s on one core)")
     ap.add_argument("--ref-reads", type=float, default=400_000, help="reads per step of the --impl reference arm")

@@ -266,6 +266,17 @@ int  tc_sample_finish(tc_ctx_t* ctx, int32_t ticket, tc_insert_call_t* calls, in
  * (the Python host layer creates it from a unique id exchanged over torch.distributed). */
 int  tc_allreduce_counts(tc_ctx_t* ctx, int32_t* counts_dev, int64_t n_elems, void* comm, void* stream);
 
+/* One rank's part of a read-range sharded sample in ONE enqueue: tc_pileup_counts of this rank's shard into `counts_dev`
+ * (device, int32[8][ref_len]) followed by the sum over all ranks, with a single synchronisation at the end instead of one
+ * between the pileup and the collective; from the second call with the same buffers on the chain is replayed as a CUDA
+ * graph (the NCCL kernel included).  Collective-safe: the shards' status blocks travel with the sum, so when any rank's
+ * shard needs another kernel variant or fails, EVERY rank repeats the pass through the separate calls and makes the same
+ * collective calls; the failing rank then returns its error.  `params->max_depth` applies to the shard: pass 0 and prove the
+ * cap on the summed coverage (host layer: sharding.check_depth_cap).  Results equal tc_pileup_counts + tc_allreduce_counts.
+ * Replaces, per shard, the reference's indexing.py:96-143 (BuildIndex over the whole BAM). */
+int  tc_pileup_counts_allreduce(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* params,
+                                int32_t* counts_dev, void* comm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

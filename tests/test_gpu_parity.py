@@ -711,6 +711,42 @@ def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
         assert np.array_equal(out.cpu().numpy(), exp)
     finally:
         comm.close()
+    # the shard's pileup and the sum in one enqueue (tc_pileup_counts_allreduce): eager, captured, replayed; a shard the
+    # bit-parallel kernel declines sends every rank through the separate calls; a failing shard still makes its collective call
+    import copy
+
+    from trueconsense_b200 import gpu
+    from trueconsense_b200.reads import ReadBatch
+
+    comm = sharding.NcclComm(0, 1, 0)
+    try:
+        p = gpu.buildindex_params()
+        p.max_depth = 0
+        dev = ctx.upload(b, with_qual=False)
+        out = torch.empty((8, L), dtype=torch.int32, device="cuda")
+        for i in range(4):
+            out.fill_(-1)
+            ctx.pileup_counts_allreduce(dev, L, p, out, comm)
+            assert np.array_equal(out.cpu().numpy(), exp), i
+        ctx.pileup_counts_allreduce(b, L, p, out, comm)                 # host arrays: staged, never captured
+        assert np.array_equal(out.cpu().numpy(), exp)
+        ref2, _, long_b = _synth("long_reads")
+        unbounded = copy.copy(long_b)
+        unbounded.max_ref_span = -1
+        exp2 = pileup.pileup_counts(long_b, len(ref2), threads=4)
+        out2 = torch.empty((8, len(ref2)), dtype=torch.int32, device="cuda")
+        dev2 = ctx.upload(unbounded, with_qual=False)
+        for i in range(3):
+            ctx.pileup_counts_allreduce(dev2, len(ref2), p, out2, comm)
+            assert np.array_equal(out2.cpu().numpy(), exp2), i
+        unsorted = ReadBatch.from_records([dict(pos=50, cigar="10M", seq="A" * 10), dict(pos=10, cigar="10M", seq="A" * 10)])
+        with pytest.raises(gpu.TcError) as ei:
+            ctx.pileup_counts_allreduce(unsorted, L, p, out, comm)
+        assert ei.value.code == -3
+        ctx.pileup_counts_allreduce(ctx.upload(b, with_qual=False), L, p, out, comm)
+        assert np.array_equal(out.cpu().numpy(), exp)
+    finally:
+        comm.close()
     total = torch.zeros((8, L), dtype=torch.int32, device="cuda")
     for rank in range(3):
         lo, hi = sharding.read_range(b.n_reads, rank, 3)

@@ -14,7 +14,7 @@
 
 constexpr int TC_SAMPLE_MAX_CAND = 256;
 
-static bool all_device(const tc_reads_t* r) {
+bool tc_reads_all_device(const tc_reads_t* r) {
     if (r->n_reads == 0) return true;
     return tc_is_device_ptr(r->pos) && tc_is_device_ptr(r->flag) && tc_is_device_ptr(r->l_seq) && tc_is_device_ptr(r->seq_off) &&
            tc_is_device_ptr(r->cigar_off) && (!r->n_seq_words || (tc_is_device_ptr(r->seq4) && tc_is_device_ptr(r->qual))) &&
@@ -111,7 +111,7 @@ TC_API int tc_sample_enqueue(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref
     const bool table_dev = (!t.call_char || tc_is_device_ptr(t.call_char)) && (!t.xrun || tc_is_device_ptr(t.xrun)) &&
                            (!t.rank_letter || tc_is_device_ptr(t.rank_letter)) && (!t.rank_count || tc_is_device_ptr(t.rank_count)) &&
                            (!t.ambig_char || tc_is_device_ptr(t.ambig_char));
-    if (!all_device(reads) || !table_dev || pp->min_base_quality > 0) {
+    if (!tc_reads_all_device(reads) || !table_dev || pp->min_base_quality > 0) {
         sl.state = 2;           // inputs the chained form does not take: the separate calls, at finish time
     } else {
         unsigned char key[512];

@@ -23,6 +23,11 @@ enum tc_slot {
 struct tc_buf { void* p; size_t cap; };
 
 constexpr size_t TC_HOST_SCRATCH = 64 * 1024;
+struct tc_status;
+struct tc_pileup_pending {      // what tc_pileup_finish needs once the status block is on the host
+    tc_status* d_status; int32_t* d_counts; int variant; int per_entry; int out_dev; int64_t n_reads; int32_t span_hint;
+};
+
 struct tc_ctx {
     int device;
     int sm_count;
@@ -49,6 +54,12 @@ struct tc_ctx {
     cudaStream_t cap_stream;    // the stream sample graphs are captured on (a user's legacy default stream cannot be captured)
     int in_capture;         // timing events inside a capture are recorded as external event nodes
     float finished_ms;      // timing on: pileup-kernel duration of the sample tc_sample_finish returned last (< 0: none)
+    // tc_pileup_counts_allreduce: the shard's chain (pileup -> status flag -> ncclAllReduce -> status read-back) as one graph
+    cudaGraphExec_t rr_exec;
+    unsigned char rr_key[256];
+    int rr_key_len, rr_seen;
+    int64_t rr_launches, rr_d2h;
+    tc_pileup_pending rr_pend;
 };
 
 // device-side status block written by kernels, read back once per call
@@ -108,13 +119,11 @@ struct dreads {
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s);
 
 // ---- pieces of the entry points that only ENQUEUE (tc_pileup_call_inserts chains them without a host round trip)
-struct tc_pileup_pending {      // what tc_pileup_finish needs once the status block is on the host
-    tc_status* d_status; int32_t* d_counts; int variant; int per_entry; int out_dev; int64_t n_reads; int32_t span_hint;
-};
 int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* p, int32_t* counts, cudaStream_t s,
                       tc_pileup_pending* pend);
 int tc_pileup_finish(tc_ctx* ctx, const tc_status& st, const tc_pileup_pending* pend, const tc_reads_t* reads, int32_t ref_len,
                      const tc_pileup_params_t* p, int32_t* counts, void* stream);
+bool tc_reads_all_device(const tc_reads_t* r);     // every array of the batch already in device memory
 int tc_candidates_enqueue(tc_ctx* ctx, const uint8_t* d_flags, int32_t ref_len, int32_t cap, int32_t** d_count, int32_t** d_sorted, cudaStream_t s);
 struct tc_ins_pending { size_t rb_extra, rb_layout, rb_over, rb_calls, rb_fixed; int cap; int64_t n_reads; };
 int tc_inserts_enqueue_dev(tc_ctx* ctx, const tc_reads_t* reads, const int32_t* d_cand, const int32_t* d_ncand, int cap,

@@ -150,6 +150,7 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < SLOT_COUNT; ++i)
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
+    if (ctx->rr_exec) cudaGraphExecDestroy(ctx->rr_exec);
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }

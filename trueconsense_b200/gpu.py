@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
                                              C.POINTER(InsertCall), vp, i64, vp]
             l.tc_list_insert_candidates.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32), vp]
             l.tc_allreduce_counts.argtypes = [vp, vp, i64, vp, vp]
+            l.tc_pileup_counts_allreduce.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), vp, vp, vp]
+            l.tc_pileup_counts_allreduce.restype = C.c_int
             l.tc_pileup_call_inserts.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
                                                  C.POINTER(PileupParams), vp, C.POINTER(CallTable), C.POINTER(InsertCall), i32,
                                                  C.POINTER(i32), vp, i64, vp]
@@ -283,6 +285,13 @@ class Context:
     def allreduce_counts(self, counts_dev, comm, stream: int = 0) -> None:
         """Sum a device count table over the ranks of ``comm`` (sharding.NcclComm) in place."""
         self._check(self._lib.tc_allreduce_counts(self._h, _ptr(counts_dev), int(counts_dev.numel()), comm.handle, stream))
+
+    def pileup_counts_allreduce(self, reads, ref_len: int, params: PileupParams, out, comm, stream: int = 0):
+        """This rank's shard piled up into the torch CUDA int32 tensor ``out`` and summed over the ranks of ``comm`` in one
+        enqueue (tc_pileup_counts_allreduce): no synchronisation between the two, a CUDA graph from the second call on."""
+        rs = self._reads_struct(reads)
+        self._check(self._lib.tc_pileup_counts_allreduce(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), comm.handle, stream))
+        return out
 
     # ------------------------------------------------------------------ (3) depth
     def depth(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):

@@ -116,11 +116,12 @@ def pileup_counts_read_range(ctx: "gpu.Context", batch: ReadBatch, ref_len: int,
         out = torch.empty((gpu.TC_NROWS, ref_len), dtype=torch.int32, device="cuda")
     shard_params = gpu.PileupParams.from_buffer_copy(params)
     shard_params.max_depth = 0                  # the cap is checked on the summed coverage below, not per shard
-    ctx.pileup_counts(batch.slice(lo, hi), ref_len, shard_params, out=out, stream=stream)
     if world > 1:
         if comm is None:
             raise ValueError("a communicator is needed to sum the per-rank tables")
-        ctx.allreduce_counts(out, comm, stream=stream)
+        ctx.pileup_counts_allreduce(batch.slice(lo, hi), ref_len, shard_params, out, comm, stream=stream)
+    else:
+        ctx.pileup_counts(batch.slice(lo, hi), ref_len, shard_params, out=out, stream=stream)
     cov = out[0]
     zero_span = int(np.count_nonzero(batch.ref_spans() == 0)) if params.max_depth and params.max_depth < 4 * batch.n_reads else 0
     check_depth_cap(int(cov.max().item()) if ref_len else 0, zero_span, int(params.max_depth))
