@@ -441,7 +441,7 @@ def run_ours(args):
     L = len(w.ref)
     bases = batch.count_aligned_bases(0x4)
     alg_bytes = batch.algorithmic_bytes(L)
-    pinned = batch.pin()
+    pinned = batch.with_cigar16().pin()       # (16-bit CIGAR transport when every operation is shorter than 4096)
     stream = torch.cuda.current_stream().cuda_stream
 
     counts_dev = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")

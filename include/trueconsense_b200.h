@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TC_ABI_VERSION 1
+#define TC_ABI_VERSION 2
 
 /* ---- error codes (0 = success, negative = failure) ---- */
 #define TC_OK              0
@@ -90,6 +90,11 @@ typedef struct tc_reads {
      * tc_pileup_counts verifies the bound while it walks the CIGARs and fails with TC_ERR_ARG if it is too small. */
     int32_t max_ref_span;
     int32_t reserved;
+    /* optional compact transport of the CIGARs: the same n_cigar_ops operations as 16-bit (len << 4 | op) entries, offered
+     * only when every operation is shorter than 4096 (the producer checks; the entries then equal the 32-bit ones).  When
+     * both arrays sit in host memory the library copies this one — half the bytes over PCIe — and widens it on the device.
+     * `cigar` may be NULL when this is given. */
+    const uint16_t* cigar16;
 } tc_reads_t;
 
 /* ---- pileup filters: the arguments of pysam's AlignmentFile.pileup() that the

@@ -691,6 +691,35 @@ def test_extract_inserts_long_insertions_both_forms(ctx, orc):
     assert got[5]["string"] == "C+12" + ins_a
 
 
+def test_compact_cigar_transport(ctx, orc):
+    """tc_reads_t.cigar16: the CIGARs travel as 16-bit entries and are widened on the device — same tables, same insertion
+    calls, half the CIGAR bytes over the link; a batch with an operation of 4096 or more keeps the 32-bit array."""
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    for case in ("amplicon_deep", "shotgun_indels", "tiny", "one_read"):
+        ref, _, b = _synth(case)
+        L = len(ref)
+        c = b.with_cigar16()
+        assert c.cigar16 is not None and c.cigar16.dtype == np.uint16 and np.array_equal(c.cigar16, b.cigar)
+        exp = pileup.pileup_counts(b, L, threads=4)
+        x0 = ctx.transfer_bytes()[0]
+        assert np.array_equal(ctx.pileup_counts(c, L), exp)
+        x1 = ctx.transfer_bytes()[0]
+        assert np.array_equal(ctx.pileup_counts(b, L), exp)
+        x2 = ctx.transfer_bytes()[0]
+        assert (x2 - x1) - (x1 - x0) == 2 * b.cigar.size
+        dev = ctx.upload(c)
+        assert np.array_equal(ctx.download(dev.struct.cigar, b.cigar.size, np.uint32), b.cigar)
+        assert np.array_equal(ctx.pileup_counts(dev, L), exp)
+        cands = ctx.list_insert_candidates(ctx.call(exp, L, 10, True).flags, L)
+        if len(cands):
+            assert ctx.extract_inserts(c, L, cands) == ctx.extract_inserts(b, L, cands)
+            assert ctx.extract_inserts(ctx.upload(c), L, cands) == ctx.extract_inserts(b, L, cands)
+    long_op = ReadBatch.from_records([dict(pos=0, cigar="5000M", seq="A" * 5000)])
+    assert long_op.with_cigar16() is long_op
+
+
 # ---------------------------------------------------------------------------- multi-GPU pieces on one device
 def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
     """tc_allreduce_counts through a real NCCL communicator (one rank: identity), and the per-rank slices of

@@ -29,7 +29,7 @@ def test_cuda_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/trueconsense_b200.h but not exported"
     lib.tc_abi_version.restype = ctypes.c_int
-    assert lib.tc_abi_version() == 1
+    assert lib.tc_abi_version() == 2
 
 
 def test_cuda_library_is_sm100a_only():

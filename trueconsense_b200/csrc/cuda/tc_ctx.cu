@@ -61,6 +61,18 @@ const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cuda
     return d;
 }
 
+// 16-bit (len << 4 | op) entries to the 32-bit ones the kernels read: 8 per thread and step (the buffers are 16-byte aligned
+// and padded by tc_dev_buf)
+__global__ void widen_cigar_kernel(const uint16_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+    const int64_t n8 = n / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+        reinterpret_cast<uint4*>(out)[2 * i] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+        reinterpret_cast<uint4*>(out)[2 * i + 1] = make_uint4(v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - 8 * n8)) out[8 * n8 + threadIdx.x] = in[8 * n8 + threadIdx.x];
+}
+
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s) {
     if (!in) return tc_fail(ctx, TC_ERR_ARG, "reads is NULL");
     if (in->n_reads < 0 || in->n_seq_words < 0 || in->n_cigar_ops < 0) return tc_fail(ctx, TC_ERR_ARG, "negative sizes in tc_reads_t");
@@ -69,7 +81,7 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
     memset(out, 0, sizeof(*out));
     out->n = n;
     if (n == 0) return TC_OK;
-    if (!in->pos || !in->flag || !in->l_seq || !in->seq_off || !in->cigar_off || (!in->cigar && in->n_cigar_ops) ||
+    if (!in->pos || !in->flag || !in->l_seq || !in->seq_off || !in->cigar_off || (!in->cigar && !in->cigar16 && in->n_cigar_ops) ||
         (!in->seq4 && in->n_seq_words))
         return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: a required array is NULL");
     int rc;
@@ -87,7 +99,22 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
         if (!out->field) return TC_ERR_NOMEM;                                                           \
     } else { STAGE(field, slot, type, count) }
     STAGE_OR_DEFER(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words, DEFER_SEQ)
-    STAGE_OR_DEFER(cigar, SLOT_CIGAR, uint32_t, in->n_cigar_ops, DEFER_CIGAR)
+    if (in->cigar16 && in->n_cigar_ops && !tc_is_device_ptr(in->cigar16) && (!in->cigar || !tc_is_device_ptr(in->cigar)) &&
+        !((need & DEFER_CIGAR) && in->cigar)) {
+        // compact transport: 2 bytes per operation over the link, widened behind it
+        const uint16_t* c16 = (const uint16_t*)tc_stage_in(ctx, SLOT_CIGAR16, in->cigar16, sizeof(uint16_t) * (size_t)in->n_cigar_ops, s, &rc);
+        if (rc) return rc;
+        uint32_t* c32 = (uint32_t*)tc_dev_buf(ctx, SLOT_CIGAR, sizeof(uint32_t) * (size_t)in->n_cigar_ops);
+        if (!c32) return TC_ERR_NOMEM;
+        const int64_t n8 = (in->n_cigar_ops + 7) / 8;
+        const int grid = (int)((n8 + 255) / 256 < (int64_t)ctx->sm_count * 8 ? (n8 + 255) / 256 : (int64_t)ctx->sm_count * 8);
+        widen_cigar_kernel<<<grid, 256, 0, s>>>(c16, c32, in->n_cigar_ops);
+        TC_LAUNCH_CHECK();
+        out->cigar = c32;
+    } else {
+        if (!in->cigar && in->n_cigar_ops) return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: cigar is NULL and cigar16 is not a host array");
+        STAGE_OR_DEFER(cigar, SLOT_CIGAR, uint32_t, in->n_cigar_ops, DEFER_CIGAR)
+    }
     if (in->mapq) { STAGE(mapq, SLOT_MAPQ, uint8_t, n) }
     if (need & NEED_QUAL) {
         if (!in->qual && in->n_seq_words) return tc_fail(ctx, TC_ERR_ARG, "this pass applies a base-quality filter but reads->qual is NULL");
@@ -202,6 +229,7 @@ TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* de
     dev->pos = d.pos; dev->flag = d.flag; dev->mapq = d.mapq; dev->l_seq = d.l_seq; dev->seq_off = d.seq_off;
     dev->cigar_off = d.cigar_off; dev->seq4 = d.seq4; dev->qual = d.qual; dev->cigar = d.cigar;
     dev->qname_hash = d.qname_hash; dev->mpos = d.mpos; dev->isize = d.isize;
+    dev->cigar16 = nullptr;
     return TC_OK;
 }
 

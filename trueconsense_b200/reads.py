@@ -40,6 +40,7 @@ class TcReads(C.Structure):
         ("isize", C.c_void_p),
         ("max_ref_span", C.c_int32),
         ("reserved", C.c_int32),
+        ("cigar16", C.c_void_p),
     ]
 
 
@@ -75,6 +76,7 @@ class ReadBatch:
     sorted: bool = True
     info: dict = field(default_factory=dict)
     _owner: Any = None       # keeps backing memory alive
+    cigar16: np.ndarray | None = None    # the same operations in 16 bits (tc_reads_t.cigar16), see with_cigar16()
 
     # ------------------------------------------------------------------ basics
     @property
@@ -113,7 +115,19 @@ class ReadBatch:
                 a = self._mpos_for_abi()
             setattr(s, name, None if a is None else a.ctypes.data)
         s.max_ref_span = max(int(self.max_ref_span), 0)      # 0 = unknown
+        s.cigar16 = None if self.cigar16 is None else self.cigar16.ctypes.data
         return s
+
+    def with_cigar16(self) -> "ReadBatch":
+        """This batch with the compact CIGAR transport array attached (``tc_reads_t.cigar16``: half the bytes over PCIe) when
+        every operation is shorter than 4096; otherwise the batch itself."""
+        import copy
+
+        if self.cigar16 is not None or self.cigar.size == 0 or int(self.cigar.max()) >= (4096 << 4):
+            return self
+        out = copy.copy(self)
+        out.cigar16 = self.cigar.astype(np.uint16)
+        return out
 
     def _mpos_for_abi(self) -> np.ndarray:
         """tc_reads_t.mpos: PNEXT, -1 if unavailable, -2 when the mate maps to another reference (htslib's overlap
@@ -201,6 +215,7 @@ class ReadBatch:
             aligned_bases=self.aligned_bases, max_ref_span=self.max_ref_span, sorted=self.sorted,
             info=dict(self.info),
         )
+        out.cigar16 = pinned(self.cigar16)
         out._owner = keep
         return out
 
