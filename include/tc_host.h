@@ -71,6 +71,25 @@ typedef struct tc_bampayload {
 int  tc_bam_payload(const char* path, int n_threads, tc_bampayload_t* out, char* err, int errlen);
 void tc_bampayload_free(tc_bampayload_t* p);
 
+/* One BGZF member: its raw DEFLATE stream is file[coff .. coff + csize) — the member's CRC-32 and ISIZE follow it — and
+ * inflates to payload[uoff .. uoff + usize).  (Same layout as trueconsense_b200.h's tc_bgzf_block_t.) */
+#ifndef TC_BGZF_BLOCK_T
+#define TC_BGZF_BLOCK_T
+typedef struct tc_bgzf_block { int64_t coff; int32_t csize; int32_t usize; int64_t uoff; } tc_bgzf_block_t;
+#endif
+/* The BAM file mapped read-only and the index of its members (one header read per member: the only sequential step left on
+ * the host when the GPU inflates — tc_bgzf_inflate).  Replaces htslib's bgzf reader under the reference's
+ * indexing.py:6-19 (`Readbam`). */
+typedef struct tc_bgzf_map {
+    const uint8_t*   file;
+    int64_t          file_bytes;
+    tc_bgzf_block_t* blocks;
+    int64_t          n_blocks;
+    int64_t          payload_bytes;     /* sum of the members' ISIZE */
+} tc_bgzf_map_t;
+int  tc_bgzf_map(const char* path, tc_bgzf_map_t* out, char* err, int errlen);
+void tc_bgzf_unmap(tc_bgzf_map_t* m);
+
 /* Write flat arrays as a coordinate-sorted single-contig BAM (names are "q<hash hex>"). */
 int  tc_bam_write(const char* path, const tc_hostreads_t* reads, const char* ref_name,
                   int32_t ref_len, int level, char* err, int errlen);

@@ -203,6 +203,31 @@ typedef struct tc_bam_stats {
 int  tc_bam_records_to_reads(tc_ctx_t* ctx, const uint8_t* payload, int64_t n_bytes, const int64_t* rec_off, int64_t n_reads,
                              tc_reads_t* dev, tc_bam_stats_t* stats, void* stream);
 
+/* ---- the BAM file as it lies on disk: inflate and record index on the GPU ----
+ * Replaces htslib's bgzf reader and bam_read1 under pysam (reference: indexing.py:6-19 `Readbam`, :96).  The host maps
+ * the file and walks the BGZF member headers (tc_host.h: tc_bgzf_map — one header per member); the file's bytes travel as
+ * they are, fewer than the payload.
+ *
+ * tc_bgzf_inflate: every member inflated by one device thread (RFC 1951: stored, fixed and dynamic blocks), its CRC-32
+ * checked by one warp; *payload_dev = the uncompressed payload in a context buffer (valid until the next call that
+ * decodes a BAM on this context).  TC_ERR_ARG names the first member that does not inflate or fails its CRC, like htslib.
+ *
+ * tc_bam_index_records: the offsets of the placed records' refID fields (refID >= 0), in file order — what the host reader's
+ * sequential hop produces — found in parallel over 64 KiB chunks of the payload and PROVEN by linking every chunk's chain
+ * of records to the next chunk's start from the header's end on (bgzf.cu).  `first_record`: payload offset behind the
+ * header (the caller parses the header: it needs the reference names anyway); `ref_len`: the header's reference lengths
+ * (host or device).  Records are validated as the host reader does (sizes against block_size, NUL-terminated name, the
+ * CG-tag placeholder refused): TC_ERR_ARG then; the host reader (tc_bam_payload) names the record.
+ * The results feed tc_bam_records_to_reads, which takes device pointers as they are. */
+#ifndef TC_BGZF_BLOCK_T
+#define TC_BGZF_BLOCK_T
+typedef struct tc_bgzf_block { int64_t coff; int32_t csize; int32_t usize; int64_t uoff; } tc_bgzf_block_t;
+#endif
+int  tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_bytes, const tc_bgzf_block_t* blocks, int64_t n_blocks,
+                     int64_t payload_bytes, const uint8_t** payload_dev, void* stream);
+int  tc_bam_index_records(tc_ctx_t* ctx, const uint8_t* payload_dev, int64_t n_bytes, int64_t first_record, int32_t n_ref,
+                          const int32_t* ref_len, const int64_t** rec_off_dev, int64_t* n_placed, int64_t* n_records, void* stream);
+
 /* ---- (1) pileup: replaces pysam pileup + parse_query_sequences, indexing.py:100-143 ----
  * counts: int32[TC_NROWS][ref_len] (host or device), fully overwritten, zero rows for uncovered
  * positions (indexing.py:147-151).  Reads starting at or beyond ref_len are an error (TC_ERR_RANGE). */

@@ -1148,3 +1148,167 @@ def test_bam_records_parsed_on_device_equal_host_decode(ctx, name):
         assert np.array_equal(got, arr.reshape(-1)), field
     L = host.ref_lens[0]
     assert np.array_equal(ctx.pileup_counts(dev, L), ctx.pileup_counts(host, L))
+
+
+# ---------------------------------------------------------------------------- BAM files inflated and indexed on the device
+def _assert_device_reads_equal_host(ctx, dev, host):
+    st = dev.stats
+    assert dev.n_reads == host.n_reads
+    assert (st.n_seq_words, st.n_cigar_ops) == (host.seq4.shape[0], host.cigar.shape[0])
+    if host.n_reads:
+        assert st.max_ref_span == host.max_ref_span and bool(st.sorted) == host.sorted
+        assert st.aligned_bases == host.count_aligned_bases(0)
+    s = dev.struct
+    for field, arr in (("pos", host.pos), ("flag", host.flag), ("mapq", host.mapq), ("l_seq", host.l_seq), ("seq_off", host.seq_off),
+                       ("cigar_off", host.cigar_off), ("seq4", host.seq4), ("qual", host.qual), ("cigar", host.cigar),
+                       ("qname_hash", host.qname_hash), ("mpos", host._mpos_for_abi()), ("isize", host.isize)):
+        if host.n_reads == 0 and field in ("seq_off", "cigar_off"):
+            continue
+        got = ctx.download(getattr(s, field), arr.size, arr.dtype)
+        assert np.array_equal(got, arr.reshape(-1)), field
+
+
+def _rebgzf(src: str, dst: str, member_bytes, level=6, strategy=0, empty_every=0):
+    """Re-block a BAM's payload into BGZF members of the given payload sizes (cycled), compression level and strategy."""
+    import gzip
+    import struct
+    import zlib
+
+    with gzip.open(src, "rb") as fh:
+        payload = fh.read()
+    out, p, k = [], 0, 0
+
+    def member(chunk):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        data = c.compress(chunk) + c.flush()
+        bsize = 18 + len(data) + 8
+        assert bsize <= 65536
+        return (bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255]) + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + data +
+                struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    while p < len(payload):
+        n = member_bytes[k % len(member_bytes)]
+        out.append(member(payload[p:p + n]))
+        p += n
+        k += 1
+        if empty_every and k % empty_every == 0:
+            out.append(member(b""))
+    out.append(member(b""))
+    with open(dst, "wb") as fh:
+        fh.write(b"".join(out))
+    return payload
+
+
+@pytest.mark.parametrize("name", MINIS)
+def test_bam_file_inflated_and_indexed_on_device(ctx, name, tmp_path):
+    """tc_bgzf_inflate + tc_bam_index_records + tc_bam_records_to_reads (the host only maps the file and walks the member
+    headers) give exactly the arrays of csrc/host/bamio.c's reader — for the golden BAMs as they are and re-blocked into
+    members of odd sizes (records split across members at every possible place), at compression levels 0 (stored blocks),
+    1, 9, with fixed Huffman codes, and with empty members in between."""
+    import zlib
+
+    from trueconsense_b200 import bamio
+
+    path = f"{GOLD}/{name}.bam"
+    host = bamio.read_bam(path)
+    dev = ctx.bam_file_to_device(path)
+    assert (dev.ref_names, dev.ref_lens) == (host.ref_names, host.ref_lens)
+    assert dev.info["n_records"] == host.info["n_records"] and dev.info["n_dropped_unplaced"] == host.info["n_dropped_unplaced"]
+    _assert_device_reads_equal_host(ctx, dev, host)
+    assert bamio.read_bam_header(path) == (host.ref_names, host.ref_lens)
+    L = host.ref_lens[0]
+    assert np.array_equal(ctx.pileup_counts(dev, L), ctx.pileup_counts(host, L))
+    for k, (sizes, level, strategy, empty) in enumerate((([65280], 0, 0, 0), ([1, 7, 300, 4000], 1, 0, 3), ([60000, 13], 9, zlib.Z_FIXED, 0),
+                                                          ([997], 6, zlib.Z_HUFFMAN_ONLY, 5))):
+        p2 = str(tmp_path / f"re{k}.bam")
+        _rebgzf(path, p2, sizes, level, strategy, empty)
+        host2 = bamio.read_bam(p2)
+        assert host2.n_reads == host.n_reads
+        _assert_device_reads_equal_host(ctx, ctx.bam_file_to_device(p2), host)
+
+
+def test_bam_file_on_device_synthetic_sizes(ctx, tmp_path):
+    """Thousands of members and records; reads longer than a 64 KiB chunk of the payload (the chain of records jumps over
+    chunks: the resolver's walk); a BAM with a header and no record; unplaced records in between."""
+    from trueconsense_b200 import bamio, synth
+    from trueconsense_b200.reads import ReadBatch
+
+    for case in ("amplicon_deep", "shotgun_indels", "long_reads", "paired"):
+        ref, _, b = _synth(case)
+        p = str(tmp_path / f"{case}.bam")
+        bamio.write_bam(p, b, "ref", len(ref), level=1)
+        host = bamio.read_bam(p)
+        dev = ctx.bam_file_to_device(p)
+        _assert_device_reads_equal_host(ctx, dev, host)
+        assert np.array_equal(ctx.pileup_counts(dev, len(ref)), ctx.pileup_counts(b, len(ref)))
+    rng = np.random.default_rng(2)
+    recs = []
+    for i, n in enumerate((50, 70000, 30, 120000, 65536, 10, 200000, 40)):      # records of up to 300 KB between short ones
+        recs.append(dict(pos=5 + i, cigar=f"{n}M", seq="".join("ACGT"[x] for x in rng.integers(0, 4, n)), qual=[int(x) for x in rng.integers(0, 40, n)]))
+    big = ReadBatch.from_records(recs)
+    p = str(tmp_path / "big.bam")
+    bamio.write_bam(p, big, "ref", 300000, level=1)
+    _assert_device_reads_equal_host(ctx, ctx.bam_file_to_device(p), bamio.read_bam(p))
+    empty = ReadBatch.from_records([])
+    p = str(tmp_path / "empty.bam")
+    bamio.write_bam(p, empty, "ref", 1000, level=1)
+    dev = ctx.bam_file_to_device(p)
+    assert dev.n_reads == 0 and dev.ref_lens == [1000]
+
+
+def test_bam_file_on_device_rejects_damaged_files(ctx, tmp_path):
+    """A flipped payload bit is a CRC-32 mismatch (htslib fails there too), a damaged DEFLATE stream does not inflate, a
+    record whose sizes do not add up is refused — errors, not crashes; BamHandle then lets the host reader name the spot."""
+    from trueconsense_b200 import bamio, gpu
+    from trueconsense_b200.indexing import BamHandle
+
+    ref, _, b = _synth("shotgun_indels")
+    good = str(tmp_path / "good.bam")
+    bamio.write_bam(good, b, "ref", len(ref), level=1)
+    raw = bytearray(open(good, "rb").read())
+    m = bamio.map_bgzf(good)
+    blocks = m.blocks()
+    m.release()
+    assert len(blocks) > 5
+    rng = np.random.default_rng(9)
+    refused = 0
+    for trial in range(24):
+        bad = bytearray(raw)
+        blk = blocks[int(rng.integers(0, len(blocks) - 1))]
+        if trial % 3 == 0:          # the stored CRC
+            bad[int(blk["coff"]) + int(blk["csize"]) + int(rng.integers(0, 4))] ^= 1 << int(rng.integers(0, 8))
+        else:                       # the DEFLATE stream
+            bad[int(blk["coff"]) + int(rng.integers(0, blk["csize"]))] ^= 1 << int(rng.integers(0, 8))
+        p = str(tmp_path / f"bad{trial}.bam")
+        open(p, "wb").write(bytes(bad))
+        with pytest.raises(gpu.TcError) as ei:
+            ctx.bam_file_to_device(p)
+        assert "BGZF member" in str(ei.value)
+        refused += 1
+        if trial < 3:
+            with pytest.raises(OSError):
+                BamHandle(p).device_reads()
+    assert refused == 24
+    # a record that lies about its sizes, inside intact members
+    import struct
+
+    payload = bytearray(_rebgzf(good, str(tmp_path / "tmp.bam"), [65280]))
+    hdr = bamio.parse_bam_header(bytes(payload[:4096]), len(payload))
+    q = hdr[2]
+    for _ in range(40):
+        q += 4 + struct.unpack_from("<i", payload, q)[0]
+    struct.pack_into("<I", payload, q + 4 + 16, 1 << 20)            # l_seq far beyond block_size
+    src = str(tmp_path / "lying_payload.bin.gz")
+    import gzip
+
+    with gzip.open(src, "wb") as fh:
+        fh.write(bytes(payload))
+    lying = str(tmp_path / "lying.bam")
+    _rebgzf(src, lying, [65280])
+    with pytest.raises(gpu.TcError):
+        ctx.bam_file_to_device(lying)
+    with pytest.raises(OSError) as ei:
+        BamHandle(lying).device_reads()
+    assert "shorter than its fields" in str(ei.value)
+    # and the context still works
+    _assert_device_reads_equal_host(ctx, ctx.bam_file_to_device(good), bamio.read_bam(good))

@@ -81,6 +81,112 @@ class BamPayload:
             pass
 
 
+class TcBgzfBlock(C.Structure):
+    """ctypes mirror of ``tc_bgzf_block_t``: the raw DEFLATE stream file[coff : coff + csize] inflates to payload[uoff : uoff + usize]."""
+
+    _fields_ = [("coff", C.c_int64), ("csize", C.c_int32), ("usize", C.c_int32), ("uoff", C.c_int64)]
+
+
+class TcBgzfMap(C.Structure):
+    """ctypes mirror of ``tc_bgzf_map_t`` (include/tc_host.h)."""
+
+    _fields_ = [("file", C.POINTER(C.c_uint8)), ("file_bytes", C.c_int64), ("blocks", C.POINTER(TcBgzfBlock)), ("n_blocks", C.c_int64),
+                ("payload_bytes", C.c_int64)]
+
+
+class BgzfMap:
+    """A BAM file mapped read-only plus the index of its BGZF members (``tc_bgzf_map``): what the GPU needs to inflate it
+    (``gpu.Context.bam_file_to_device``).  The host has read one header per member, nothing else."""
+
+    def __init__(self, st: TcBgzfMap, lib: C.CDLL):
+        self._st, self._lib = st, lib
+        self.file_bytes = int(st.file_bytes)
+        self.n_blocks = int(st.n_blocks)
+        self.payload_bytes = int(st.payload_bytes)
+
+    @property
+    def file_ptr(self) -> int:
+        return C.cast(self._st.file, C.c_void_p).value or 0
+
+    @property
+    def blocks_ptr(self) -> int:
+        return C.cast(self._st.blocks, C.c_void_p).value or 0
+
+    def blocks(self) -> np.ndarray:
+        """The member index as a structured array (a copy)."""
+        dt = np.dtype([("coff", "<i8"), ("csize", "<i4"), ("usize", "<i4"), ("uoff", "<i8")])
+        return np.frombuffer(C.string_at(self._st.blocks, self.n_blocks * dt.itemsize), dtype=dt).copy()
+
+    def release(self) -> None:
+        if self._st is not None:
+            self._lib.tc_bgzf_unmap(C.byref(self._st))
+            self._st = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def parse_bam_header(buf: bytes, n_total: int):
+    """(reference names, reference lengths, payload offset of the first record) from the first bytes of a BAM's payload;
+    None when ``buf`` ends inside the header (and the payload is longer: fetch more)."""
+    import struct
+
+    def short():
+        if len(buf) >= n_total:
+            raise OSError("truncated BAM header")
+        return None
+
+    if len(buf) < 12:
+        if n_total < 12:
+            raise OSError("missing BAM magic")
+        return short()
+    if buf[:4] != b"BAM\1":
+        raise OSError("missing BAM magic")
+    l_text = struct.unpack_from("<i", buf, 4)[0]
+    if l_text < 0 or 8 + l_text + 4 > n_total:
+        raise OSError("truncated BAM header")
+    p = 8 + l_text
+    if p + 4 > len(buf):
+        return short()
+    n_ref = struct.unpack_from("<i", buf, p)[0]
+    p += 4
+    if n_ref < 0 or n_ref * 8 > n_total - p:
+        raise OSError(f"bad BAM reference count {n_ref}")
+    names, lens = [], []
+    for _ in range(n_ref):
+        if p + 4 > len(buf):
+            return short()
+        l_name = struct.unpack_from("<i", buf, p)[0]
+        p += 4
+        if l_name < 0 or p + l_name + 4 > n_total:
+            raise OSError("truncated BAM reference list")
+        if p + l_name + 4 > len(buf):
+            return short()
+        names.append(buf[p:p + l_name].split(b"\0")[0].decode(errors="replace"))
+        p += l_name
+        lens.append(struct.unpack_from("<i", buf, p)[0])
+        p += 4
+    return names, lens, p
+
+
+def read_bam_header(path: str):
+    """(reference names, reference lengths) of a BAM: only the members holding the header are inflated."""
+    import gzip
+
+    n = 1 << 16
+    size = os.path.getsize(path)
+    while True:
+        with gzip.open(path, "rb") as fh:
+            buf = fh.read(n)
+        got = parse_bam_header(buf, len(buf) if len(buf) < n else max(n + 1, 64 * size))
+        if got is not None:
+            return got[0], got[1]
+        n *= 4
+
+
 _lib = None
 
 
@@ -103,6 +209,10 @@ def host_lib() -> C.CDLL:
         lib.tc_bam_payload.restype = C.c_int
         lib.tc_bampayload_free.argtypes = [C.POINTER(TcBamPayload)]
         lib.tc_bampayload_free.restype = None
+        lib.tc_bgzf_map.argtypes = [C.c_char_p, C.POINTER(TcBgzfMap), C.c_char_p, C.c_int]
+        lib.tc_bgzf_map.restype = C.c_int
+        lib.tc_bgzf_unmap.argtypes = [C.POINTER(TcBgzfMap)]
+        lib.tc_bgzf_unmap.restype = None
         _lib = lib
     return _lib
 
@@ -185,6 +295,17 @@ def read_bam_payload(path: str, threads: int = 0) -> BamPayload:
     if rc != 0:
         raise OSError(f"tc_bam_payload({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
     return BamPayload(st, lib)
+
+
+def map_bgzf(path: str) -> BgzfMap:
+    """Map a BAM and index its BGZF members (``tc_bgzf_map``); the device inflates them (``gpu.Context.bam_file_to_device``)."""
+    lib = host_lib()
+    st = TcBgzfMap()
+    err = C.create_string_buffer(512)
+    rc = lib.tc_bgzf_map(os.fsencode(path), C.byref(st), err, len(err))
+    if rc != 0:
+        raise OSError(f"tc_bgzf_map({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
+    return BgzfMap(st, lib)
 
 
 def hostreads_struct(batch: ReadBatch) -> TcHostReads:

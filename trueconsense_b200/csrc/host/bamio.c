@@ -99,7 +99,7 @@ int tc_hostreads_alloc_(tc_hostreads_t* o, int64_t n, int64_t n_words, int64_t n
     return alloc_reads(o, n, n_words, n_ops);
 }
 
-typedef struct { int64_t coff; int32_t csize; int64_t uoff; int32_t usize; } blk_t;
+typedef tc_bgzf_block_t blk_t;
 
 /* header + record hop over the payload while it is still being inflated */
 typedef struct {
@@ -215,31 +215,13 @@ static int scan_payload(scan_t* s) {
 }
 
 
-/* Stages (1)-(3): the file's uncompressed payload, its header in *out, and the offsets of the placed records (of their
- * refID field, i.e. behind block_size).  The caller owns *u_out and *recoff_out (free). */
-static int bam_payload_stage(const char* path, int n_threads, tc_hostreads_t* out, uint8_t** u_out, int64_t* utotal_out,
-                             int64_t** recoff_out, int64_t* nkept_out, char* err, int errlen) {
-    memset(out, 0, sizeof(*out));
-#ifdef _OPENMP
-    if (n_threads <= 0) n_threads = omp_get_num_procs();
-#else
-    n_threads = 1;
-#endif
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail(err, errlen, -1, "cannot open %s", path);
-    struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); return fail(err, errlen, -1, "cannot stat %s", path); }
-    int64_t fsize = st.st_size;
-    if (fsize < 28) { close(fd); return fail(err, errlen, -2, "%s: too short for a BAM file", path); }
-    const uint8_t* f = mmap(NULL, (size_t)fsize, PROT_READ, MAP_PRIVATE, fd, 0);
-    close(fd);
-    if (f == MAP_FAILED) return fail(err, errlen, -1, "mmap failed for %s", path);
-
-    double t0 = now_s();
-    /* (1) index BGZF blocks */
+/* (1) of every reader: walk the BGZF member headers (each says how long it is) — where every raw DEFLATE stream sits in the
+ * file, how many bytes it inflates to, and where those go in the payload.  Every size comes from the file: nothing is
+ * used before it has been checked against the file and the format. */
+static int bgzf_index_blocks(const uint8_t* f, int64_t fsize, blk_t** blk_out, int64_t* nblk_out, int64_t* utotal_out, char* err, int errlen) {
     int64_t nblk = 0, cap = 1024;
     blk_t* blk = malloc(cap * sizeof(blk_t));
-    if (!blk) { munmap((void*)f, fsize); return fail(err, errlen, -5, "out of memory"); }
+    if (!blk) return fail(err, errlen, -5, "out of memory");
     int64_t off = 0, uoff = 0;
     int rc = 0;
     while (off < fsize) {
@@ -248,7 +230,6 @@ static int bam_payload_stage(const char* path, int n_threads, tc_hostreads_t* ou
         if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) {
             rc = fail(err, errlen, -2, "not a BGZF block at offset %lld", (long long)off); break;
         }
-        /* every size below comes from the file: nothing is used before it has been checked against the file and the format */
         int xlen = rd16(h + 10);
         if (off + 12 + xlen > fsize) { rc = fail(err, errlen, -2, "truncated BGZF extra field at %lld", (long long)off); break; }
         int bsize = -1;
@@ -275,8 +256,37 @@ static int bam_payload_stage(const char* path, int n_threads, tc_hostreads_t* ou
         blk[nblk].uoff = uoff; blk[nblk].usize = usize;
         ++nblk; off += bsize; uoff += usize;
     }
-    if (rc) { free(blk); munmap((void*)f, fsize); return rc; }
-    int64_t utotal = uoff;
+    if (rc) { free(blk); return rc; }
+    *blk_out = blk; *nblk_out = nblk; *utotal_out = uoff;
+    return 0;
+}
+
+/* Stages (1)-(3): the file's uncompressed payload, its header in *out, and the offsets of the placed records (of their
+ * refID field, i.e. behind block_size).  The caller owns *u_out and *recoff_out (free). */
+static int bam_payload_stage(const char* path, int n_threads, tc_hostreads_t* out, uint8_t** u_out, int64_t* utotal_out,
+                             int64_t** recoff_out, int64_t* nkept_out, char* err, int errlen) {
+    memset(out, 0, sizeof(*out));
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_num_procs();
+#else
+    n_threads = 1;
+#endif
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(err, errlen, -1, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return fail(err, errlen, -1, "cannot stat %s", path); }
+    int64_t fsize = st.st_size;
+    if (fsize < 28) { close(fd); return fail(err, errlen, -2, "%s: too short for a BAM file", path); }
+    const uint8_t* f = mmap(NULL, (size_t)fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (f == MAP_FAILED) return fail(err, errlen, -1, "mmap failed for %s", path);
+
+    double t0 = now_s();
+    /* (1) index BGZF blocks */
+    blk_t* blk = NULL;
+    int64_t nblk = 0, utotal = 0;
+    int rc = bgzf_index_blocks(f, fsize, &blk, &nblk, &utotal, err, errlen);
+    if (rc) { munmap((void*)f, fsize); return rc; }
     uint8_t* u = malloc((size_t)(utotal > 0 ? utotal : 1));
     if (!u) { free(blk); munmap((void*)f, fsize); return fail(err, errlen, -5, "out of memory (%lld bytes)", (long long)utotal); }
 
@@ -457,6 +467,32 @@ void tc_bampayload_free(tc_bampayload_t* p) {
     if (!p) return;
     free(p->payload); free(p->rec_off); free(p->ref_len); free(p->ref_names);
     memset(p, 0, sizeof(*p));
+}
+
+/* The file as it is, plus the index of its BGZF members: what tc_bgzf_inflate (trueconsense_b200.h) needs to inflate the
+ * members on the GPU — the host touches one header per member and nothing else. */
+int tc_bgzf_map(const char* path, tc_bgzf_map_t* out, char* err, int errlen) {
+    memset(out, 0, sizeof(*out));
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(err, errlen, -1, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return fail(err, errlen, -1, "cannot stat %s", path); }
+    int64_t fsize = st.st_size;
+    if (fsize < 28) { close(fd); return fail(err, errlen, -2, "%s: too short for a BAM file", path); }
+    const uint8_t* f = mmap(NULL, (size_t)fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (f == MAP_FAILED) return fail(err, errlen, -1, "mmap failed for %s", path);
+    int rc = bgzf_index_blocks(f, fsize, &out->blocks, &out->n_blocks, &out->payload_bytes, err, errlen);
+    if (rc) { munmap((void*)f, fsize); return rc; }
+    out->file = f; out->file_bytes = fsize;
+    return 0;
+}
+
+void tc_bgzf_unmap(tc_bgzf_map_t* m) {
+    if (!m) return;
+    if (m->file) munmap((void*)m->file, (size_t)m->file_bytes);
+    free(m->blocks);
+    memset(m, 0, sizeof(*m));
 }
 
 /* ------------------------------------------------------------------ writer */

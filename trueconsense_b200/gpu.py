@@ -116,6 +116,10 @@ def lib() -> C.CDLL:
                                                  C.POINTER(i32), vp, i64, vp]
             l.tc_bam_records_to_reads.argtypes = [vp, vp, i64, vp, i64, C.POINTER(TcReads), C.POINTER(BamStats), vp]
             l.tc_bam_records_to_reads.restype = C.c_int
+            l.tc_bgzf_inflate.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(vp), vp]
+            l.tc_bgzf_inflate.restype = C.c_int
+            l.tc_bam_index_records.argtypes = [vp, vp, i64, i64, i32, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), vp]
+            l.tc_bam_index_records.restype = C.c_int
             l.tc_download.argtypes = [vp, vp, vp, i64, vp]
             l.tc_download.restype = C.c_int
             l.tc_sample_enqueue.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
@@ -269,6 +273,53 @@ class Context:
                                                       payload.n_reads, C.byref(dev), C.byref(st), stream))
         d = DeviceReads(dev, None, self, self._generation)
         d.stats = st
+        return d
+
+    def bam_file_to_device(self, path: str, stream: int = 0) -> DeviceReads:
+        """A BAM file to the flat read arrays in device memory with the GPU doing all of it: the host maps the file and walks
+        the BGZF member headers (``bamio.map_bgzf``); the device inflates every member and checks its CRC-32
+        (``tc_bgzf_inflate``), finds and proves the record offsets (``tc_bam_index_records``) and parses the records
+        (``tc_bam_records_to_reads``).  The result carries ``.ref_names``, ``.ref_lens``, ``.stats`` and ``.info``
+        (records, unplaced records dropped, timings).  ``TcError`` / ``OSError`` for a file that does not decode."""
+        import time
+
+        from . import bamio
+
+        t0 = time.perf_counter()
+        m = bamio.map_bgzf(path)
+        t1 = time.perf_counter()
+        try:
+            payload = C.c_void_p()
+            self._generation += 1
+            self._check(self._lib.tc_bgzf_inflate(self._h, m.file_ptr, m.file_bytes, m.blocks_ptr, m.n_blocks, m.payload_bytes,
+                                                  C.byref(payload), stream))
+            n_bytes, info = m.payload_bytes, {"bam_bytes": m.file_bytes, "payload_bytes": m.payload_bytes, "n_members": m.n_blocks}
+        finally:
+            m.release()
+        t2 = time.perf_counter()
+        n = 1 << 16
+        while True:
+            head = self.download(payload.value, min(n, n_bytes), np.uint8, stream).tobytes() if n_bytes else b""
+            hdr = bamio.parse_bam_header(head, n_bytes)
+            if hdr is not None:
+                break
+            n *= 4
+        names, lens, first = hdr
+        ref_len = np.asarray(lens if lens else [0], dtype=np.int32)
+        rec, n_placed, n_records = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.tc_bam_index_records(self._h, payload, n_bytes, first, len(lens), ref_len.ctypes.data, C.byref(rec),
+                                                   C.byref(n_placed), C.byref(n_records), stream))
+        t3 = time.perf_counter()
+        dev = TcReads()
+        st = BamStats()
+        self._check(self._lib.tc_bam_records_to_reads(self._h, payload, n_bytes, rec, n_placed.value, C.byref(dev), C.byref(st), stream))
+        t4 = time.perf_counter()
+        d = DeviceReads(dev, None, self, self._generation)
+        d.stats = st
+        d.ref_names, d.ref_lens = names, lens
+        info.update(n_records=int(n_records.value), n_dropped_unplaced=int(n_records.value - n_placed.value), t_map_s=t1 - t0,
+                    t_inflate_s=t2 - t1, t_index_s=t3 - t2, t_parse_s=t4 - t3)
+        d.info = info
         return d
 
     # ------------------------------------------------------------------ (1) pileup

@@ -21,14 +21,15 @@ COLUMNS = ["coverage", "A", "T", "C", "G", "X", "I"]
 
 class BamHandle:
     """What ``Readbam`` returns: a BAM on its way to the device plus the attributes of ``pysam.AlignmentFile`` the reference
-    touches (``references``; Events.py:63).  The file is inflated on the host's cores, its records are parsed on the GPU
-    (``tc_bam_records_to_reads``) straight into the context's read buffers; ``reads`` (a host-side decode into numpy arrays) is
+    touches (``references``; Events.py:63).  The file travels to the device as it is: BGZF members inflated, record offsets
+    found and records parsed on the GPU (``gpu.Context.bam_file_to_device``) straight into the context's read buffers; ``reads`` (a host-side decode into numpy arrays) is
     only made when somebody asks for it."""
 
     def __init__(self, filename: str, reads: ReadBatch | None = None):
         self.filename = filename
         self._reads = reads
         self._payload = None
+        self._hdr = None
         self._dev = None
         self._lock = threading.Lock()
         self._insert_cache: dict = {}
@@ -45,9 +46,11 @@ class BamHandle:
         with self._lock:
             if self._reads is not None:
                 return self._reads.ref_names, self._reads.ref_lens
-            if self._payload is None:
-                self._payload = bamio.read_bam_payload(self.filename)
-            return self._payload.ref_names, self._payload.ref_lens
+            if self._payload is not None:
+                return self._payload.ref_names, self._payload.ref_lens
+            if self._hdr is None:
+                self._hdr = bamio.read_bam_header(self.filename)       # only the members holding the header are inflated
+            return self._hdr
 
     @property
     def references(self):
@@ -87,10 +90,15 @@ class BamHandle:
                         raise ValueError("Unsorted input. Pileup aborts")
                     d = ctx.upload(b, with_qual=False)
                 else:
-                    if self._payload is None or self._payload.n_bytes == 0:        # (released after an earlier parse)
+                    try:
+                        d = ctx.bam_file_to_device(self.filename)      # inflate, record index and parse on the GPU
+                        self._hdr = (d.ref_names, d.ref_lens)
+                    except gpu.TcError:
+                        # a file the device path refuses: the host reader names the broken member / record (or, should it
+                        # read the file after all, feeds the device parse)
                         self._payload = bamio.read_bam_payload(self.filename)
-                    d = ctx.bam_to_device(self._payload)
-                    self._payload.release()         # the device holds the arrays now; the header stays
+                        d = ctx.bam_to_device(self._payload)
+                        self._payload.release()     # the device holds the arrays now; the header stays
                     if d.stats.multi_contig:
                         raise ValueError("multi-contig BAM: TrueConsense indexes positions of a single reference "
                                          "(its DataFrame index would hold duplicate positions)")
