@@ -35,11 +35,13 @@ GUARD = 64
 
 def _inflate(lib, comp: bytes, n_out: int, misalign: int = 0, stride: int = 1):
     """(rc, output bytes); asserts the guard bytes around the output are untouched."""
-    buf = np.zeros(misalign + len(comp) + 16, dtype=np.uint8)        # (padded: the reader loads aligned words)
-    buf[misalign:misalign + len(comp)] = np.frombuffer(comp, dtype=np.uint8)
-    # an aligned base + misalign: the stream starts `misalign` bytes into a word
-    base = buf.ctypes.data
-    assert base % 4 == 0 or True
+    # the reader fetches aligned 16-byte vectors: readable from the boundary in front of the stream to the one behind it
+    raw = np.zeros(len(comp) + 80, dtype=np.uint8)
+    start = (-raw.ctypes.data) % 16 + 16 + misalign
+    raw[start:start + len(comp)] = np.frombuffer(comp, dtype=np.uint8)
+    raw[start + len(comp):] = 0xEE                                   # (bytes behind the stream must not matter)
+    raw[:start] = 0xEE
+    base, misalign = raw.ctypes.data + start, 0
     out = np.full(n_out + 2 * GUARD, 0xA5, dtype=np.uint8)
     rc = lib.h_inflate(base + misalign, len(comp), out.ctypes.data + GUARD, n_out, stride)
     assert (out[:GUARD] == 0xA5).all() and (out[GUARD + n_out:] == 0xA5).all(), "wrote outside the output"
@@ -75,7 +77,7 @@ def test_inflate_equals_zlib_for_every_block_type(h):
         for level in (0, 1, 6, 9):
             for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
                 comp = _raw_deflate(data, level, strategy, mem=8 if n % 3 else 1)
-                for mis in ((0,) if n % 4 else (0, 1, 2, 3)):
+                for mis in ((0,) if n % 4 else (0, 1, 2, 3, 5, 11, 15)):
                     rc, got = _inflate(h, comp, len(data), misalign=mis, stride=1 if n % 2 else 32)
                     assert rc == 0, (len(data), level, strategy, mis, rc)
                     assert got == data

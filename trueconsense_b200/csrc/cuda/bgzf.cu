@@ -6,10 +6,9 @@
 // sample is a gigabyte and more.  Here the host only walks the member headers (csrc/host/bamio.c tc_bgzf_map: one header
 // per member) and ships the file's bytes as they are — fewer than the payload — and the device does the rest:
 //
-//   bgzf_inflate_kernel   one THREAD per member (Huffman decoding is a serial walk of a bit stream; the members are
-//                         independent): inflate_core.cuh's decoder, the warp's 32 first-level tables interleaved in shared
-//                         memory (entry i of lane t at [i][t]: conflict-free whatever the lanes look up).  Thousands of
-//                         members in flight; the kernel is latency-bound per thread, throughput comes from their number.
+//   bgzf_inflate_kernel   one member per warp, decoded by one lane (Huffman decoding is a serial walk of a bit stream; the
+//                         members are independent): inflate_core.cuh's decoder, first-level tables in shared memory.
+//                         Thousands of members in flight; latency-bound per member, throughput comes from their number.
 //   bgzf_crc_kernel       one WARP per member: every lane the CRC-32 of 1/32 of the member's payload, the 32 pieces
 //                         combined by multiplication in GF(2)[x] / p(x) (zlib's crc32_combine), compared with the member's
 //                         stored CRC.  htslib fails on a CRC mismatch: so does this.
@@ -47,18 +46,23 @@ __device__ __forceinline__ void report(unsigned long long* status, long long mem
     atomicMin(status, ((unsigned long long)member << 8) | (unsigned long long)code);
 }
 
-constexpr int INFLATE_SMEM = 2 * 32 * (LUT_SIZE + DLUT_SIZE);
+// One member per WARP, decoded by its first lane.  Thirty-two members per warp (a lane each) was measured first: the
+// lanes of a warp run different code paths at every symbol (literal, match, refill, table build) and do not reconverge —
+// 32 x serialised, 269 ms for 2348 members.  A lane alone in its warp loses nothing to divergence, and the members in flight
+// per SM are the same (64 warps against 3 x 32 lanes at 72 KB of tables per warp).
+constexpr int INFLATE_WARPS = 8;
 
-__global__ void __launch_bounds__(32) bgzf_inflate_kernel(const uint8_t* __restrict__ file, const tc_bgzf_block_t* __restrict__ blk, long long n_blk,
-                                                          uint8_t* __restrict__ payload, unsigned long long* status) {
-    extern __shared__ __align__(16) uint16_t tables[];          // [LUT_SIZE][32] literal/length, [DLUT_SIZE][32] distance
-    const long long m = (long long)blockIdx.x * 32 + threadIdx.x;
-    if (m >= n_blk) return;
+
+__global__ void __launch_bounds__(32 * INFLATE_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ file, const tc_bgzf_block_t* __restrict__ blk,
+                                                                          long long n_blk, uint8_t* __restrict__ payload, unsigned long long* status) {
+    __shared__ __align__(16) uint16_t tables[INFLATE_WARPS][LUT_SIZE + DLUT_SIZE];
+    const int w = threadIdx.x >> 5;
+    const long long m = (long long)blockIdx.x * INFLATE_WARPS + w;
+    if (m >= n_blk || (threadIdx.x & 31) != 0) return;
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
     const tc_bgzf_block_t b = blk[m];
-    const int rc = inflate_block(file + b.coff, b.csize, payload + b.uoff, b.usize, tables + threadIdx.x, tables + 32 * LUT_SIZE + threadIdx.x, 32,
-                                 hl, hd, lens);
+    const int rc = inflate_block(file + b.coff, b.csize, payload + b.uoff, b.usize, tables[w], tables[w] + LUT_SIZE, 1, hl, hd, lens);
     if (rc) report(status, m, rc);
 }
 
@@ -268,8 +272,11 @@ TC_API int tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_byte
     }
     if (uoff != payload_bytes) return tc_fail(ctx, TC_ERR_ARG, "the members inflate to %lld bytes, not %lld", (long long)uoff, (long long)payload_bytes);
     int rc;
-    // (the bit reader loads aligned words: up to 3 bytes in front of a stream — the member's own header — and behind it —
-    // its CRC; tc_dev_buf pads every buffer)
+    const bool trace = getenv("TC_TRACE") != nullptr;       // stage times to stderr (diagnostics)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
+    // (the bit reader fetches aligned 16-byte vectors: up to 15 bytes in front of a stream — the member's own 18-byte
+    // header — and behind it — its CRC, ISIZE and the next header; the buffer is padded behind the file's end)
     if (!tc_is_device_ptr(file) && !tc_dev_buf(ctx, SLOT_BGZF_FILE, (size_t)file_bytes + 16)) return TC_ERR_NOMEM;
     const uint8_t* d_file = (const uint8_t*)tc_stage_in(ctx, SLOT_BGZF_FILE, file, (size_t)file_bytes, s, &rc); if (rc) return rc;
     const tc_bgzf_block_t* d_blk = (const tc_bgzf_block_t*)tc_stage_in(ctx, SLOT_BGZF_BLOCKS, blocks, sizeof(tc_bgzf_block_t) * (size_t)n_blocks, s, &rc);
@@ -278,14 +285,23 @@ TC_API int tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_byte
     unsigned long long* d_status = (unsigned long long*)tc_dev_buf(ctx, SLOT_STATUS, 64);
     if (!d_payload || !d_status) return TC_ERR_NOMEM;
     TC_CUDA(cudaMemsetAsync(d_status, 0xff, 8, s));
-    TC_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INFLATE_SMEM));
-    bgzf_inflate_kernel<<<(unsigned)((n_blocks + 31) / 32), 32, INFLATE_SMEM, s>>>(d_file, d_blk, n_blocks, d_payload, d_status);
+    if (trace) cudaEventRecord(ev[1], s);
+    bgzf_inflate_kernel<<<(unsigned)((n_blocks + INFLATE_WARPS - 1) / INFLATE_WARPS), 32 * INFLATE_WARPS, 0, s>>>(d_file, d_blk, n_blocks, d_payload, d_status);
     TC_LAUNCH_CHECK();
+    if (trace) cudaEventRecord(ev[2], s);
     bgzf_crc_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, s>>>(d_file, d_blk, n_blocks, d_payload, d_status);
     TC_LAUNCH_CHECK();
     unsigned long long* h = (unsigned long long*)ctx->host_status;
     TC_D2H(h, d_status, 8, s);
+    if (trace) cudaEventRecord(ev[3], s);
     TC_CUDA(cudaStreamSynchronize(s));
+    if (trace) {
+        float t01 = 0, t12 = 0, t23 = 0;
+        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+        fprintf(stderr, "[tc_bgzf_inflate] %lld members, %lld -> %lld bytes: upload %.3f ms, inflate %.3f ms, crc %.3f ms\n", (long long)n_blocks,
+                (long long)file_bytes, (long long)payload_bytes, t01, t12, t23);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     if (h[0] != NO_ERROR) {
         const int code = (int)(h[0] & 0xff);
         return tc_fail(ctx, TC_ERR_ARG, code == CRC_ERR ? "BGZF member %lld: CRC-32 mismatch" : "BGZF member %lld does not inflate (code %d)",

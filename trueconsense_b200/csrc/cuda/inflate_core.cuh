@@ -44,31 +44,58 @@ struct huff {
     uint16_t symbol[288];       // symbols ordered by (length, symbol)
 };
 
-// LSB-first bit reader over aligned 32-bit words.  `base` is 4-byte aligned; the stream starts `skip` bytes into it.
-// Words at and behind `n_words` read as zero: a corrupt stream cannot walk out of the buffer; bits_over() tells whether
-// more bits were CONSUMED than the stream holds (the buffer itself runs up to 64 bits ahead).
+// LSB-first bit reader.  The stream is fetched in aligned 16-byte vectors, one vector AHEAD of the one being consumed: a
+// member's decode is a chain of dependent steps, and a load that has to come from L2 / DRAM (~700 cycles against ~90 for a
+// symbol) in the middle of it was two thirds of the time — the vector asked for 16 symbols earlier has arrived when it is
+// needed.  Vectors at and behind `n_vec` read as zero: a corrupt stream cannot walk out of the buffer (which must be
+// readable from the 16-byte boundary in front of the stream to the one behind it); bits_over() tells whether more bits
+// were CONSUMED than the stream holds.
+struct alignas(16) vec4 { uint32_t x, y, z, w; };
+
 struct bits {
-    const uint32_t* base;
-    int64_t k, n_words, lim_bits;
+    const vec4* base;
+    int64_t k, n_vec;           // next vector to fetch, vectors covering the stream
+    vec4 nxt;                   // fetched ahead
+    uint64_t lo, hi;            // words of the current vector not yet taken
+    int words_left;
+    int64_t taken_bits, lim_bits;
     uint64_t buf;
     int n;
 };
 
+TCI_HD uint32_t bits_pop_word(bits& b) {
+    if (b.words_left == 0) {
+        b.lo = (uint64_t)b.nxt.x | ((uint64_t)b.nxt.y << 32);
+        b.hi = (uint64_t)b.nxt.z | ((uint64_t)b.nxt.w << 32);
+        b.words_left = 4;
+        if (b.k < b.n_vec) b.nxt = b.base[b.k]; else b.nxt = vec4{0, 0, 0, 0};
+        b.k++;
+    }
+    const uint32_t w = (uint32_t)b.lo;
+    b.lo = (b.lo >> 32) | (b.hi << 32);
+    b.hi >>= 32;
+    b.words_left--;
+    return w;
+}
 TCI_HD void bits_init(bits& b, const uint8_t* in, int64_t n_bytes) {
-    const uintptr_t a = (uintptr_t)in & 3u;
-    b.base = (const uint32_t*)(in - a);
-    b.n_words = ((int64_t)a + n_bytes + 3) / 4;
-    b.lim_bits = 8 * ((int64_t)a + n_bytes);
-    b.k = 0; b.buf = 0; b.n = 0;
-    if (b.n_words > 0) { b.buf = (uint64_t)(b.base[0] >> (8 * a)); b.n = 32 - 8 * (int)a; b.k = 1; }
+    const uintptr_t a = (uintptr_t)in & 15u;
+    b.base = (const vec4*)(in - a);
+    b.n_vec = ((int64_t)a + n_bytes + 15) / 16;
+    b.nxt = b.n_vec > 0 ? b.base[0] : vec4{0, 0, 0, 0};
+    b.k = 1;
+    b.words_left = 0; b.lo = b.hi = 0;
+    for (uintptr_t i = 0; i < a / 4; ++i) bits_pop_word(b);
+    const int skip = (int)(a & 3u);
+    b.buf = (uint64_t)(bits_pop_word(b) >> (8 * skip));
+    b.n = 32 - 8 * skip;
+    b.taken_bits = 32;
+    b.lim_bits = 8 * ((int64_t)skip + n_bytes);
 }
 TCI_HD void bits_refill(bits& b) {          // afterwards: at least 33 bits
     if (b.n <= 32) {
-        uint32_t w = 0;
-        if (b.k < b.n_words) w = b.base[b.k];
-        b.k++;
-        b.buf |= (uint64_t)w << b.n;
+        b.buf |= (uint64_t)bits_pop_word(b) << b.n;
         b.n += 32;
+        b.taken_bits += 32;
     }
 }
 TCI_HD uint32_t bits_take(bits& b, int n) {  // n <= 32, after a refill
@@ -76,7 +103,7 @@ TCI_HD uint32_t bits_take(bits& b, int n) {  // n <= 32, after a refill
     b.buf >>= n; b.n -= n;
     return v;
 }
-TCI_HD bool bits_over(const bits& b) { return 32 * b.k - b.n > b.lim_bits; }
+TCI_HD bool bits_over(const bits& b) { return b.taken_bits - b.n > b.lim_bits; }
 
 // canonical code from code lengths (puff.c's construct): < 0 over-subscribed, 0 complete, > 0 incomplete
 TCI_HD int huff_build(huff& h, const uint8_t* lengths, int n) {
@@ -244,7 +271,27 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 }
                 if (dist > o) return INF_ERR_DIST;
                 if (o + len > n_out) return INF_ERR_OUTPUT;
-                for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dist];
+                // the copy.  Byte by byte, every byte waits for its own load to come back (the store needs the value, the
+                // next load may alias the store): a round trip to L2 per byte.  So: a run (distance 1) loads once; a source
+                // at least 8 bytes back is fetched 8 bytes at a time, loads first, stores after; only short overlapping
+                // periods go byte by byte.
+                if (dist == 1) {
+                    const uint8_t v = out[o - 1];
+                    for (int i = 0; i < len; ++i) out[o + i] = v;
+                    o += len;
+                } else if (dist >= 8) {
+                    while (len > 0) {
+                        const int n8 = len < 8 ? len : 8;
+                        uint8_t t[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (j < n8) t[j] = out[o - dist + j];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (j < n8) out[o + j] = t[j];
+                        o += n8; len -= n8;
+                    }
+                } else {
+                    for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dist];
+                }
                 if (bits_over(b)) return INF_ERR_INPUT;
             }
             if (bits_over(b)) return INF_ERR_INPUT;
