@@ -306,6 +306,12 @@ int  tc_allreduce_counts(tc_ctx_t* ctx, int32_t* counts_dev, int64_t n_elems, vo
  * Replaces, per shard, the reference's indexing.py:96-143 (BuildIndex over the whole BAM). */
 int  tc_pileup_counts_allreduce(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* params,
                                 int32_t* counts_dev, void* comm, void* stream);
+/* The same in two halves, so that the host's part of pass i (and a caller's reading of its table) hides behind the
+ * device's work on pass i + 1: at most two passes in flight on a context, on the same stream, each with its own table;
+ * reads and table stay untouched until the pass's finish returns.  Every rank must enqueue and finish in the same order. */
+int  tc_pileup_counts_allreduce_enqueue(tc_ctx_t* ctx, const tc_reads_t* reads, int32_t ref_len, const tc_pileup_params_t* params,
+                                        int32_t* counts_dev, void* comm, void* stream, int32_t* ticket);
+int  tc_pileup_counts_allreduce_finish(tc_ctx_t* ctx, int32_t ticket);
 
 #ifdef __cplusplus
 }

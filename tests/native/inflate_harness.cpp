@@ -12,7 +12,8 @@ extern "C" int h_inflate(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
     uint16_t* dlut = (uint16_t*)calloc((size_t)DLUT_SIZE * stride, 2);
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
-    const int rc = inflate_block(in, n_in, out, n_out, lut, dlut, stride, hl, hd, lens);
+    (void)stride;
+    const int rc = inflate_block(in, n_in, out, n_out, lut, dlut, hl, hd, lens);
     free(lut); free(dlut);
     return rc;
 }

@@ -757,6 +757,20 @@ def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
             out.fill_(-1)
             ctx.pileup_counts_allreduce(dev, L, p, out, comm)
             assert np.array_equal(out.cpu().numpy(), exp), i
+        # two passes in flight, a table each, finished in order; a third is refused
+        out_b = torch.empty_like(out)
+        t0 = ctx.pileup_counts_allreduce_enqueue(dev, L, p, out, comm)
+        for i in range(5):
+            t1 = ctx.pileup_counts_allreduce_enqueue(dev, L, p, out if i % 2 else out_b, comm)
+            ctx.pileup_counts_allreduce_finish(t0)
+            assert np.array_equal((out_b if i % 2 else out).cpu().numpy(), exp), i
+            t0 = t1
+        t1 = ctx.pileup_counts_allreduce_enqueue(dev, L, p, out, comm)
+        with pytest.raises(gpu.TcError):
+            ctx.pileup_counts_allreduce_enqueue(dev, L, p, out, comm)
+        ctx.pileup_counts_allreduce_finish(t0)
+        ctx.pileup_counts_allreduce_finish(t1)
+        assert np.array_equal(out.cpu().numpy(), exp) and np.array_equal(out_b.cpu().numpy(), exp)
         ctx.pileup_counts_allreduce(b, L, p, out, comm)                 # host arrays: staged, never captured
         assert np.array_equal(out.cpu().numpy(), exp)
         ref2, _, long_b = _synth("long_reads")

@@ -62,7 +62,11 @@ __global__ void __launch_bounds__(32 * INFLATE_WARPS) bgzf_inflate_kernel(const 
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
     const tc_bgzf_block_t b = blk[m];
-    const int rc = inflate_block(file + b.coff, b.csize, payload + b.uoff, b.usize, tables[w], tables[w] + LUT_SIZE, 1, hl, hd, lens);
+    // (the tables' shared address pinned in a register: re-deriving it from %tid at every look-up was 3 % of the instructions)
+    uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(tables[w]);
+    asm volatile("" : "+r"(lut_s));
+    uint16_t* lut = (uint16_t*)__cvta_shared_to_generic((size_t)lut_s);
+    const int rc = inflate_block(file + b.coff, b.csize, payload + b.uoff, b.usize, lut, lut + LUT_SIZE, hl, hd, lens);
     if (rc) report(status, m, rc);
 }
 

@@ -58,7 +58,7 @@ struct bits {
     vec4 nxt;                   // fetched ahead
     uint64_t lo, hi;            // words of the current vector not yet taken
     int words_left;
-    int64_t taken_bits, lim_bits;
+    uint32_t taken_bits, lim_bits;   // (streams of less than 2^28 bytes)
     uint64_t buf;
     int n;
 };
@@ -89,7 +89,7 @@ TCI_HD void bits_init(bits& b, const uint8_t* in, int64_t n_bytes) {
     b.buf = (uint64_t)(bits_pop_word(b) >> (8 * skip));
     b.n = 32 - 8 * skip;
     b.taken_bits = 32;
-    b.lim_bits = 8 * ((int64_t)skip + n_bytes);
+    b.lim_bits = 8u * ((uint32_t)skip + (uint32_t)n_bytes);
 }
 TCI_HD void bits_refill(bits& b) {          // afterwards: at least 33 bits
     if (b.n <= 32) {
@@ -103,7 +103,7 @@ TCI_HD uint32_t bits_take(bits& b, int n) {  // n <= 32, after a refill
     b.buf >>= n; b.n -= n;
     return v;
 }
-TCI_HD bool bits_over(const bits& b) { return b.taken_bits - b.n > b.lim_bits; }
+TCI_HD bool bits_over(const bits& b) { return b.taken_bits - (uint32_t)b.n > b.lim_bits; }
 
 // canonical code from code lengths (puff.c's construct): < 0 over-subscribed, 0 complete, > 0 incomplete
 TCI_HD int huff_build(huff& h, const uint8_t* lengths, int n) {
@@ -124,18 +124,20 @@ TCI_HD int huff_build(huff& h, const uint8_t* lengths, int n) {
     return left;
 }
 
-// first-level table: lut[i * stride] for every LUT index i (stride > 1: tables of the threads of a warp interleaved)
-template <int BITS>
-TCI_HD void lut_build(const huff& h, uint16_t* lut, int stride) {
-    for (int i = 0; i < (1 << BITS); ++i) lut[i * stride] = 0;
+// first-level table.  LIT: entries of literals (symbols < 256) carry bit 15, so the hot loop tests one bit
+constexpr uint32_t LIT_FLAG = 0x8000u;
+template <int BITS, bool LIT>
+TCI_HD void lut_build(const huff& h, uint16_t* lut) {
+    for (int i = 0; i < (1 << BITS); ++i) lut[i] = 0;
     uint32_t code = 0;
     int idx = 0;
     for (int l = 1; l <= BITS; ++l) {
         for (int j = 0; j < h.count[l]; ++j, ++idx, ++code) {
             uint32_t r = 0;                                     // the code arrives MSB first in an LSB-first stream
             for (int k = 0; k < l; ++k) r |= ((code >> k) & 1u) << (l - 1 - k);
-            const uint16_t e = (uint16_t)((h.symbol[idx] << 4) | l);
-            for (uint32_t v = r; v < (1u << BITS); v += 1u << l) lut[v * stride] = e;
+            const uint32_t sym = h.symbol[idx];
+            const uint16_t e = (uint16_t)((sym << 4) | (uint32_t)l | ((LIT && sym < 256u) ? LIT_FLAG : 0u));
+            for (uint32_t v = r; v < (1u << BITS); v += 1u << l) lut[v] = e;
         }
         code <<= 1;
     }
@@ -158,21 +160,24 @@ TCI_HD int huff_decode_slow(bits& b, const huff& h) {
 }
 
 template <int BITS>
-TCI_HD int huff_decode(bits& b, const huff& h, const uint16_t* lut, int stride) {
-    const uint16_t e = lut[(uint32_t)(b.buf & ((1u << BITS) - 1u)) * stride];
-    if (e) { b.buf >>= (e & 15); b.n -= (e & 15); return e >> 4; }
+TCI_HD int huff_decode(bits& b, const huff& h, const uint16_t* lut) {
+    const uint32_t e = lut[(uint32_t)(b.buf & ((1u << BITS) - 1u))];
+    if (e) { b.buf >>= (e & 15u); b.n -= (int)(e & 15u); return (int)((e & ~LIT_FLAG) >> 4); }
     return huff_decode_slow(b, h);
 }
 
 // Inflate `in[0 .. n_in)` (a raw DEFLATE stream: what sits between a BGZF member's header and its CRC) into
-// `out[0 .. n_out)`, n_out = the member's ISIZE.  `lut` / `dlut`: LUT_SIZE / DLUT_SIZE entries of this thread at the
-// given stride.  `lens`, `hl`, `hd`: per-thread scratch.  Returns INF_OK or the first error; never reads outside the
+// `out[0 .. n_out)`, n_out = the member's ISIZE (< 2^31).  `lut` / `dlut`: LUT_SIZE / DLUT_SIZE entries of this thread.
+// `lens`, `hl`, `hd`: per-thread scratch.  Returns INF_OK or the first error; never reads outside the
 // words covering the input, never writes outside `out`.
-TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out, uint16_t* lut, uint16_t* dlut, int stride,
+TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out_, uint16_t* lut, uint16_t* dlut,
                          huff& hl, huff& hd, uint8_t* lens /* [LENS_SIZE] */) {
+    if (n_out_ < 0 || n_out_ > 0x7fffffff) return INF_ERR_OUTPUT;
+    if (n_in < 0 || n_in >= (1 << 28)) return INF_ERR_INPUT;
+    const uint32_t n_out = (uint32_t)n_out_;
     bits b;
     bits_init(b, in, n_in);
-    int64_t o = 0;
+    uint32_t o = 0;
     for (;;) {
         bits_refill(b);
         if (bits_over(b)) return INF_ERR_INPUT;
@@ -185,7 +190,7 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
             bits_refill(b);
             const uint32_t nlen = bits_take(b, 16);
             if ((len ^ 0xffffu) != nlen) return INF_ERR_STORED;
-            if (o + (int64_t)len > n_out) return INF_ERR_OUTPUT;
+            if (len > n_out - o) return INF_ERR_OUTPUT;
             for (uint32_t i = 0; i < len; ++i) {
                 bits_refill(b);
                 out[o++] = (uint8_t)bits_take(b, 8);
@@ -240,16 +245,40 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 left = huff_build(hd, lens + 19 + nlen, ndist);
                 if (left < 0 || (left > 0 && !(hd.count[1] == 1 && ndist - hd.count[0] == 1))) return INF_ERR_HEADER;
             }
-            lut_build<LUT_BITS>(hl, lut, stride);
-            lut_build<DLUT_BITS>(hd, dlut, stride);
+            lut_build<LUT_BITS, true>(hl, lut);
+            lut_build<DLUT_BITS, false>(hd, dlut);
             for (;;) {
                 bits_refill(b);
-                int sym = huff_decode<LUT_BITS>(b, hl, lut, stride);
-                if (sym < 256) {
-                    if (sym < 0) return INF_ERR_CODE;
-                    if (o >= n_out) return INF_ERR_OUTPUT;
-                    out[o++] = (uint8_t)sym;
+                uint32_t e = lut[(uint32_t)b.buf & (uint32_t)(LUT_SIZE - 1)];
+                if (e & LIT_FLAG) {
+                    // literals, up to three per refill (a code in the table has at most LUT_BITS = 10 bits, 33 are there):
+                    // look-up, one flag test, store, shift — the chain a member's decode time is made of
+                    if (n_out - o >= 3u) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            out[o++] = (uint8_t)(e >> 4);
+                            b.buf >>= (e & 15u); b.n -= (int)(e & 15u);
+                            if (r == 2) break;
+                            e = lut[(uint32_t)b.buf & (uint32_t)(LUT_SIZE - 1)];
+                            if (!(e & LIT_FLAG)) break;
+                        }
+                    } else {
+                        if (o >= n_out) return INF_ERR_OUTPUT;
+                        out[o++] = (uint8_t)(e >> 4);
+                        b.buf >>= (e & 15u); b.n -= (int)(e & 15u);
+                    }
                     continue;
+                }
+                int sym;
+                if (e) { b.buf >>= (e & 15u); b.n -= (int)(e & 15u); sym = (int)(e >> 4); }
+                else {
+                    sym = huff_decode_slow(b, hl);
+                    if (sym < 0) return INF_ERR_CODE;
+                    if (sym < 256) {
+                        if (o >= n_out) return INF_ERR_OUTPUT;
+                        out[o++] = (uint8_t)sym;
+                        continue;
+                    }
                 }
                 if (sym == 256) break;
                 if (sym > 285) return INF_ERR_CODE;
@@ -257,20 +286,20 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 if (sym < 265) len = sym - 254;
                 else if (sym == 285) len = 258;
                 else {
-                    const int e = (sym - 261) >> 2;
-                    len = ((4 | ((sym - 265) & 3)) << e) + 3 + (int)bits_take(b, e);
+                    const int x = (sym - 261) >> 2;
+                    len = ((4 | ((sym - 265) & 3)) << x) + 3 + (int)bits_take(b, x);
                 }
                 bits_refill(b);
-                const int ds = huff_decode<DLUT_BITS>(b, hd, dlut, stride);
+                const int ds = huff_decode<DLUT_BITS>(b, hd, dlut);
                 if (ds < 0 || ds > 29) return INF_ERR_DIST;
-                int64_t dist;
-                if (ds < 4) dist = ds + 1;
+                uint32_t dist;
+                if (ds < 4) dist = (uint32_t)ds + 1u;
                 else {
-                    const int e = (ds >> 1) - 1;
-                    dist = ((int64_t)(2 | (ds & 1)) << e) + 1 + (int64_t)bits_take(b, e);
+                    const int x = (ds >> 1) - 1;
+                    dist = ((uint32_t)(2 | (ds & 1)) << x) + 1u + bits_take(b, x);
                 }
                 if (dist > o) return INF_ERR_DIST;
-                if (o + len > n_out) return INF_ERR_OUTPUT;
+                if ((uint32_t)len > n_out - o) return INF_ERR_OUTPUT;
                 // the copy.  Byte by byte, every byte waits for its own load to come back (the store needs the value, the
                 // next load may alias the store): a round trip to L2 per byte.  So: a run (distance 1) loads once; a source
                 // at least 8 bytes back is fetched 8 bytes at a time, loads first, stores after; only short overlapping
@@ -280,14 +309,36 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                     for (int i = 0; i < len; ++i) out[o + i] = v;
                     o += len;
                 } else if (dist >= 8) {
-                    while (len > 0) {
-                        const int n8 = len < 8 ? len : 8;
-                        uint8_t t[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) if (j < n8) t[j] = out[o - dist + j];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) if (j < n8) out[o + j] = t[j];
-                        o += n8; len -= n8;
+                    // (exactly n loads, then n stores: two jumps into unrolled runs — a predicated run of 8 + 8 cost 45
+                    // instructions per match whatever its length, and the typical match is 3-6 bytes)
+                    const uint8_t* src = out + o - dist;
+                    uint8_t* dst = out + o;
+                    o += (uint32_t)len;
+                    while (len >= 8) {
+                        const uint8_t t0 = src[0], t1 = src[1], t2 = src[2], t3 = src[3], t4 = src[4], t5 = src[5], t6 = src[6], t7 = src[7];
+                        dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = t3; dst[4] = t4; dst[5] = t5; dst[6] = t6; dst[7] = t7;
+                        src += 8; dst += 8; len -= 8;
+                    }
+                    uint8_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+                    switch (len) {
+                        case 7: t6 = src[6];  // fall through
+                        case 6: t5 = src[5];  // fall through
+                        case 5: t4 = src[4];  // fall through
+                        case 4: t3 = src[3];  // fall through
+                        case 3: t2 = src[2];  // fall through
+                        case 2: t1 = src[1];  // fall through
+                        case 1: t0 = src[0];  // fall through
+                        default: break;
+                    }
+                    switch (len) {
+                        case 7: dst[6] = t6;  // fall through
+                        case 6: dst[5] = t5;  // fall through
+                        case 5: dst[4] = t4;  // fall through
+                        case 4: dst[3] = t3;  // fall through
+                        case 3: dst[2] = t2;  // fall through
+                        case 2: dst[1] = t1;  // fall through
+                        case 1: dst[0] = t0;  // fall through
+                        default: break;
                     }
                 } else {
                     for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dist];

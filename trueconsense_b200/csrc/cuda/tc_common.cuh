@@ -54,12 +54,10 @@ struct tc_ctx {
     cudaStream_t cap_stream;    // the stream sample graphs are captured on (a user's legacy default stream cannot be captured)
     int in_capture;         // timing events inside a capture are recorded as external event nodes
     float finished_ms;      // timing on: pileup-kernel duration of the sample tc_sample_finish returned last (< 0: none)
-    // tc_pileup_counts_allreduce: the shard's chain (pileup -> status flag -> ncclAllReduce -> status read-back) as one graph
-    cudaGraphExec_t rr_exec;
-    unsigned char rr_key[256];
-    int rr_key_len, rr_seen;
-    int64_t rr_launches, rr_d2h;
-    tc_pileup_pending rr_pend;
+    // tc_pileup_counts_allreduce_enqueue / _finish: two shard passes in flight (allreduce.cu), each slot with its own graph
+    struct tc_rr_slot* rr; int rr_next;
+    // staging ring for large uploads from pageable memory (tc_stage_in): TC_RING_SLOTS pinned buffers of TC_RING_CHUNK bytes
+    void* ring; cudaEvent_t ring_ev[8];
 };
 
 // device-side status block written by kernels, read back once per call

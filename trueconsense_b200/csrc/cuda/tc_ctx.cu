@@ -2,10 +2,13 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <thread>
+
 #include "tc_common.cuh"
 
 static char g_create_err[512] = "";
 void tc_sample_slots_free(tc_ctx* ctx);     // sample.cu
+void tc_rr_slots_free(tc_ctx* ctx);         // allreduce.cu
 
 int tc_fail(tc_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_create_err;
@@ -47,6 +50,53 @@ bool tc_is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Large uploads from PAGEABLE host memory (numpy arrays, a mapped BAM file).  cudaMemcpyAsync stages such a copy through
+// the driver's own pinned buffer on the calling thread: ~11 GB/s measured for a 92 MB file, a fifth of the link.  Here the
+// source is cut into 8 MB chunks; four host threads copy a wave of four chunks into pinned ring slots while the previous
+// wave's slots are on their way over PCIe (two sets of four slots), so the link sees pinned memory only and the host copy
+// runs at several cores' memory bandwidth.  Returns when every chunk has been ENQUEUED: the source may be released then,
+// exactly as with the plain call.
+constexpr size_t TC_RING_CHUNK = 8u << 20;
+constexpr int TC_RING_SLOTS = 8;
+constexpr size_t TC_RING_MIN = 24u << 20;
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_pageable(tc_ctx* ctx, void* d, const void* p, size_t bytes, cudaStream_t s) {
+    if (!ctx->ring) {
+        TC_CUDA(cudaMallocHost(&ctx->ring, TC_RING_CHUNK * TC_RING_SLOTS));
+        for (int i = 0; i < TC_RING_SLOTS; ++i) TC_CUDA(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+    }
+    const size_t n_chunks = (bytes + TC_RING_CHUNK - 1) / TC_RING_CHUNK;
+    const int wave = TC_RING_SLOTS / 2;
+    for (size_t c0 = 0, w = 0; c0 < n_chunks; c0 += wave, ++w) {
+        const int n = (int)((n_chunks - c0) < (size_t)wave ? (n_chunks - c0) : (size_t)wave);
+        const int base = (int)(w & 1) * wave;
+        std::thread th[TC_RING_SLOTS / 2];
+        for (int k = 0; k < n; ++k) {
+            TC_CUDA(cudaEventSynchronize(ctx->ring_ev[base + k]));          // the copy that used this slot two waves ago
+            const size_t off = (c0 + k) * TC_RING_CHUNK;
+            const size_t len = bytes - off < TC_RING_CHUNK ? bytes - off : TC_RING_CHUNK;
+            char* slot = (char*)ctx->ring + (size_t)(base + k) * TC_RING_CHUNK;
+            const char* src = (const char*)p + off;
+            if (k + 1 < n) th[k] = std::thread([=] { memcpy(slot, src, len); });
+            else memcpy(slot, src, len);                                     // the calling thread takes the last one
+        }
+        for (int k = 0; k + 1 < n; ++k) th[k].join();
+        for (int k = 0; k < n; ++k) {
+            const size_t off = (c0 + k) * TC_RING_CHUNK;
+            const size_t len = bytes - off < TC_RING_CHUNK ? bytes - off : TC_RING_CHUNK;
+            TC_CUDA(cudaMemcpyAsync((char*)d + off, (char*)ctx->ring + (size_t)(base + k) * TC_RING_CHUNK, len, cudaMemcpyHostToDevice, s));
+            TC_CUDA(cudaEventRecord(ctx->ring_ev[base + k], s));
+        }
+    }
+    return TC_OK;
+}
+
 const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cudaStream_t s, int* rc) {
     *rc = TC_OK;
     if (!p) return NULL;
@@ -54,8 +104,13 @@ const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cuda
     void* d = tc_dev_buf(ctx, slot, bytes);
     if (!d) { *rc = TC_ERR_NOMEM; return NULL; }
     if (bytes) {
-        cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { *rc = tc_cuda_fail(ctx, e, "cudaMemcpyAsync H2D"); return NULL; }
+        if (bytes >= TC_RING_MIN && is_pageable(p)) {
+            *rc = stage_pageable(ctx, d, p, bytes, s);
+            if (*rc) return NULL;
+        } else {
+            cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { *rc = tc_cuda_fail(ctx, e, "cudaMemcpyAsync H2D"); return NULL; }
+        }
         ctx->h2d_bytes += (int64_t)bytes;
     }
     return d;
@@ -177,7 +232,8 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < SLOT_COUNT; ++i)
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
-    if (ctx->rr_exec) cudaGraphExecDestroy(ctx->rr_exec);
+    tc_rr_slots_free(ctx);
+    if (ctx->ring) { cudaFreeHost(ctx->ring); for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ring_ev[i]); }
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }

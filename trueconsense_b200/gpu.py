@@ -111,6 +111,10 @@ def lib() -> C.CDLL:
             l.tc_allreduce_counts.argtypes = [vp, vp, i64, vp, vp]
             l.tc_pileup_counts_allreduce.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), vp, vp, vp]
             l.tc_pileup_counts_allreduce.restype = C.c_int
+            l.tc_pileup_counts_allreduce_enqueue.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), vp, vp, vp, C.POINTER(i32)]
+            l.tc_pileup_counts_allreduce_enqueue.restype = C.c_int
+            l.tc_pileup_counts_allreduce_finish.argtypes = [vp, i32]
+            l.tc_pileup_counts_allreduce_finish.restype = C.c_int
             l.tc_pileup_call_inserts.argtypes = [vp, C.POINTER(TcReads), i32, C.POINTER(PileupParams), C.POINTER(CallParams),
                                                  C.POINTER(PileupParams), vp, C.POINTER(CallTable), C.POINTER(InsertCall), i32,
                                                  C.POINTER(i32), vp, i64, vp]
@@ -343,6 +347,23 @@ class Context:
         rs = self._reads_struct(reads)
         self._check(self._lib.tc_pileup_counts_allreduce(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), comm.handle, stream))
         return out
+
+    def pileup_counts_allreduce_enqueue(self, reads, ref_len: int, params: PileupParams, out, comm, stream: int = 0) -> int:
+        """First half of ``pileup_counts_allreduce``: returns a ticket as soon as the pass is enqueued.  Two passes may be in
+        flight (each with its own ``out``); ``reads`` / ``out`` stay untouched until ``pileup_counts_allreduce_finish``."""
+        rs = self._reads_struct(reads)
+        t = C.c_int32(-1)
+        self._check(self._lib.tc_pileup_counts_allreduce_enqueue(self._h, C.byref(rs), int(ref_len), C.byref(params), _ptr(out), comm.handle,
+                                                                 stream, C.byref(t)))
+        self._rr_keep = getattr(self, "_rr_keep", {})
+        self._rr_keep[t.value] = (reads, out, params, rs)
+        return int(t.value)
+
+    def pileup_counts_allreduce_finish(self, ticket: int) -> None:
+        try:
+            self._check(self._lib.tc_pileup_counts_allreduce_finish(self._h, int(ticket)))
+        finally:
+            getattr(self, "_rr_keep", {}).pop(ticket, None)
 
     # ------------------------------------------------------------------ (3) depth
     def depth(self, reads, ref_len: int, params: PileupParams | None = None, out=None, stream: int = 0):
