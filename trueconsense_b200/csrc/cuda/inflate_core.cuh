@@ -303,42 +303,35 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 // the copy.  Byte by byte, every byte waits for its own load to come back (the store needs the value, the
                 // next load may alias the store): a round trip to L2 per byte.  So: a run (distance 1) loads once; a source
                 // at least 8 bytes back is fetched 8 bytes at a time, loads first, stores after; only short overlapping
-                // periods go byte by byte.
+                // periods go byte by byte.  (Measured: 8 + 8 predicated by the length = 45 instructions per match; jumps into
+                // unrolled runs of exactly `len` = fewer instructions and MORE time, the indirect branches stall.)
                 if (dist == 1) {
                     const uint8_t v = out[o - 1];
                     for (int i = 0; i < len; ++i) out[o + i] = v;
                     o += len;
                 } else if (dist >= 8) {
-                    // (exactly n loads, then n stores: two jumps into unrolled runs — a predicated run of 8 + 8 cost 45
-                    // instructions per match whatever its length, and the typical match is 3-6 bytes)
                     const uint8_t* src = out + o - dist;
                     uint8_t* dst = out + o;
-                    o += (uint32_t)len;
-                    while (len >= 8) {
-                        const uint8_t t0 = src[0], t1 = src[1], t2 = src[2], t3 = src[3], t4 = src[4], t5 = src[5], t6 = src[6], t7 = src[7];
-                        dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = t3; dst[4] = t4; dst[5] = t5; dst[6] = t6; dst[7] = t7;
-                        src += 8; dst += 8; len -= 8;
-                    }
-                    uint8_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
-                    switch (len) {
-                        case 7: t6 = src[6];  // fall through
-                        case 6: t5 = src[5];  // fall through
-                        case 5: t4 = src[4];  // fall through
-                        case 4: t3 = src[3];  // fall through
-                        case 3: t2 = src[2];  // fall through
-                        case 2: t1 = src[1];  // fall through
-                        case 1: t0 = src[0];  // fall through
-                        default: break;
-                    }
-                    switch (len) {
-                        case 7: dst[6] = t6;  // fall through
-                        case 6: dst[5] = t5;  // fall through
-                        case 5: dst[4] = t4;  // fall through
-                        case 4: dst[3] = t3;  // fall through
-                        case 3: dst[2] = t2;  // fall through
-                        case 2: dst[1] = t1;  // fall through
-                        case 1: dst[0] = t0;  // fall through
-                        default: break;
+                    if (n_out - o >= (uint32_t)len + 7u) {
+                        // whole groups of 8, no predicates: the bytes a group writes beyond the match's end are overwritten by
+                        // what the stream produces next (the output only grows, and the member must end exactly at n_out)
+                        o += (uint32_t)len;
+                        for (int done = 0; done < len; done += 8, src += 8, dst += 8) {
+                            const uint8_t t0 = src[0], t1 = src[1], t2 = src[2], t3 = src[3], t4 = src[4], t5 = src[5], t6 = src[6], t7 = src[7];
+                            dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = t3; dst[4] = t4; dst[5] = t5; dst[6] = t6; dst[7] = t7;
+                        }
+                    } else {
+                        // the last bytes of the member: exactly `len`
+                        o += (uint32_t)len;
+                        while (len > 0) {
+                            const int n8 = len < 8 ? len : 8;
+                            uint8_t t[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (j < n8) t[j] = src[j];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (j < n8) dst[j] = t[j];
+                            src += n8; dst += n8; len -= n8;
+                        }
                     }
                 } else {
                     for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dist];
