@@ -464,6 +464,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gpu.Context(local)
+    if args.read_range_only:        # diagnostics: the read-range block alone (not a bench line)
+        rr = read_range_block(ctx, gpu, torch, dist, rank, world, local, args.steps, args.warmup, args.deep_scale, peaks()[0])
+        if rank == 0:
+            print(json.dumps({"read_range": rr}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     w, batch = make_sample(args.scale, rank)
     L = len(w.ref)
     bases = batch.count_aligned_bases(0x4)
@@ -676,6 +683,7 @@ def main():
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed passes before the warm-up steps (clock / driver spin-up of a cold GPU)")
     ap.add_argument("--deep-scale", type=float, default=1.0, help="fraction of configs[3]'s 50 M reads in the read-range block (1.0: the whole sample, 4.8 GB of read arrays on one GPU)")
     ap.add_argument("--no-read-range", action="store_true", help="skip the read-range sharded block (configs[3])")
+    ap.add_argument("--read-range-only", action="store_true", help="diagnostics: only the read-range block, printed on its own")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (N = 1 only)")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="samples travelling at a time in the end-to-end loop (1 or 2)")
     ap.add_argument("--h2d-ceiling", action="store_true", help="also measure the concurrent pinned H2D ceiling at N = 1")
