@@ -475,7 +475,9 @@ def run_ours(args):
     L = len(w.ref)
     bases = batch.count_aligned_bases(0x4)
     alg_bytes = batch.algorithmic_bytes(L)
-    pinned = batch.with_cigar16().pin()       # (16-bit CIGAR transport when every operation is shorter than 4096)
+    # the host batch in its compact transport forms: 16-bit CIGARs (when every operation is shorter than 4096), two bits per base
+    # plus the words that hold anything else than A C G T (what a decoder emits next to the 4-bit words: tc_seq2_pack)
+    pinned = batch.with_cigar16().with_seq2().pin()
     stream = torch.cuda.current_stream().cuda_stream
 
     counts_dev = torch.empty((gpu.TC_NROWS, L), dtype=torch.int32, device="cuda")

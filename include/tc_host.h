@@ -94,6 +94,14 @@ void tc_bgzf_unmap(tc_bgzf_map_t* m);
 int  tc_bam_write(const char* path, const tc_hostreads_t* reads, const char* ref_name,
                   int32_t ref_len, int level, char* err, int errlen);
 
+/* ---- compact transport forms (trueconsense_b200.h: tc_reads_t.seq2) ----
+ * seq2[w] = the 8 bases of seq4[w] at two bits each (A C G T = 0 1 2 3, base j in bits 2j+1:2j); *exc_idx / *exc_val (malloc'd,
+ * release with tc_host_free; NULL when there are none) list, ascending, the words that hold anything else over their valid
+ * bases.  Words of seq2 that are on the list are unspecified.  0 on success. */
+int  tc_seq2_pack(const uint32_t* seq4, int64_t n_seq_words, const uint32_t* seq_off, const int32_t* l_seq, int64_t n_reads,
+                  uint16_t* seq2, uint32_t** exc_idx, uint32_t** exc_val, int64_t* n_exc, int n_threads);
+void tc_host_free(void* p);
+
 /* ---- synthetic reads ---- */
 enum { TC_VAR_SUB = 0, TC_VAR_INS = 1, TC_VAR_DEL = 2 };
 

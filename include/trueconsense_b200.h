@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TC_ABI_VERSION 2
+#define TC_ABI_VERSION 3
 
 /* ---- error codes (0 = success, negative = failure) ---- */
 #define TC_OK              0
@@ -95,6 +95,16 @@ typedef struct tc_reads {
      * both arrays sit in host memory the library copies this one — half the bytes over PCIe — and widens it on the device.
      * `cigar` may be NULL when this is given. */
     const uint16_t* cigar16;
+    /* optional compact transport of SEQ: two bits per base (A C G T = 0 1 2 3), one 16-bit entry per seq4 word with the same
+     * offsets — entry w holds the 8 bases of seq4[w], base j of the word in bits 2j+1:2j — plus the list of the words that hold
+     * anything else than A / C / G / T over their valid bases (N, IUPAC codes, '='): seq_exc_idx (ascending word indices) and
+     * seq_exc_val (those seq4 words as they are).  A decoder has both forms for free (tc_host.h: tc_seq2_pack).  When SEQ sits
+     * in host memory the library copies seq2 and the exceptions — half the bytes — and rebuilds seq4 on the device, zero padding
+     * included.  `seq4` may be NULL when this is given. */
+    const uint16_t* seq2;
+    const uint32_t* seq_exc_idx;
+    const uint32_t* seq_exc_val;
+    int64_t         n_seq_exc;
 } tc_reads_t;
 
 /* ---- pileup filters: the arguments of pysam's AlignmentFile.pileup() that the

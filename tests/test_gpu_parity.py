@@ -720,6 +720,44 @@ def test_compact_cigar_transport(ctx, orc):
     assert long_op.with_cigar16() is long_op
 
 
+def test_compact_seq_transport(ctx, orc):
+    """tc_reads_t.seq2: SEQ travels at two bits per base plus the list of words that hold anything else than A C G T, and seq4
+    is rebuilt on the device bit for bit (N / IUPAC / '=' codes, zero padding of every read's last word, reads without SEQ);
+    same tables and insertion calls; half the SEQ bytes over the link."""
+    from trueconsense_b200.reads import ReadBatch
+
+    pileup, _ = orc
+    for case in ("amplicon_deep", "shotgun_indels", "paired", "tiny", "one_read"):
+        ref, _, b = _synth(case)
+        L = len(ref)
+        c = b.with_seq2(max_exception_fraction=1.0).with_cigar16()     # (shotgun_indels: N and IUPAC codes in a fifth of the words)
+        assert c.seq2 is not None and c.seq2.dtype == np.uint16 and c.seq2.shape == b.seq4.shape
+        dev = ctx.upload(c)
+        assert np.array_equal(ctx.download(dev.struct.seq4, b.seq4.size, np.uint32), b.seq4), case
+        exp = pileup.pileup_counts(b, L, threads=4)
+        assert np.array_equal(ctx.pileup_counts(dev, L), exp)
+        x0 = ctx.transfer_bytes()[0]
+        assert np.array_equal(ctx.pileup_counts(b.with_seq2(max_exception_fraction=1.0), L), exp)
+        x1 = ctx.transfer_bytes()[0]
+        assert np.array_equal(ctx.pileup_counts(b, L), exp)
+        x2 = ctx.transfer_bytes()[0]
+        assert (x2 - x1) - (x1 - x0) == 2 * b.seq4.size - 8 * c.seq_exc_idx.size
+        cands = ctx.list_insert_candidates(ctx.call(exp, L, 10, True).flags, L)
+        if len(cands):
+            assert ctx.extract_inserts(c, L, cands) == ctx.extract_inserts(b, L, cands)
+            assert ctx.extract_inserts(ctx.upload(c), L, cands) == ctx.extract_inserts(b, L, cands)
+    # every code, odd lengths, a read without SEQ, '=' bases
+    recs = [dict(pos=3, cigar="16M", seq="=ACMGRSVTWYHKDBN"), dict(pos=4, cigar="5M", seq="ACGTN"), dict(pos=5, cigar="9M", seq="ACGTACGTA"),
+            dict(pos=6, cigar="7M", seq="*"), dict(pos=7, cigar="1M", seq="T"), dict(pos=8, cigar="8M", seq="GGGGGGGG"),
+            dict(pos=9, cigar="17M", seq="ACGTACGTACGTACGT=")]
+    odd = ReadBatch.from_records(recs)
+    c = odd.with_seq2(max_exception_fraction=1.0)
+    assert c.seq2 is not None and c.seq_exc_idx.size >= 3
+    assert np.array_equal(ctx.download(ctx.upload(c).struct.seq4, odd.seq4.size, np.uint32), odd.seq4)
+    assert np.array_equal(ctx.pileup_counts(c, 40), pileup.pileup_counts(odd, 40))
+    assert odd.with_seq2(max_exception_fraction=0.01) is odd          # too many exceptions: the 4-bit words travel
+
+
 # ---------------------------------------------------------------------------- multi-GPU pieces on one device
 def test_read_range_sharding_single_rank_and_emulated_ranks(ctx, orc):
     """tc_allreduce_counts through a real NCCL communicator (one rank: identity), and the per-rank slices of

@@ -29,7 +29,7 @@ def test_cuda_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/trueconsense_b200.h but not exported"
     lib.tc_abi_version.restype = ctypes.c_int
-    assert lib.tc_abi_version() == 2
+    assert lib.tc_abi_version() == 3
 
 
 def test_cuda_library_is_sm100a_only():
@@ -403,3 +403,35 @@ def test_clock_sampler_reports_only_samples_inside_the_timed_windows():
     r = s.stop()
     assert r["samples"] == 2 and r["sm_mhz"] == pytest.approx(1957.5) and r["sm_max_mhz"] == 1965.0
     assert r["reasons"] == ["sw_power_cap"]
+
+
+def test_seq2_pack_reconstructs_seq4(host_libs):
+    """tc_seq2_pack (compact SEQ transport): expanding the 2-bit codes and patching the exception words gives seq4 back bit for
+    bit — valid bases, zero padding, every non-ACGT code."""
+    from trueconsense_b200 import synth
+    from trueconsense_b200.reads import ReadBatch
+
+    def rebuild(c, b):
+        h = c.seq2.astype(np.uint32)
+        v = np.zeros_like(b.seq4)
+        nw = np.diff(b.seq_off.astype(np.int64))
+        widx = np.arange(b.seq4.shape[0])
+        rid = np.repeat(np.arange(b.n_reads), nw)
+        valid = b.l_seq[rid] - 8 * (widx - b.seq_off[rid].astype(np.int64))
+        for j in range(8):
+            nib = (1 << ((h >> (2 * j)) & 3)).astype(np.uint32)
+            v |= np.where(j < valid, nib << (8 * (j >> 1) + (0 if j & 1 else 4)), 0).astype(np.uint32)
+        v[c.seq_exc_idx] = c.seq_exc_val
+        return v
+
+    w = synth.config(0, scale=0.05)
+    b = synth.generate_reads(w.params, w.ref)
+    c = b.with_seq2()
+    assert c is not b and c.seq2.shape == b.seq4.shape and np.all(np.diff(c.seq_exc_idx.astype(np.int64)) > 0)
+    assert np.array_equal(rebuild(c, b), b.seq4)
+    odd = ReadBatch.from_records([dict(pos=3, cigar="16M", seq="=ACMGRSVTWYHKDBN"), dict(pos=4, cigar="5M", seq="ACGTN"),
+                                  dict(pos=6, cigar="7M", seq="*"), dict(pos=7, cigar="1M", seq="T"), dict(pos=9, cigar="9M", seq="ACGTACGTA")])
+    c = odd.with_seq2(max_exception_fraction=1.0)
+    assert np.array_equal(rebuild(c, odd), odd.seq4)
+    assert c.c_struct().n_seq_exc == c.seq_exc_idx.size > 0
+    assert odd.with_seq2(max_exception_fraction=0.0) is odd

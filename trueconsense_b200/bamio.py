@@ -213,6 +213,11 @@ def host_lib() -> C.CDLL:
         lib.tc_bgzf_map.restype = C.c_int
         lib.tc_bgzf_unmap.argtypes = [C.POINTER(TcBgzfMap)]
         lib.tc_bgzf_unmap.restype = None
+        lib.tc_seq2_pack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64), C.c_int]
+        lib.tc_seq2_pack.restype = C.c_int
+        lib.tc_host_free.argtypes = [C.c_void_p]
+        lib.tc_host_free.restype = None
         _lib = lib
     return _lib
 

@@ -17,7 +17,7 @@ enum tc_slot {
     SLOT_QHASH, SLOT_MPOS, SLOT_ISIZE,
     SLOT_COUNTS, SLOT_DIFF, SLOT_STATUS, SLOT_SPAN_END, SLOT_CALL_A, SLOT_CALL_B, SLOT_CALL_C, SLOT_CALL_D,
     SLOT_CALL_E, SLOT_CALL_F, SLOT_INS_A, SLOT_INS_B, SLOT_INS_C, SLOT_INS_D, SLOT_INS_E, SLOT_INS_F, SLOT_INS_G,
-    SLOT_TMP_A, SLOT_TMP_B, SLOT_TMP_C, SLOT_TILES, SLOT_SEGS, SLOT_COV_TOTALS, SLOT_BAM_PAYLOAD, SLOT_BAM_REC, SLOT_CIGAR16, SLOT_BGZF_FILE, SLOT_BGZF_BLOCKS, SLOT_COUNT
+    SLOT_TMP_A, SLOT_TMP_B, SLOT_TMP_C, SLOT_TILES, SLOT_SEGS, SLOT_COV_TOTALS, SLOT_BAM_PAYLOAD, SLOT_BAM_REC, SLOT_CIGAR16, SLOT_SEQ2, SLOT_SEQ_EXC_IDX, SLOT_SEQ_EXC_VAL, SLOT_BGZF_FILE, SLOT_BGZF_BLOCKS, SLOT_COUNT
 };
 
 struct tc_buf { void* p; size_t cap; };

@@ -128,6 +128,32 @@ __global__ void widen_cigar_kernel(const uint16_t* __restrict__ in, uint32_t* __
     if (blockIdx.x == 0 && threadIdx.x < (int)(n - 8 * n8)) out[8 * n8 + threadIdx.x] = in[8 * n8 + threadIdx.x];
 }
 
+// 2-bit SEQ transport -> the 4-bit one-hot words the kernels read.  One warp per read (it needs the read's length for the zero
+// padding of its last word); base j of a word sits in nibble (j even: high, odd: low) of byte j / 2, as in BAM.
+__global__ void __launch_bounds__(256) widen_seq_kernel(const uint16_t* __restrict__ seq2, const uint32_t* __restrict__ seq_off,
+                                                        const int32_t* __restrict__ l_seq, int64_t n_reads, uint32_t* __restrict__ seq4) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t w0 = seq_off[r], w1 = seq_off[r + 1];
+        const int len = l_seq[r];
+        for (uint32_t w = w0 + lane; w < w1; w += 32) {
+            const uint32_t h = seq2[w];
+            const int valid = len - 8 * (int)(w - w0);          // bases of this word that exist (>= 8: all)
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t nib = 1u << ((h >> (2 * j)) & 3u);
+                if (j < valid) v |= nib << (8 * (j >> 1) + ((j & 1) ? 0 : 4));
+            }
+            seq4[w] = v;
+        }
+    }
+}
+__global__ void patch_seq_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val, int64_t n, uint32_t* __restrict__ seq4) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) seq4[idx[k]] = val[k];
+}
+
 int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, cudaStream_t s) {
     if (!in) return tc_fail(ctx, TC_ERR_ARG, "reads is NULL");
     if (in->n_reads < 0 || in->n_seq_words < 0 || in->n_cigar_ops < 0) return tc_fail(ctx, TC_ERR_ARG, "negative sizes in tc_reads_t");
@@ -137,7 +163,7 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
     out->n = n;
     if (n == 0) return TC_OK;
     if (!in->pos || !in->flag || !in->l_seq || !in->seq_off || !in->cigar_off || (!in->cigar && !in->cigar16 && in->n_cigar_ops) ||
-        (!in->seq4 && in->n_seq_words))
+        (!in->seq4 && !in->seq2 && in->n_seq_words))
         return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: a required array is NULL");
     int rc;
 #define STAGE(field, slot, type, count)                                                              \
@@ -153,7 +179,28 @@ int tc_resolve_reads(tc_ctx* ctx, const tc_reads_t* in, dreads* out, int need, c
         out->field = (const type*)tc_dev_buf(ctx, slot, sizeof(type) * (size_t)(count));                \
         if (!out->field) return TC_ERR_NOMEM;                                                           \
     } else { STAGE(field, slot, type, count) }
-    STAGE_OR_DEFER(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words, DEFER_SEQ)
+    if (in->seq2 && in->n_seq_words && !tc_is_device_ptr(in->seq2) && (!in->seq4 || !tc_is_device_ptr(in->seq4)) &&
+        !((need & DEFER_SEQ) && in->seq4)) {
+        // compact transport: 2 bits per base over the link (+ the words that hold something else), widened behind it
+        if (in->n_seq_exc < 0 || (in->n_seq_exc > 0 && (!in->seq_exc_idx || !in->seq_exc_val)))
+            return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: seq2 without its exception list");
+        const uint16_t* s2 = (const uint16_t*)tc_stage_in(ctx, SLOT_SEQ2, in->seq2, sizeof(uint16_t) * (size_t)in->n_seq_words, s, &rc);
+        if (rc) return rc;
+        const uint32_t* ei = (const uint32_t*)tc_stage_in(ctx, SLOT_SEQ_EXC_IDX, in->seq_exc_idx, 4 * (size_t)in->n_seq_exc, s, &rc); if (rc) return rc;
+        const uint32_t* ev = (const uint32_t*)tc_stage_in(ctx, SLOT_SEQ_EXC_VAL, in->seq_exc_val, 4 * (size_t)in->n_seq_exc, s, &rc); if (rc) return rc;
+        uint32_t* s4 = (uint32_t*)tc_dev_buf(ctx, SLOT_SEQ4, sizeof(uint32_t) * (size_t)in->n_seq_words);
+        if (!s4) return TC_ERR_NOMEM;
+        widen_seq_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(s2, out->seq_off, out->l_seq, n, s4);
+        TC_LAUNCH_CHECK();
+        if (in->n_seq_exc > 0) {
+            patch_seq_kernel<<<(unsigned)((in->n_seq_exc + 255) / 256), 256, 0, s>>>(ei, ev, in->n_seq_exc, s4);
+            TC_LAUNCH_CHECK();
+        }
+        out->seq4 = s4;
+    } else {
+        if (!in->seq4 && in->n_seq_words) return tc_fail(ctx, TC_ERR_ARG, "tc_reads_t: seq4 is NULL and seq2 is not a host array");
+        STAGE_OR_DEFER(seq4, SLOT_SEQ4, uint32_t, in->n_seq_words, DEFER_SEQ)
+    }
     if (in->cigar16 && in->n_cigar_ops && !tc_is_device_ptr(in->cigar16) && (!in->cigar || !tc_is_device_ptr(in->cigar)) &&
         !((need & DEFER_CIGAR) && in->cigar)) {
         // compact transport: 2 bytes per operation over the link, widened behind it
@@ -286,6 +333,7 @@ TC_API int tc_reads_upload(tc_ctx_t* ctx, const tc_reads_t* host, tc_reads_t* de
     dev->cigar_off = d.cigar_off; dev->seq4 = d.seq4; dev->qual = d.qual; dev->cigar = d.cigar;
     dev->qname_hash = d.qname_hash; dev->mpos = d.mpos; dev->isize = d.isize;
     dev->cigar16 = nullptr;
+    dev->seq2 = nullptr; dev->seq_exc_idx = nullptr; dev->seq_exc_val = nullptr; dev->n_seq_exc = 0;
     return TC_OK;
 }
 

@@ -41,6 +41,10 @@ class TcReads(C.Structure):
         ("max_ref_span", C.c_int32),
         ("reserved", C.c_int32),
         ("cigar16", C.c_void_p),
+        ("seq2", C.c_void_p),
+        ("seq_exc_idx", C.c_void_p),
+        ("seq_exc_val", C.c_void_p),
+        ("n_seq_exc", C.c_int64),
     ]
 
 
@@ -77,6 +81,9 @@ class ReadBatch:
     info: dict = field(default_factory=dict)
     _owner: Any = None       # keeps backing memory alive
     cigar16: np.ndarray | None = None    # the same operations in 16 bits (tc_reads_t.cigar16), see with_cigar16()
+    seq2: np.ndarray | None = None       # two bits per base, one uint16 per seq4 word (tc_reads_t.seq2), see with_seq2()
+    seq_exc_idx: np.ndarray | None = None    # ... and the words that hold anything else than A C G T
+    seq_exc_val: np.ndarray | None = None
 
     # ------------------------------------------------------------------ basics
     @property
@@ -116,7 +123,43 @@ class ReadBatch:
             setattr(s, name, None if a is None else a.ctypes.data)
         s.max_ref_span = max(int(self.max_ref_span), 0)      # 0 = unknown
         s.cigar16 = None if self.cigar16 is None else self.cigar16.ctypes.data
+        if self.seq2 is not None:
+            s.seq2 = self.seq2.ctypes.data
+            s.n_seq_exc = int(self.seq_exc_idx.shape[0])
+            s.seq_exc_idx = self.seq_exc_idx.ctypes.data if s.n_seq_exc else None
+            s.seq_exc_val = self.seq_exc_val.ctypes.data if s.n_seq_exc else None
         return s
+
+    def with_seq2(self, max_exception_fraction: float = 0.125) -> "ReadBatch":
+        """This batch with the compact SEQ transport attached (``tc_reads_t.seq2``: two bits per base plus the list of words that
+        hold anything else than A C G T — half the SEQ bytes over PCIe); the batch itself when more than
+        ``max_exception_fraction`` of the words would be exceptions."""
+        import copy
+
+        from . import bamio
+
+        if self.seq2 is not None or self.seq4.size == 0:
+            return self
+        lib = bamio.host_lib()
+        seq2 = np.empty(self.seq4.shape[0], dtype=np.uint16)
+        idx, val, n = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_int64(0)
+        seq4 = np.ascontiguousarray(self.seq4)
+        rc = lib.tc_seq2_pack(seq4.ctypes.data, seq4.shape[0], np.ascontiguousarray(self.seq_off).ctypes.data,
+                              np.ascontiguousarray(self.l_seq).ctypes.data, self.n_reads, seq2.ctypes.data, C.byref(idx), C.byref(val),
+                              C.byref(n), 0)
+        if rc != 0:
+            raise ValueError(f"tc_seq2_pack failed ({rc})")
+        try:
+            if n.value > max_exception_fraction * seq4.shape[0]:
+                return self
+            out = copy.copy(self)
+            out.seq2 = seq2
+            out.seq_exc_idx = np.ctypeslib.as_array(idx, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint32)
+            out.seq_exc_val = np.ctypeslib.as_array(val, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint32)
+            return out
+        finally:
+            lib.tc_host_free(idx)
+            lib.tc_host_free(val)
 
     def with_cigar16(self) -> "ReadBatch":
         """This batch with the compact CIGAR transport array attached (``tc_reads_t.cigar16``: half the bytes over PCIe) when
@@ -216,6 +259,7 @@ class ReadBatch:
             info=dict(self.info),
         )
         out.cigar16 = pinned(self.cigar16)
+        out.seq2, out.seq_exc_idx, out.seq_exc_val = pinned(self.seq2), pinned(self.seq_exc_idx), pinned(self.seq_exc_val)
         out._owner = keep
         return out
 
