@@ -435,3 +435,7 @@ def test_seq2_pack_reconstructs_seq4(host_libs):
     assert np.array_equal(rebuild(c, odd), odd.seq4)
     assert c.c_struct().n_seq_exc == c.seq_exc_idx.size > 0
     assert odd.with_seq2(max_exception_fraction=0.0) is odd
+    from trueconsense_b200 import bamio
+
+    g = bamio.read_bam(f"{GOLD}/mini_ont.bam", compact=True)
+    assert g.seq2 is not None and g.cigar16 is not None and np.array_equal(rebuild(g, g), g.seq4)

@@ -279,15 +279,17 @@ def batch_from_hostreads(hr: TcHostReads, lib: C.CDLL) -> ReadBatch:
     return b
 
 
-def read_bam(path: str, threads: int = 0) -> ReadBatch:
-    """Decode a BAM into flat arrays (all placed records, file order)."""
+def read_bam(path: str, threads: int = 0, compact: bool = False) -> ReadBatch:
+    """Decode a BAM into flat arrays (all placed records, file order).  ``compact``: also attach the transport forms every
+    later upload of the batch moves instead of the full arrays (16-bit CIGARs, 2-bit SEQ + exception words)."""
     lib = host_lib()
     hr = TcHostReads()
     err = C.create_string_buffer(512)
     rc = lib.tc_bam_read(os.fsencode(path), threads, C.byref(hr), err, len(err))
     if rc != 0:
         raise OSError(f"tc_bam_read({path!r}) failed ({rc}): {err.value.decode(errors='replace')}")
-    return batch_from_hostreads(hr, lib)
+    batch = batch_from_hostreads(hr, lib)
+    return batch.with_cigar16().with_seq2() if compact else batch
 
 
 def read_bam_payload(path: str, threads: int = 0) -> BamPayload:
