@@ -1364,3 +1364,55 @@ def test_bam_file_on_device_rejects_damaged_files(ctx, tmp_path):
     assert "shorter than its fields" in str(ei.value)
     # and the context still works
     _assert_device_reads_equal_host(ctx, ctx.bam_file_to_device(good), bamio.read_bam(good))
+
+
+def test_bam_file_on_device_long_header_and_unplaced_records(ctx, tmp_path):
+    """A header of 6000 references (longer than two 64 KiB chunks of the payload: the chain's anchor is not chunk 0) and
+    unplaced records (refID -1) between and behind the placed ones: same arrays, same counts as the host reader."""
+    import gzip
+    import struct
+
+    from trueconsense_b200 import bamio
+
+    src = f"{GOLD}/mini_illumina.bam"
+    with gzip.open(src, "rb") as fh:
+        payload = fh.read()
+    names, lens, first = bamio.parse_bam_header(payload[:65536], len(payload))
+    refs = [(names[0], lens[0])] + [(f"decoy_{i:05d}_with_a_long_name", 1000 + i) for i in range(6000)]
+    text = b"@HD\tVN:1.6\tSO:coordinate\n"
+    hdr = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, l in refs:
+        nb = n.encode() + b"\0"
+        hdr += struct.pack("<i", len(nb)) + nb + struct.pack("<i", l)
+    assert len(hdr) > 2 * 65536
+    # the records, with an unplaced one (refID -1, pos -1) spliced in after every 50th and three at the end
+    recs, q = [], first
+    while q + 4 <= len(payload):
+        bs = struct.unpack_from("<i", payload, q)[0]
+        recs.append(payload[q:q + 4 + bs])
+        q += 4 + bs
+
+    def unplaced(k):
+        name = b"unplaced%04d\0" % k
+        body = struct.pack("<iiBBHHHIiii", -1, -1, len(name), 0, 4680, 0, 4, 6, -1, -1, 0) + name + bytes([0x12, 0x48, 0x21]) + bytes([30] * 6)
+        return struct.pack("<i", len(body)) + body
+
+    out = []
+    for i, r in enumerate(recs):
+        out.append(r)
+        if i % 50 == 49:
+            out.append(unplaced(i))
+    out += [unplaced(9000 + k) for k in range(3)]
+    body = hdr + b"".join(out)
+    raw = str(tmp_path / "payload.gz")
+    with gzip.open(raw, "wb") as fh:
+        fh.write(body)
+    path = str(tmp_path / "long_header.bam")
+    _rebgzf(raw, path, [65280, 40000, 777])
+    host = bamio.read_bam(path)
+    assert host.n_reads == len(recs) and host.info["n_dropped_unplaced"] == len(out) - len(recs) and len(host.ref_names) == 6001
+    dev = ctx.bam_file_to_device(path)
+    assert dev.ref_names == host.ref_names and dev.ref_lens == host.ref_lens
+    assert dev.info["n_records"] == len(out) and dev.info["n_dropped_unplaced"] == len(out) - len(recs)
+    _assert_device_reads_equal_host(ctx, dev, host)
+    assert bamio.read_bam_header(path) == (host.ref_names, host.ref_lens)
