@@ -54,11 +54,12 @@ constexpr int INFLATE_WARPS = 8;
 
 
 __global__ void __launch_bounds__(32 * INFLATE_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ file, const tc_bgzf_block_t* __restrict__ blk,
-                                                                          long long n_blk, uint8_t* __restrict__ payload, unsigned long long* status) {
+                                                                          long long m0, long long n_blk, uint8_t* __restrict__ payload,
+                                                                          unsigned long long* status) {
     __shared__ __align__(16) uint16_t tables[INFLATE_WARPS][LUT_SIZE + DLUT_SIZE];
     const int w = threadIdx.x >> 5;
-    const long long m = (long long)blockIdx.x * INFLATE_WARPS + w;
-    if (m >= n_blk || (threadIdx.x & 31) != 0) return;
+    const long long m = m0 + (long long)blockIdx.x * INFLATE_WARPS + w;
+    if (m >= m0 + n_blk || (threadIdx.x & 31) != 0) return;
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
     const tc_bgzf_block_t b = blk[m];
@@ -72,14 +73,14 @@ __global__ void __launch_bounds__(32 * INFLATE_WARPS) bgzf_inflate_kernel(const 
 
 constexpr int CRC_ERR = 32;
 
-__global__ void __launch_bounds__(256) bgzf_crc_kernel(const uint8_t* __restrict__ file, const tc_bgzf_block_t* __restrict__ blk, long long n_blk,
-                                                       const uint8_t* __restrict__ payload, unsigned long long* status) {
+__global__ void __launch_bounds__(256) bgzf_crc_kernel(const uint8_t* __restrict__ file, const tc_bgzf_block_t* __restrict__ blk, long long m0,
+                                                       long long n_blk, const uint8_t* __restrict__ payload, unsigned long long* status) {
     __shared__ uint32_t tab[256];
     tab[threadIdx.x] = crc_table_entry(threadIdx.x);
     __syncthreads();
-    const long long m = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const long long m = m0 + (((long long)blockIdx.x * 256 + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (m >= n_blk) return;
+    if (m >= m0 + n_blk) return;
     const tc_bgzf_block_t b = blk[m];
     const uint32_t per = ((uint32_t)b.usize + 31u) / 32u;
     const uint32_t s0 = min(per * lane, (uint32_t)b.usize), s1 = min(s0 + per, (uint32_t)b.usize);
@@ -281,20 +282,56 @@ TC_API int tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_byte
     if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
     // (the bit reader fetches aligned 16-byte vectors: up to 15 bytes in front of a stream — the member's own 18-byte
     // header — and behind it — its CRC, ISIZE and the next header; the buffer is padded behind the file's end)
-    if (!tc_is_device_ptr(file) && !tc_dev_buf(ctx, SLOT_BGZF_FILE, (size_t)file_bytes + 16)) return TC_ERR_NOMEM;
-    const uint8_t* d_file = (const uint8_t*)tc_stage_in(ctx, SLOT_BGZF_FILE, file, (size_t)file_bytes, s, &rc); if (rc) return rc;
     const tc_bgzf_block_t* d_blk = (const tc_bgzf_block_t*)tc_stage_in(ctx, SLOT_BGZF_BLOCKS, blocks, sizeof(tc_bgzf_block_t) * (size_t)n_blocks, s, &rc);
     if (rc) return rc;
     uint8_t* d_payload = (uint8_t*)tc_dev_buf(ctx, SLOT_BAM_PAYLOAD, (size_t)payload_bytes + 64);
     unsigned long long* d_status = (unsigned long long*)tc_dev_buf(ctx, SLOT_STATUS, 64);
     if (!d_payload || !d_status) return TC_ERR_NOMEM;
     TC_CUDA(cudaMemsetAsync(d_status, 0xff, 8, s));
+    const bool file_dev = tc_is_device_ptr(file);
+    uint8_t* d_file = file_dev ? (uint8_t*)file : (uint8_t*)tc_dev_buf(ctx, SLOT_BGZF_FILE, (size_t)file_bytes + 64);
+    if (!d_file) return TC_ERR_NOMEM;
     if (trace) cudaEventRecord(ev[1], s);
-    bgzf_inflate_kernel<<<(unsigned)((n_blocks + INFLATE_WARPS - 1) / INFLATE_WARPS), 32 * INFLATE_WARPS, 0, s>>>(d_file, d_blk, n_blocks, d_payload, d_status);
-    TC_LAUNCH_CHECK();
+    // A large file goes in four groups of members: the host copies group g + 1 into the staging ring while the device inflates
+    // group g, each group's kernels on a side stream of its own behind its upload (a member's decode is a serial chain of ~9 ms
+    // whatever the group's size: kernels queued on one stream would wait for one another; four streams share the SMs).  A small
+    // file is one group: its time is the upload plus that one chain, and nothing overlaps with a chain.
+    constexpr int N_SIDE = 4;
+    if (!ctx->aux[0]) {
+        for (int i = 0; i < N_SIDE; ++i) TC_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        for (int i = 0; i < N_SIDE + 1; ++i) TC_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
+    }
+    const int n_groups = (file_bytes >= (128ll << 20) && n_blocks >= 4 * N_SIDE) ? N_SIDE : 1;
+    const int64_t group_bytes = (file_bytes + n_groups - 1) / n_groups;
+    int64_t sent = 0;               // file bytes [0, sent) are on their way
+    int g = 0;
+    for (int64_t g0 = 0; g0 < n_blocks; ++g) {
+        int64_t g1 = g0 + 1;
+        if (g + 1 >= n_groups) g1 = n_blocks;
+        else while (g1 < n_blocks && blocks[g1].coff + blocks[g1].csize + 8 - sent <= group_bytes) ++g1;
+        // (32 bytes more than the group's last member: the vectors a bit reader fetches behind a stream's end stay inside what was sent)
+        int64_t end = g1 == n_blocks ? file_bytes : blocks[g1 - 1].coff + blocks[g1 - 1].csize + 8 + 32;
+        if (end > file_bytes) end = file_bytes;
+        if (!file_dev && end > sent) {
+            rc = tc_h2d(ctx, d_file + sent, file + sent, (size_t)(end - sent), s);
+            if (rc) return rc;
+            sent = end;
+        }
+        cudaStream_t side = ctx->aux[g % N_SIDE];
+        TC_CUDA(cudaEventRecord(ctx->aux_ev[N_SIDE], s));           // everything up to this group's bytes (and the status block's reset)
+        TC_CUDA(cudaStreamWaitEvent(side, ctx->aux_ev[N_SIDE], 0));
+        const int64_t n = g1 - g0;
+        bgzf_inflate_kernel<<<(unsigned)((n + INFLATE_WARPS - 1) / INFLATE_WARPS), 32 * INFLATE_WARPS, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
+        TC_LAUNCH_CHECK();
+        bgzf_crc_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
+        TC_LAUNCH_CHECK();
+        g0 = g1;
+    }
+    for (int i = 0; i < N_SIDE && i < g; ++i) {                     // the caller's stream continues behind the side streams
+        TC_CUDA(cudaEventRecord(ctx->aux_ev[i], ctx->aux[i]));
+        TC_CUDA(cudaStreamWaitEvent(s, ctx->aux_ev[i], 0));
+    }
     if (trace) cudaEventRecord(ev[2], s);
-    bgzf_crc_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, s>>>(d_file, d_blk, n_blocks, d_payload, d_status);
-    TC_LAUNCH_CHECK();
     unsigned long long* h = (unsigned long long*)ctx->host_status;
     TC_D2H(h, d_status, 8, s);
     if (trace) cudaEventRecord(ev[3], s);
@@ -302,8 +339,8 @@ TC_API int tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_byte
     if (trace) {
         float t01 = 0, t12 = 0, t23 = 0;
         cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
-        fprintf(stderr, "[tc_bgzf_inflate] %lld members, %lld -> %lld bytes: upload %.3f ms, inflate %.3f ms, crc %.3f ms\n", (long long)n_blocks,
-                (long long)file_bytes, (long long)payload_bytes, t01, t12, t23);
+        fprintf(stderr, "[tc_bgzf_inflate] %lld members, %lld -> %lld bytes: member index %.3f ms, upload + inflate + crc (in groups) %.3f ms, read-back %.3f ms\n",
+                (long long)n_blocks, (long long)file_bytes, (long long)payload_bytes, t01, t12, t23);
         for (auto& e : ev) cudaEventDestroy(e);
     }
     if (h[0] != NO_ERROR) {

@@ -58,6 +58,7 @@ struct tc_ctx {
     struct tc_rr_slot* rr; int rr_next;
     // staging ring for large uploads from pageable memory (tc_stage_in): TC_RING_SLOTS pinned buffers of TC_RING_CHUNK bytes
     void* ring; cudaEvent_t ring_ev[8];
+    cudaStream_t aux[4]; cudaEvent_t aux_ev[5];      // tc_bgzf_inflate: groups of members inflate on two side streams behind their upload
 };
 
 // device-side status block written by kernels, read back once per call
@@ -121,6 +122,7 @@ int tc_pileup_enqueue(tc_ctx* ctx, const tc_reads_t* reads, int32_t ref_len, con
                       tc_pileup_pending* pend);
 int tc_pileup_finish(tc_ctx* ctx, const tc_status& st, const tc_pileup_pending* pend, const tc_reads_t* reads, int32_t ref_len,
                      const tc_pileup_params_t* p, int32_t* counts, void* stream);
+int tc_h2d(tc_ctx* ctx, void* d, const void* p, size_t bytes, cudaStream_t s);
 bool tc_reads_all_device(const tc_reads_t* r);     // every array of the batch already in device memory
 int tc_candidates_enqueue(tc_ctx* ctx, const uint8_t* d_flags, int32_t ref_len, int32_t cap, int32_t** d_count, int32_t** d_sorted, cudaStream_t s);
 struct tc_ins_pending { size_t rb_extra, rb_layout, rb_over, rb_calls, rb_fixed; int cap; int64_t n_reads; };

@@ -97,6 +97,19 @@ static int stage_pageable(tc_ctx* ctx, void* d, const void* p, size_t bytes, cud
     return TC_OK;
 }
 
+// host -> device into a caller-chosen place (part of a larger buffer): the ring for large pageable sources, a plain async copy otherwise
+int tc_h2d(tc_ctx* ctx, void* d, const void* p, size_t bytes, cudaStream_t s) {
+    if (!bytes) return TC_OK;
+    if (bytes >= TC_RING_MIN && is_pageable(p)) {
+        const int rc = stage_pageable(ctx, d, p, bytes, s);
+        if (rc) return rc;
+    } else {
+        TC_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+    }
+    ctx->h2d_bytes += (int64_t)bytes;
+    return TC_OK;
+}
+
 const void* tc_stage_in(tc_ctx* ctx, int slot, const void* p, size_t bytes, cudaStream_t s, int* rc) {
     *rc = TC_OK;
     if (!p) return NULL;
@@ -280,6 +293,7 @@ TC_API int tc_ctx_destroy(tc_ctx_t* ctx) {
     for (int i = 0; i < SLOT_COUNT; ++i)
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
     tc_rr_slots_free(ctx);
+    if (ctx->aux[0]) { for (int i = 0; i < 4; ++i) cudaStreamDestroy(ctx->aux[i]); for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->aux_ev[i]); }
     if (ctx->ring) { cudaFreeHost(ctx->ring); for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ring_ev[i]); }
     if (ctx->host_status) cudaFreeHost(ctx->host_status);
     if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
