@@ -13,7 +13,7 @@ extern "C" int h_inflate(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
     (void)stride;
-    const int rc = inflate_block(in, n_in, out, n_out, lut, dlut, hl, hd, lens);
+    const int rc = inflate_block<1>(in, n_in, out, n_out, lut, dlut, hl, hd, lens, 0);
     free(lut); free(dlut);
     return rc;
 }

@@ -6,9 +6,11 @@
 // sample is a gigabyte and more.  Here the host only walks the member headers (csrc/host/bamio.c tc_bgzf_map: one header
 // per member) and ships the file's bytes as they are — fewer than the payload — and the device does the rest:
 //
-//   bgzf_inflate_kernel   one member per warp, decoded by one lane (Huffman decoding is a serial walk of a bit stream; the
-//                         members are independent): inflate_core.cuh's decoder, first-level tables in shared memory.
-//                         Thousands of members in flight; latency-bound per member, throughput comes from their number.
+//   bgzf_inflate_kernel   one member per warp (Huffman decoding is a serial walk of a bit stream; the members are independent):
+//                         inflate_core.cuh's decoder, first-level tables in shared memory.  All 32 lanes run the same chain on
+//                         the same values — an instruction costs one issue slot however many lanes are active — and share what is
+//                         data-parallel: match copies (32 bytes per step) and table fills.  Thousands of members in flight; the
+//                         kernel is bound by issue slots, and with one chain per warp resident warps are what fills them.
 //   bgzf_crc_kernel       one WARP per member: every lane the CRC-32 of 1/32 of the member's payload, the 32 pieces
 //                         combined by multiplication in GF(2)[x] / p(x) (zlib's crc32_combine), compared with the member's
 //                         stored CRC.  htslib fails on a CRC mismatch: so does this.
@@ -46,14 +48,14 @@ __device__ __forceinline__ void report(unsigned long long* status, long long mem
     atomicMin(status, ((unsigned long long)member << 8) | (unsigned long long)code);
 }
 
-// One member per WARP, decoded by its first lane.  Thirty-two members per warp (a lane each) was measured first: the
-// lanes of a warp run different code paths at every symbol (literal, match, refill, table build) and do not reconverge —
-// 32 x serialised, 269 ms for 2348 members.  A lane alone in its warp loses nothing to divergence, and the members in flight
-// per SM are the same (64 warps against 3 x 32 lanes at 72 KB of tables per warp).
+// One member per WARP.  Thirty-two members per warp (a lane each) was measured first: the lanes of a warp run different code
+// paths at every symbol (literal, match, refill, table build) and do not reconverge — 32 x serialised, 269 ms for 2348 members
+// against 10.3 ms with one member per warp (then one lane; now all lanes in step on the same member: 13.9 -> 13.3 ms with the
+// upload, 42.4 -> 40.2 ms for 11 724 members).
 constexpr int INFLATE_WARPS = 8;
 
 
-// MIN_CTAS: 1 = as many registers as the decoder likes (116: 16 warps per SM, the fastest single member); 4 = capped at 64 (32 warps
+// MIN_CTAS: 2 = up to 128 registers (16 warps per SM, the fastest single member); 4 = capped at 64 (32 warps
 // per SM: a file with more members than the SMs hold at 16 warps is bound by issue slots, and every warp is one lane: 51.7 -> 42.0 ms
 // for 11 724 members, 14.0 -> 14.8 ms for 2346)
 template <int MIN_CTAS>
@@ -63,7 +65,8 @@ __global__ void __launch_bounds__(32 * INFLATE_WARPS, MIN_CTAS) bgzf_inflate_ker
     __shared__ __align__(16) uint16_t tables[INFLATE_WARPS][LUT_SIZE + DLUT_SIZE];
     const int w = threadIdx.x >> 5;
     const long long m = m0 + (long long)blockIdx.x * INFLATE_WARPS + w;
-    if (m >= m0 + n_blk || (threadIdx.x & 31) != 0) return;
+    if (m >= m0 + n_blk) return;
+    const int lane = threadIdx.x & 31;
     huff hl, hd;
     uint8_t lens[LENS_SIZE];
     const tc_bgzf_block_t b = blk[m];
@@ -71,8 +74,8 @@ __global__ void __launch_bounds__(32 * INFLATE_WARPS, MIN_CTAS) bgzf_inflate_ker
     uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(tables[w]);
     asm volatile("" : "+r"(lut_s));
     uint16_t* lut = (uint16_t*)__cvta_shared_to_generic((size_t)lut_s);
-    const int rc = inflate_block(file + b.coff, b.csize, payload + b.uoff, b.usize, lut, lut + LUT_SIZE, hl, hd, lens);
-    if (rc) report(status, m, rc);
+    const int rc = inflate_block<32>(file + b.coff, b.csize, payload + b.uoff, b.usize, lut, lut + LUT_SIZE, hl, hd, lens, lane);
+    if (rc && lane == 0) report(status, m, rc);
 }
 
 constexpr int CRC_ERR = 32;
@@ -327,7 +330,7 @@ TC_API int tc_bgzf_inflate(tc_ctx_t* ctx, const uint8_t* file, int64_t file_byte
         const int64_t n = g1 - g0;
         const unsigned grid = (unsigned)((n + INFLATE_WARPS - 1) / INFLATE_WARPS);
         if (n_blocks > (int64_t)ctx->sm_count * 16) bgzf_inflate_kernel<4><<<grid, 32 * INFLATE_WARPS, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
-        else bgzf_inflate_kernel<1><<<grid, 32 * INFLATE_WARPS, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
+        else bgzf_inflate_kernel<2><<<grid, 32 * INFLATE_WARPS, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
         TC_LAUNCH_CHECK();
         bgzf_crc_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, side>>>(d_file, d_blk, g0, n, d_payload, d_status);
         TC_LAUNCH_CHECK();

@@ -20,6 +20,16 @@
 #define TCI_HD static inline
 #endif
 
+// NL lanes of a warp may run one member's decode TOGETHER (NL = 32 on the device, 1 on the host): every lane executes the same
+// instructions on the same values — the decode is one serial chain either way, a warp instruction costs one issue slot whether
+// one lane or all of them are active — and the lanes share what is data-parallel: a match is copied NL bytes per step, a table is
+// filled NL entries per step.  Stores of single bytes are lane 0's.
+#if defined(__CUDA_ARCH__)
+#define TCI_WARP_SYNC() __syncwarp()
+#else
+#define TCI_WARP_SYNC() ((void)0)
+#endif
+
 namespace tcinf {
 
 constexpr int LUT_BITS = 10;
@@ -126,9 +136,11 @@ TCI_HD int huff_build(huff& h, const uint8_t* lengths, int n) {
 
 // first-level table.  LIT: entries of literals (symbols < 256) carry bit 15, so the hot loop tests one bit
 constexpr uint32_t LIT_FLAG = 0x8000u;
-template <int BITS, bool LIT>
-TCI_HD void lut_build(const huff& h, uint16_t* lut) {
-    for (int i = 0; i < (1 << BITS); ++i) lut[i] = 0;
+template <int BITS, bool LIT, int NL>
+TCI_HD void lut_build(const huff& h, uint16_t* lut, int lane) {
+    if (NL > 1) TCI_WARP_SYNC();                                // nobody still reads the previous block's table
+    for (int i = lane; i < (1 << BITS); i += NL) lut[i] = 0;
+    if (NL > 1) TCI_WARP_SYNC();
     uint32_t code = 0;
     int idx = 0;
     for (int l = 1; l <= BITS; ++l) {
@@ -137,10 +149,11 @@ TCI_HD void lut_build(const huff& h, uint16_t* lut) {
             for (int k = 0; k < l; ++k) r |= ((code >> k) & 1u) << (l - 1 - k);
             const uint32_t sym = h.symbol[idx];
             const uint16_t e = (uint16_t)((sym << 4) | (uint32_t)l | ((LIT && sym < 256u) ? LIT_FLAG : 0u));
-            for (uint32_t v = r; v < (1u << BITS); v += 1u << l) lut[v] = e;
+            for (uint32_t v = r + ((uint32_t)lane << l); v < (1u << BITS); v += (uint32_t)NL << l) lut[v] = e;
         }
         code <<= 1;
     }
+    if (NL > 1) TCI_WARP_SYNC();
 }
 
 // bit by bit (puff.c's decode): any code length
@@ -170,8 +183,10 @@ TCI_HD int huff_decode(bits& b, const huff& h, const uint16_t* lut) {
 // `out[0 .. n_out)`, n_out = the member's ISIZE (< 2^31).  `lut` / `dlut`: LUT_SIZE / DLUT_SIZE entries of this thread.
 // `lens`, `hl`, `hd`: per-thread scratch.  Returns INF_OK or the first error; never reads outside the
 // words covering the input, never writes outside `out`.
+template <int NL>
 TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t n_out_, uint16_t* lut, uint16_t* dlut,
-                         huff& hl, huff& hd, uint8_t* lens /* [LENS_SIZE] */) {
+                         huff& hl, huff& hd, uint8_t* lens /* [LENS_SIZE] */, int lane) {
+    const bool writer = NL == 1 || lane == 0;
     if (n_out_ < 0 || n_out_ > 0x7fffffff) return INF_ERR_OUTPUT;
     if (n_in < 0 || n_in >= (1 << 28)) return INF_ERR_INPUT;
     const uint32_t n_out = (uint32_t)n_out_;
@@ -193,7 +208,9 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
             if (len > n_out - o) return INF_ERR_OUTPUT;
             for (uint32_t i = 0; i < len; ++i) {
                 bits_refill(b);
-                out[o++] = (uint8_t)bits_take(b, 8);
+                const uint8_t v8 = (uint8_t)bits_take(b, 8);
+                if (writer) out[o] = v8;
+                ++o;
             }
             if (bits_over(b)) return INF_ERR_INPUT;
         } else if (btype == 1 || btype == 2) {
@@ -245,8 +262,8 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 left = huff_build(hd, lens + 19 + nlen, ndist);
                 if (left < 0 || (left > 0 && !(hd.count[1] == 1 && ndist - hd.count[0] == 1))) return INF_ERR_HEADER;
             }
-            lut_build<LUT_BITS, true>(hl, lut);
-            lut_build<DLUT_BITS, false>(hd, dlut);
+            lut_build<LUT_BITS, true, NL>(hl, lut, lane);
+            lut_build<DLUT_BITS, false, NL>(hd, dlut, lane);
             for (;;) {
                 bits_refill(b);
                 uint32_t e = lut[(uint32_t)b.buf & (uint32_t)(LUT_SIZE - 1)];
@@ -256,7 +273,8 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                     if (n_out - o >= 3u) {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
-                            out[o++] = (uint8_t)(e >> 4);
+                            if (writer) out[o] = (uint8_t)(e >> 4);
+                            ++o;
                             b.buf >>= (e & 15u); b.n -= (int)(e & 15u);
                             if (r == 2) break;
                             e = lut[(uint32_t)b.buf & (uint32_t)(LUT_SIZE - 1)];
@@ -264,7 +282,8 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                         }
                     } else {
                         if (o >= n_out) return INF_ERR_OUTPUT;
-                        out[o++] = (uint8_t)(e >> 4);
+                        if (writer) out[o] = (uint8_t)(e >> 4);
+                        ++o;
                         b.buf >>= (e & 15u); b.n -= (int)(e & 15u);
                     }
                     continue;
@@ -276,7 +295,8 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                     if (sym < 0) return INF_ERR_CODE;
                     if (sym < 256) {
                         if (o >= n_out) return INF_ERR_OUTPUT;
-                        out[o++] = (uint8_t)sym;
+                        if (writer) out[o] = (uint8_t)sym;
+                        ++o;
                         continue;
                     }
                 }
@@ -305,7 +325,19 @@ TCI_HD int inflate_block(const uint8_t* in, int64_t n_in, uint8_t* out, int64_t 
                 // at least 8 bytes back is fetched 8 bytes at a time, loads first, stores after; only short overlapping
                 // periods go byte by byte.  (Measured: 8 + 8 predicated by the length = 45 instructions per match; jumps into
                 // unrolled runs of exactly `len` = fewer instructions and MORE time, the indirect branches stall.)
-                if (dist == 1) {
+                if (NL > 1) {
+                    // all lanes: NL bytes per step.  A source that overlaps its destination (distance < length) repeats with
+                    // the distance as its period, so every byte is read from in front of the match
+                    TCI_WARP_SYNC();                            // what other lanes wrote of this member so far is visible
+                    const uint8_t* src = out + o - dist;
+                    uint8_t* dst = out + o;
+                    if (dist >= (uint32_t)len) {
+                        for (int i = lane; i < len; i += NL) dst[i] = src[i];
+                    } else {
+                        for (int i = lane; i < len; i += NL) dst[i] = src[(uint32_t)i % dist];
+                    }
+                    o += (uint32_t)len;
+                } else if (dist == 1) {
                     const uint8_t v = out[o - 1];
                     for (int i = 0; i < len; ++i) out[o + i] = v;
                     o += len;
