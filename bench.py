@@ -332,6 +332,7 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     sync()
     ms = e0.elapsed_time(e1) / steps
     ar_ms = 0.0
+    ar_iso_ms = 0.0
     if comm is not None:            # the collective alone (the table is summed in place over and over: timing only)
         scratch = out.clone()
         for _ in range(3):
@@ -343,6 +344,15 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
         e1.record()
         sync()
         ar_ms = e0.elapsed_time(e1) / steps
+        ar_iso = []                 # ... and one at a time, every rank idle before it: the latency a pass pays
+        for _ in range(min(steps, 20)):
+            sync()
+            e0.record()
+            ctx.allreduce_counts(scratch, comm, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ar_iso.append(e0.elapsed_time(e1))
+        ar_iso_ms = statistics.median(ar_iso)
         one_pass()                  # `out` again holds the sum of the shards' tables
     t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -351,7 +361,11 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     # ---- the single-GPU table and time (rank 0), and the comparison on every rank
     single = torch.empty_like(out)
     single_ms = ms
-    if world > 1:
+    if world > 1 and os.environ.get("TC_RR_SKIP_SINGLE"):       # diagnostics only (--read-range-only): no single-GPU reference pass
+        bases = float(shard.count_aligned_bases(0x4)) * world
+        alg = float(shard.algorithmic_bytes(L)) * world
+        equal = None
+    elif world > 1:
         if rank == 0:
             whole = synth.generate_reads(w.params, w.ref)
             ctx2 = gpu.Context(local)
@@ -380,7 +394,7 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     block = {
         "workload": w.name, "sharding": "by read range, tc_pileup_counts_allreduce_enqueue / _finish per pass (shard pileup + ncclAllReduce int32 sum in one enqueue, replayed as a CUDA graph, pass i + 1 enqueued before pass i is finished)",
         "scaling": "strong", "n_gpus": world, "reads": n_reads, "reads_per_rank": int(hi - lo), "aligned_bases": bases,
-        "ms_per_pass": ms, "aligned_bases_per_s": bases / (ms * 1e-3), "allreduce_ms": ar_ms, "allreduce_bytes": int(out.numel() * 4),
+        "ms_per_pass": ms, "aligned_bases_per_s": bases / (ms * 1e-3), "allreduce_ms": ar_ms, "allreduce_isolated_ms": ar_iso_ms, "allreduce_bytes": int(out.numel() * 4),
         "single_gpu_ms_per_pass": single_ms, "strong_scaling_efficiency": single_ms / (world * ms),
         "roofline_frac": alg / (ms * 1e-3) / 1e9 / (peak * world), "table_equals_single_gpu": equal,
         "limiter": ("pileup of the shard (%.3f ms) + allreduce of %.2f MB (%.3f ms: latency-bound on NVLink)" %
