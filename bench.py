@@ -361,11 +361,7 @@ def read_range_block(ctx, gpu, torch, dist, rank, world, local, steps, warmup, d
     # ---- the single-GPU table and time (rank 0), and the comparison on every rank
     single = torch.empty_like(out)
     single_ms = ms
-    if world > 1 and os.environ.get("TC_RR_SKIP_SINGLE"):       # diagnostics only (--read-range-only): no single-GPU reference pass
-        bases = float(shard.count_aligned_bases(0x4)) * world
-        alg = float(shard.algorithmic_bytes(L)) * world
-        equal = None
-    elif world > 1:
+    if world > 1:
         if rank == 0:
             whole = synth.generate_reads(w.params, w.ref)
             ctx2 = gpu.Context(local)
